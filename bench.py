@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the RWARE step path (BASELINE.json: env-steps/s on synthetic random-action rollouts).
+
+    python bench.py --gpus 1 --steps 200 --warmup 20              # our CUDA path (default)
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1  # CPU arm: the C oracle port on all host cores
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W                    # one rank per GPU, weak scaling
+
+A "step" is ONE launch of the fused kernel (rw_step) over the whole batch of worlds of a rank: action decode, move
+proposals, collision resolution, apply, deliveries/resample, counters, in-kernel auto-reset and the observation gather.
+Workload (N=1): BASELINE.json configs[1] = rware-tiny-4ag-v1 x 65 536 worlds, actions iid uniform over {0..4}
+(generated on the device beforehand, resident in HBM), episodes of 500 steps with auto-reset.
+Timing: every timed step is bracketed by its own pair of CUDA events on the launching stream; between timed steps the
+L2 is flushed by writing a 512 MiB buffer (the per-step working set, ~83 MB, is smaller than the 126 MB L2).  `value`
+= worlds * steps / sum(step times), max over ranks.  `e2e` goes through the host-buffer C-ABI call (rw_step_host):
+pinned host actions -> device, kernel, observations/rewards/done -> pinned host, inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name -> (env id, overrides, worlds per GPU)
+    "tiny-4ag": ("rware-tiny-4ag-v1", {}, 65536),
+    "tiny-2ag": ("rware-tiny-2ag-v1", {}, 65536),
+    "small-4ag": ("rware-small-4ag-v1", {}, 32768),
+    "medium-8ag-hard": ("rware-medium-8ag-hard-v1", {}, 32768),
+    "large-16ag-r2": ("rware-large-16ag-v1", {"sensor_range": 2}, 16384),
+}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_baseline(env_id, overrides, target_seconds=10.0, threads=None):
+    """The oracle port (plain C, oracle/) on the host cores, random-action rollout of the same configuration."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py
+    import rware_b200
+    kw = rware_b200.env_kwargs(env_id, **overrides)
+    (H, W), highways, goals = rware_b200.layout_from_params(kw["shelf_columns"], kw["shelf_rows"], kw["column_height"])
+    env = oracle_py.OracleEnv(highways, goals, kw["n_agents"], kw["msg_bits"], kw["sensor_range"], kw["request_queue_size"],
+                              kw["max_inactivity_steps"], kw["max_steps"], kw["reward_type"].value)
+    threads = threads or os.cpu_count() or 1
+    n_envs = threads * 8
+    t0 = time.perf_counter()
+    done, _ = oracle_py.rollout_random(env, n_envs, 200, seed=1, n_threads=threads)  # calibration
+    rate = done / (time.perf_counter() - t0)
+    steps = max(200, int(rate * target_seconds / n_envs))
+    t0 = time.perf_counter()
+    done, _ = oracle_py.rollout_random(env, n_envs, steps, seed=2, n_threads=threads)
+    dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": "env-steps/s", "cores": threads, "kind": "port",
+            "sample": f"{n_envs} worlds x {steps} random-action steps of {env_id} {overrides or ''} with reset on done, "
+                      f"{dt:.1f} s on {threads} host threads (C oracle port; the Python reference itself cannot travel to the GPU box)",
+            "seconds": dt}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    env_id, overrides, E = WORKLOADS[args.workload]
+    vals = []
+    for i in range(args.warmup + args.steps):
+        cb = cpu_baseline(env_id, overrides, target_seconds=args.ref_seconds)
+        if i >= args.warmup:
+            vals.append(cb)
+    v = sum(c["value"] for c in vals) / len(vals)
+    cb = dict(vals[-1])
+    cb["value"] = v
+    secs = sum(c["seconds"] for c in vals) / len(vals)
+    print(json.dumps({
+        "impl": "reference", "metric": "env-steps/s", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * secs, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": f"{env_id} {overrides or ''} random-action rollout, CPU (a step = one bounded sample, see cpu_baseline.sample)"},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="tiny-4ag", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs", type=int, default=None, help="worlds per GPU (default: the workload's)")
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--ref-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", action="store_true", help="all-gather obs/reward/done across ranks every step (NCCL)")
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps (diagnostic)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    import rware_b200
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    env_id, overrides, E = WORKLOADS[args.workload]
+    E = args.envs or E
+    vec = rware_b200.make_vec(env_id, E, auto_reset=True, device=dev, **overrides)
+    n, L, A = vec.n_agents, vec.obs_len, 1 + vec.msg_bits
+    info = vec.info
+    vec.reset(seed=rank * E)  # world e of rank r is seeded with r*E + e: results do not depend on the sharding
+
+    # synthetic input: a ring of pre-generated uniform action tensors, resident in HBM
+    RING = 16
+    actions = [torch.empty((E, n, A), dtype=torch.int32, device=dev) for _ in range(RING)]
+    for i, a in enumerate(actions):
+        vec.backend.random_actions(a, 12345 + rank, i)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    gathered = None
+    if args.gather and world > 1:
+        gathered = (torch.empty((world * E, n, L), dtype=torch.float32, device=dev),
+                    torch.empty((world * E, n), dtype=torch.float32, device=dev),
+                    torch.empty((world * E,), dtype=torch.uint8, device=dev))
+
+    def one_step(i):
+        obs, rew, done = vec.step(actions[i % RING])
+        if gathered is not None:
+            dist.all_gather_into_tensor(gathered[0], obs)
+            dist.all_gather_into_tensor(gathered[1], rew)
+            dist.all_gather_into_tensor(gathered[2], done)
+
+    for i in range(max(3, args.warmup)):
+        one_step(i)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        if not args.no_flush:
+            flush.fill_(i & 0xff)
+        starts[i].record()
+        one_step(args.warmup + i)
+        stops[i].record()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
+    total_ms = float(sum(step_ms))
+
+    # back-to-back (warm L2, no flush) for reference, one event pair around K launches
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for i in range(args.steps):
+        one_step(i)
+    s1.record()
+    torch.cuda.synchronize()
+    warm_ms = s0.elapsed_time(s1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end to end through the host-buffer C-ABI entry point
+    e2e_steps = args.e2e_steps
+    h_act = torch.empty((E, n, A), dtype=torch.int32).pin_memory()
+    h_act.copy_(actions[0].cpu())
+    h_obs = torch.empty((E, n, L), dtype=torch.float32).pin_memory()
+    h_rew = torch.empty((E, n), dtype=torch.float32).pin_memory()
+    h_done = torch.empty((E,), dtype=torch.uint8).pin_memory()
+    for _ in range(3):
+        vec.backend.step_host(h_act, h_obs, h_rew, h_done)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        vec.backend.step_host(h_act, h_obs, h_rew, h_done)  # synchronises internally
+    e2e_s = time.perf_counter() - t0
+
+    tot = torch.tensor([total_ms, warm_ms, e2e_s], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    total_ms, warm_ms, e2e_s = (float(x) for x in tot.tolist())
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = load_peaks()
+    kernel_ms = total_ms / args.steps  # per-GPU: one launch per step (max over ranks of the sums)
+    b_step = int(info["algorithmic_bytes_step"])
+    b_packed = int(info["packed_bytes_step"])
+    achieved = b_step * E / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "ncu_step_traffic.json")
+    if os.path.exists(prof) and args.workload == "tiny-4ag" and E == 65536:
+        with open(prof) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    cb = None
+    if not args.no_cpu_baseline:
+        cb = cpu_baseline(env_id, overrides, target_seconds=12.0)
+        cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    out = {
+        "metric": "env-steps/s", "value": world * E * args.steps / (total_ms * 1e-3), "unit": "env-steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": kernel_ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32 (state) / float32 (obs)",
+        "data": "synthetic",
+        "config": {"workload": f"{env_id} {overrides or ''}".strip() + f", {E} worlds per GPU, random-action rollout, auto-reset",
+                   "worlds_per_gpu": E, "n_agents": n, "obs_len": L, "parallelism": f"dp{world} (independent worlds, no exchange"
+                   + (", obs/reward/done all-gathered" if gathered is not None else "") + ")",
+                   "l2": "flushed between timed steps (512 MiB write)" if not args.no_flush else "not flushed",
+                   "timing": "per-step CUDA event pairs on the launch stream, summed; max over ranks"},
+        "agent_steps_per_s": world * E * n * args.steps / (total_ms * 1e-3),
+        "value_warm_l2": world * E * args.steps / (warm_ms * 1e-3),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "rw_main_kernel<STEP>",
+                     "algorithmic_bytes_per_env_step": b_step, "layout_bytes_per_env_step": b_packed,
+                     "achieved_layout_bytes": b_packed * E / (kernel_ms * 1e-3) / 1e9,
+                     "kernel_us": kernel_ms * 1e3},
+        "e2e": {"value": world * E * e2e_steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": E * n * A * 4,
+                "d2h_bytes_per_step": E * n * L * 4 + E * n * 4 + E, "steps": e2e_steps,
+                "api": "rw_step_host (pinned host buffers, copies + kernel + sync inside the timed region)"},
+        "gpu_launches": args.steps,
+        "clocks": clocks,
+        "wall_s_timed_region": t_wall,
+    }
+    if cb:
+        out["cpu_baseline"] = cb
+    print(json.dumps(out))
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

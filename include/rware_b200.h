@@ -1,0 +1,141 @@
+/* rware_b200.h -- C ABI of the B200-native batched RWARE step path.
+ *
+ * This is the drop-in boundary.  In the reference the step path sits behind the Gymnasium `Env` protocol
+ * of `rware.warehouse:Warehouse` (registered at rware/__init__.py:24-39).  The reference has no native
+ * code and no FFI; the binding a maintainer adds is a ctypes stub that makes
+ * `Warehouse.reset/step/_make_obs` forward to the entry points below.  Each entry point names the
+ * reference interface it replaces (file:line in /root/reference/rware/warehouse.py unless noted).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative RW_E* code; rw_last_error() gives text;
+ *   - no exceptions, no torch types, plain pointers and sizes only;
+ *   - all device entry points are stream-ordered and asynchronous on `stream` (a cudaStream_t passed as
+ *     void*, NULL = the legacy default stream); the *_host entry points synchronise before returning;
+ *   - the caller owns every I/O buffer; the library owns the world state (a packed struct-of-arrays in HBM);
+ *   - one handle is bound to one GPU; a handle is not thread-safe, different handles are independent;
+ *   - `E` = num_envs, `n` = n_agents, `L` = rw_info.obs_len, `S` = rw_info.n_shelves,
+ *     `R` = request_queue_size, `A` = 1 + msg_bits (ints per agent action).
+ */
+#ifndef RWARE_B200_H
+#define RWARE_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RW_ABI_VERSION 1
+
+enum {
+    RW_OK = 0,
+    RW_EINVAL = -1,   /* bad argument / unsupported configuration */
+    RW_ECUDA = -2,    /* a CUDA runtime call failed */
+    RW_ENOMEM = -3,
+    RW_ESTATE = -4    /* handle used in the wrong state (e.g. step before reset) */
+};
+
+/* Action / Direction / RewardType values are the reference's (warehouse.py:31-36, 39-43, 46-49). */
+enum { RW_NOOP = 0, RW_FORWARD = 1, RW_LEFT = 2, RW_RIGHT = 3, RW_TOGGLE_LOAD = 4 };
+enum { RW_UP = 0, RW_DOWN = 1, RW_DIR_LEFT = 2, RW_DIR_RIGHT = 3 };
+enum { RW_REWARD_GLOBAL = 0, RW_REWARD_INDIVIDUAL = 1, RW_REWARD_TWO_STAGE = 2 };
+
+/* Constructor kwargs of Warehouse.__init__ (warehouse.py:146-170) after layout construction
+ * (warehouse.py:294-350, done by the host-side facade): all pointers are HOST pointers, copied by rw_create. */
+typedef struct rw_config {
+    int32_t abi_version;          /* RW_ABI_VERSION */
+    int32_t grid_h, grid_w;       /* grid_size, warehouse.py:297-300 / 337 */
+    int32_t n_agents;             /* 1..32 */
+    int32_t msg_bits;             /* 0..16 */
+    int32_t sensor_range;         /* >= 1 */
+    int32_t request_queue_size;   /* 1..n_shelves */
+    int32_t max_inactivity_steps; /* 0 == None */
+    int32_t max_steps;            /* 0 == None */
+    int32_t reward_type;          /* RW_REWARD_* */
+    int32_t normalised_coordinates;
+    int32_t n_goals;              /* 1..16 */
+    const uint8_t *highways;      /* [grid_h*grid_w], row-major [y][x], 1 = highway (warehouse.py:308-326) */
+    const int32_t *goals_xy;      /* [n_goals][2] = (x, y) in the reference's order (warehouse.py:303-306, 344-345) */
+} rw_config;
+
+typedef struct rw_info {
+    int64_t num_envs;
+    int32_t n_agents, n_shelves, obs_len, act_width; /* act_width = 1 + msg_bits */
+    int32_t request_queue_size, grid_h, grid_w, device;
+    int32_t state_words_per_env;  /* packed int32 words per world in the HBM tile layout */
+    int32_t envs_per_tile;        /* 32 */
+    int32_t smem_bytes_per_warp, warps_per_cta;
+    int64_t algorithmic_bytes_step; /* SURVEY.md section 8(d) B_step for this config */
+    int64_t algorithmic_bytes_obs;  /* SURVEY.md section 8(d) B_obs */
+    int64_t packed_bytes_step;      /* bytes this layout really moves per env-step (obs+2*state+act+rew+done) */
+    int64_t packed_bytes_obs;
+} rw_info;
+
+/* Plain-array view of the world state: what the reference keeps in env.agents[i].{x,y,dir,carrying_shelf,
+ * has_delivered,message}, env.shelfs[j].{x,y}, env.request_queue, env._cur_steps, env._cur_inactive_steps and
+ * env.np_random (warehouse.py:82-93, 128-133, 249-250, 262-265).  All DEVICE pointers, int32 unless noted;
+ * NULL members are skipped.  Shelf ids are 1-based (row-major rank of the home cell, warehouse.py:771-778);
+ * carry == 0 means "not carrying". */
+typedef struct rw_state_view {
+    int32_t *agent_x, *agent_y, *agent_dir, *agent_carry, *agent_has_delivered; /* [E][n] */
+    int32_t *agent_msg;   /* [E][n][msg_bits] */
+    int32_t *shelf_x, *shelf_y; /* [E][S] */
+    int32_t *queue;       /* [E][R] shelf ids */
+    int32_t *cur_steps, *cur_inactive; /* [E] */
+    uint32_t *rng;        /* [E][10]: numpy PCG64 state: state[4] lo..hi, inc[4], has_uint32, uinteger */
+} rw_state_view;
+
+typedef struct rw_handle rw_handle;
+
+/* Warehouse.__init__ (warehouse.py:146-292) for `num_envs` independent worlds on CUDA device `device`. */
+int rw_create(const rw_config *cfg, int64_t num_envs, int device, rw_handle **out);
+int rw_destroy(rw_handle *h);
+int rw_get_info(const rw_handle *h, rw_info *out);
+const char *rw_last_error(const rw_handle *h); /* h may be NULL: error of the last failed rw_create */
+
+/* Warehouse.seed(seed) / reset(seed=...) re-seeding (warehouse.py:962-964, 758-760): world e gets
+ * Generator(PCG64(SeedSequence(seeds_host[e]))).  seeds_host: HOST [E].  mask_host: HOST [E] or NULL (all). */
+int rw_seed(rw_handle *h, const uint64_t *seeds_host, const uint8_t *mask_host, void *stream);
+
+/* Warehouse.reset() (warehouse.py:757-802) for the worlds with mask_dev[e] != 0 (NULL = all), continuing each
+ * world's generator stream (call rw_seed first for reset(seed=...)).  obs_dev: [E][n][L] float32 or NULL;
+ * all worlds' observations are (re)written. */
+int rw_reset(rw_handle *h, const uint8_t *mask_dev, float *obs_dev, void *stream);
+
+/* Warehouse.step(actions) (warehouse.py:804-946): one fused kernel.  actions_dev [E][n][A] int32;
+ * obs_dev [E][n][L] float32 (may be NULL: skip the observation gather); reward_dev [E][n] float32;
+ * done_dev [E] uint8 (`terminated`; `truncated` is always False, warehouse.py:942). */
+int rw_step(rw_handle *h, const int32_t *actions_dev, float *obs_dev, float *reward_dev, uint8_t *done_dev,
+            void *stream);
+
+/* tuple(_make_obs(agent) for agent in agents) (warehouse.py:722-744 -> 598-674): the observation gather alone. */
+int rw_obs(rw_handle *h, float *obs_dev, void *stream);
+
+/* When on, a world whose step returned done is reset inside the same kernel (as `reset()` without a seed would,
+ * continuing its generator) and the returned observation is the first one of the new episode.  Default off
+ * (the reference never auto-resets). */
+int rw_set_auto_reset(rw_handle *h, int enabled);
+
+/* State injection / extraction: what the reference's tests do through env.agents[i].x = ..., env._recalc_grid()
+ * (tests/test_movement.py:14-47).  Also the checkpoint/restore hook. */
+int rw_get_state(rw_handle *h, const rw_state_view *dev, void *stream);
+int rw_set_state(rw_handle *h, const rw_state_view *dev, void *stream);
+
+/* Count of invalid action values seen so far (the reference raises ValueError from Action(a), warehouse.py:811-814;
+ * the batched kernel treats them as NOOP and counts them).  Synchronises `stream`. */
+int rw_error_count(rw_handle *h, int64_t *out, void *stream);
+
+/* End-to-end convenience with HOST buffers (pinned memory recommended, see rw_host_alloc): copies the actions
+ * to the device, runs rw_step, copies obs/reward/done back and synchronises.  Any output pointer may be NULL. */
+int rw_step_host(rw_handle *h, const int32_t *actions_host, float *obs_host, float *reward_host, uint8_t *done_host);
+int rw_reset_host(rw_handle *h, const uint64_t *seeds_host, float *obs_host);
+int rw_host_alloc(void **out, int64_t bytes); /* cudaHostAlloc */
+int rw_host_free(void *p);
+
+/* Synthetic-rollout helper for benchmarks: fills actions_dev [E][n][A] with iid uniform actions over {0..4}
+ * (message bits uniform over {0,1}) from a counter-based generator keyed by (seed, step). */
+int rw_random_actions(rw_handle *h, int32_t *actions_dev, uint64_t seed, uint64_t step, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,212 @@
+"""ctypes binding of the C ABI (include/rware_b200.h) -> librware_b200.so, and the CUDA backend object the
+Python facade drives.  PyTorch supplies device memory and streams; all compute is in the library's own kernels.
+
+There is no CPU fallback: if the library is missing or CUDA is unavailable, construction raises.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import torch
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "lib", "librware_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_PKG_DIR), "include", "rware_b200.h")
+RW_ABI_VERSION = 1
+RNG_WORDS = 10
+
+
+class RwConfig(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int32) for k in (
+        "abi_version", "grid_h", "grid_w", "n_agents", "msg_bits", "sensor_range", "request_queue_size",
+        "max_inactivity_steps", "max_steps", "reward_type", "normalised_coordinates", "n_goals")] + [
+        ("highways", ctypes.c_void_p), ("goals_xy", ctypes.c_void_p)]
+
+
+class RwInfo(ctypes.Structure):
+    _fields_ = [("num_envs", ctypes.c_int64)] + [(k, ctypes.c_int32) for k in (
+        "n_agents", "n_shelves", "obs_len", "act_width", "request_queue_size", "grid_h", "grid_w", "device",
+        "state_words_per_env", "envs_per_tile", "smem_bytes_per_warp", "warps_per_cta")] + [
+        (k, ctypes.c_int64) for k in ("algorithmic_bytes_step", "algorithmic_bytes_obs", "packed_bytes_step",
+                                      "packed_bytes_obs")]
+
+
+STATE_FIELDS = ("agent_x", "agent_y", "agent_dir", "agent_carry", "agent_has_delivered", "agent_msg", "shelf_x",
+                "shelf_y", "queue", "cur_steps", "cur_inactive", "rng")
+
+
+class RwStateView(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_void_p) for k in STATE_FIELDS]
+
+
+def build_library(force=False, verbose=False):
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> lib/librware_b200.so (in-tree, travels with the repo)."""
+    srcs = [os.path.join(_PKG_DIR, "csrc", f) for f in os.listdir(os.path.join(_PKG_DIR, "csrc"))] + [HEADER_PATH]
+    if (not force and os.path.exists(LIB_PATH)
+            and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(s) for s in srcs)):
+        return LIB_PATH
+    res = subprocess.run([os.path.join(_PKG_DIR, "build.sh")], capture_output=True, text=True)
+    if verbose or res.returncode:
+        print(res.stdout + res.stderr)
+    if res.returncode:
+        raise RuntimeError("building librware_b200.so failed")
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load_library():
+    """Loads librware_b200.so (raises if it is missing: there is no fallback path)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()' "
+            f"or robotic-warehouse_b200/build.sh).  rware_b200 has no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i64, u64, ci = ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int
+    L.rw_create.argtypes = [ctypes.POINTER(RwConfig), i64, ci, ctypes.POINTER(vp)]
+    L.rw_destroy.argtypes = [vp]
+    L.rw_get_info.argtypes = [vp, ctypes.POINTER(RwInfo)]
+    L.rw_last_error.argtypes = [vp]
+    L.rw_last_error.restype = ctypes.c_char_p
+    L.rw_seed.argtypes = [vp, vp, vp, vp]
+    L.rw_reset.argtypes = [vp, vp, vp, vp]
+    L.rw_step.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.rw_obs.argtypes = [vp, vp, vp]
+    L.rw_set_auto_reset.argtypes = [vp, ci]
+    L.rw_get_state.argtypes = [vp, ctypes.POINTER(RwStateView), vp]
+    L.rw_set_state.argtypes = [vp, ctypes.POINTER(RwStateView), vp]
+    L.rw_error_count.argtypes = [vp, ctypes.POINTER(i64), vp]
+    L.rw_step_host.argtypes = [vp, vp, vp, vp, vp]
+    L.rw_reset_host.argtypes = [vp, vp, vp]
+    L.rw_host_alloc.argtypes = [ctypes.POINTER(vp), i64]
+    L.rw_host_free.argtypes = [vp]
+    L.rw_random_actions.argtypes = [vp, vp, u64, u64, vp]
+    for name in ("rw_create", "rw_destroy", "rw_get_info", "rw_seed", "rw_reset", "rw_step", "rw_obs", "rw_set_auto_reset",
+                 "rw_get_state", "rw_set_state", "rw_error_count", "rw_step_host", "rw_reset_host", "rw_host_alloc",
+                 "rw_host_free", "rw_random_actions"):
+        getattr(L, name).restype = ci
+    _lib = L
+    return L
+
+
+class EnvConfig:
+    """Constructor kwargs of the reference's Warehouse (rware/warehouse.py:146-170) after layout construction."""
+
+    def __init__(self, highways, goals, n_agents, msg_bits=0, sensor_range=1, request_queue_size=1,
+                 max_inactivity_steps=None, max_steps=None, reward_type=1, normalised_coordinates=False):
+        self.highways = np.ascontiguousarray(highways, dtype=np.uint8)
+        self.grid_size = tuple(int(v) for v in self.highways.shape)
+        self.goals = [(int(x), int(y)) for x, y in goals]
+        self.n_agents = int(n_agents)
+        self.msg_bits = int(msg_bits)
+        self.sensor_range = int(sensor_range)
+        self.request_queue_size = int(request_queue_size)
+        self.max_inactivity_steps = max_inactivity_steps
+        self.max_steps = max_steps
+        self.reward_type = int(getattr(reward_type, "value", reward_type))
+        self.normalised_coordinates = bool(normalised_coordinates)
+        self.n_shelves = int((self.highways == 0).sum())
+        self.obs_len = 8 + (2 * self.sensor_range + 1) ** 2 * (7 + self.msg_bits)  # rware/warehouse.py:432-443
+
+    def to_struct(self):
+        self._goals_arr = np.ascontiguousarray(np.asarray(self.goals, np.int32).reshape(-1, 2))
+        H, W = self.grid_size
+        return RwConfig(RW_ABI_VERSION, H, W, self.n_agents, self.msg_bits, self.sensor_range, self.request_queue_size,
+                        int(self.max_inactivity_steps or 0), int(self.max_steps or 0), self.reward_type,
+                        int(self.normalised_coordinates), len(self.goals), self.highways.ctypes.data,
+                        self._goals_arr.ctypes.data)
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class CudaBackend:
+    """One rw_handle on one GPU.  All tensors passed in must live on `self.device` and be contiguous."""
+
+    def __init__(self, cfg: EnvConfig, num_envs: int, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("rware_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = load_library()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else torch.device(device).index or 0)
+        self.cfg = cfg
+        self.num_envs = int(num_envs)
+        self._struct = cfg.to_struct()
+        h = ctypes.c_void_p()
+        rc = self.lib.rw_create(ctypes.byref(self._struct), self.num_envs, self.device.index, ctypes.byref(h))
+        if rc:
+            raise RuntimeError(f"rw_create failed ({rc}): {self.lib.rw_last_error(None).decode()}")
+        self._h = h
+        info = RwInfo()
+        self._check(self.lib.rw_get_info(self._h, ctypes.byref(info)))
+        self.info = {k: getattr(info, k) for k, _ in RwInfo._fields_}
+
+    def _check(self, rc):
+        if rc:
+            raise RuntimeError(f"rware_b200 C-ABI call failed ({rc}): {self.lib.rw_last_error(self._h).decode()}")
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.rw_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def seed(self, seeds, mask=None):
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+        assert seeds.shape == (self.num_envs,)
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        self._check(self.lib.rw_seed(self._h, seeds.ctypes.data, None if m is None else m.ctypes.data, self._stream()))
+
+    def reset(self, mask, obs):
+        self._check(self.lib.rw_reset(self._h, _ptr(mask), _ptr(obs), self._stream()))
+
+    def step(self, actions, obs, reward, done):
+        self._check(self.lib.rw_step(self._h, _ptr(actions), _ptr(obs), _ptr(reward), _ptr(done), self._stream()))
+
+    def obs(self, obs):
+        self._check(self.lib.rw_obs(self._h, _ptr(obs), self._stream()))
+
+    def set_auto_reset(self, on):
+        self._check(self.lib.rw_set_auto_reset(self._h, int(bool(on))))
+
+    def _view(self, tensors):
+        v = RwStateView()
+        for k in STATE_FIELDS:
+            t = tensors.get(k)
+            setattr(v, k, None if t is None else t.data_ptr())
+        return v
+
+    def get_state(self, tensors):
+        self._check(self.lib.rw_get_state(self._h, ctypes.byref(self._view(tensors)), self._stream()))
+
+    def set_state(self, tensors):
+        self._check(self.lib.rw_set_state(self._h, ctypes.byref(self._view(tensors)), self._stream()))
+
+    def error_count(self):
+        out = ctypes.c_int64()
+        self._check(self.lib.rw_error_count(self._h, ctypes.byref(out), self._stream()))
+        return out.value
+
+    def random_actions(self, actions, seed, step):
+        self._check(self.lib.rw_random_actions(self._h, _ptr(actions), int(seed), int(step), self._stream()))
+
+    # end-to-end entry points with host (pinned) buffers
+    def step_host(self, actions, obs, reward, done):
+        self._check(self.lib.rw_step_host(self._h, _ptr(actions), _ptr(obs), _ptr(reward), _ptr(done)))
+
+    def reset_host(self, seeds, obs):
+        s = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint64)
+        self._check(self.lib.rw_reset_host(self._h, None if s is None else s.ctypes.data, _ptr(obs)))

@@ -1,0 +1,338 @@
+// rw_capi.cu -- host side of the C ABI declared in include/rware_b200.h.
+//
+// Owns the packed world state in HBM, the static per-configuration tables, the shared-memory carve-up of the
+// fused kernel, and the numpy-compatible seeding (SeedSequence -> PCG64) that makes reset(seed=k) reproduce the
+// reference's generator stream (rware/warehouse.py:758-760, 962-964; numpy/random/bit_generator.pyx).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rware_b200.h"
+#include "rw_launch.h"
+#include "rw_host_layout.h"
+
+struct rw_handle {
+    RwParams p;
+    rw_config cfg;
+    int device;
+    bool ready;  // worlds hold a valid state (after rw_reset / rw_set_state)
+    std::string err;
+    void *d_highway = nullptr, *d_home = nullptr, *d_normx = nullptr, *d_normy = nullptr;
+    void *d_state = nullptr, *d_rng = nullptr, *d_err = nullptr;
+    // staging for the *_host entry points
+    int32_t *d_actions = nullptr;
+    float *d_obs = nullptr, *d_reward = nullptr;
+    uint8_t *d_done = nullptr;
+    cudaStream_t host_stream = nullptr;
+    rw_info info;
+};
+
+static thread_local std::string g_create_error;
+
+static int fail(rw_handle *h, int code, const std::string &msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess)                                                                        \
+            return fail(h, RW_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));             \
+    } while (0)
+
+static int create_impl(rw_handle *h, const rw_config *cfg, int64_t num_envs, int device, const std::vector<uint16_t> &home);
+
+extern "C" {
+
+const char *rw_last_error(const rw_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int rw_create(const rw_config *cfg, int64_t num_envs, int device, rw_handle **out) {
+    rw_handle *h = nullptr;
+    if (!cfg || !out) return fail(h, RW_EINVAL, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != RW_ABI_VERSION) return fail(h, RW_EINVAL, "rw_config.abi_version mismatch");
+    if (num_envs < 1 || num_envs > (1LL << 31)) return fail(h, RW_EINVAL, "num_envs out of range");
+    if (cfg->grid_h < 1 || cfg->grid_w < 1 || cfg->grid_h > 255 || cfg->grid_w > 255)
+        return fail(h, RW_EINVAL, "grid must be within 255x255");
+    if (cfg->n_agents < 1 || cfg->n_agents > RW_MAX_AGENTS) return fail(h, RW_EINVAL, "n_agents must be 1..32");
+    if (cfg->msg_bits < 0 || cfg->msg_bits > RW_MAX_MSG_BITS) return fail(h, RW_EINVAL, "msg_bits must be 0..16");
+    if (cfg->sensor_range < 0 || cfg->sensor_range > 8) return fail(h, RW_EINVAL, "sensor_range must be 0..8");
+    if (cfg->n_goals < 1 || cfg->n_goals > RW_MAX_GOALS) return fail(h, RW_EINVAL, "n_goals must be 1..16");
+    if (!cfg->highways || !cfg->goals_xy) return fail(h, RW_EINVAL, "highways/goals_xy missing");
+    if (cfg->reward_type < 0 || cfg->reward_type > 2) return fail(h, RW_EINVAL, "bad reward_type");
+    const int H = cfg->grid_h, W = cfg->grid_w, cells = H * W, n = cfg->n_agents;
+    if (n > cells) return fail(h, RW_EINVAL, "more agents than cells");
+    std::vector<uint16_t> home;
+    for (int c = 0; c < cells; c++)
+        if (!cfg->highways[c]) home.push_back((uint16_t)c);
+    const int S = (int)home.size();
+    if (S > RW_MAX_SHELVES) return fail(h, RW_EINVAL, "too many shelves");
+    if (cfg->request_queue_size < 0 || cfg->request_queue_size > S)
+        return fail(h, RW_EINVAL, "request_queue_size must be 0..n_shelves");
+    for (int g = 0; g < cfg->n_goals; g++) {
+        int gx = cfg->goals_xy[2 * g], gy = cfg->goals_xy[2 * g + 1];
+        if (gx < 0 || gy < 0 || gx >= W || gy >= H) return fail(h, RW_EINVAL, "goal outside the grid");
+    }
+
+    h = new rw_handle();
+    int rc = create_impl(h, cfg, num_envs, device, home);
+    if (rc != RW_OK) {
+        g_create_error = h->err;
+        rw_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return RW_OK;
+}
+
+}  // extern "C"
+
+static int create_impl(rw_handle *h, const rw_config *cfg, int64_t num_envs, int device, const std::vector<uint16_t> &home) {
+    const int H = cfg->grid_h, W = cfg->grid_w, cells = H * W, n = cfg->n_agents;
+    const int S = (int)home.size();
+    h->cfg = *cfg;
+    h->cfg.highways = nullptr;
+    h->cfg.goals_xy = nullptr;
+    h->device = device;
+    h->ready = false;
+    RwParams &p = h->p;
+    rw_fill_params(p, *cfg, num_envs, S);
+
+    cudaDeviceProp prop;
+    CK(cudaSetDevice(device));
+    CK(cudaGetDeviceProperties(&prop, device));
+    const int smem_cap = (int)prop.sharedMemPerBlockOptin;
+    if (p.sm_warp_bytes > smem_cap)
+        return fail(h, RW_EINVAL, "configuration needs " + std::to_string(p.sm_warp_bytes) +
+                                      " B of shared memory per warp, device allows " + std::to_string(smem_cap));
+    {   // warps per CTA: keep CTAs small so that several fit per SM; env var override for tuning
+        int per_sm = (int)prop.sharedMemPerMultiprocessor / (p.sm_warp_bytes + 1024);
+        if (per_sm < 1) per_sm = 1;
+        int wpc = per_sm >= 8 ? 4 : (per_sm >= 4 ? 2 : 1);
+        const char *ev = getenv("RWARE_B200_WARPS_PER_CTA");
+        if (ev) wpc = atoi(ev);
+        if (wpc < 1) wpc = 1;
+        if (wpc > 8) wpc = 8;
+        while (wpc > 1 && wpc * p.sm_warp_bytes > smem_cap) wpc--;
+        p.warps_per_cta = wpc;
+    }
+    CK(rw_configure_kernels(p.sm_warp_bytes * p.warps_per_cta));
+
+    // static tables
+    std::vector<float> nx(W), ny(H);
+    for (int x = 0; x < W; x++) nx[x] = W > 1 ? (float)((double)x / (double)(W - 1)) : 0.0f;
+    for (int y = 0; y < H; y++) ny[y] = H > 1 ? (float)((double)y / (double)(H - 1)) : 0.0f;
+    CK(cudaMalloc(&h->d_highway, cells));
+    CK(cudaMemcpy(h->d_highway, cfg->highways, cells, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&h->d_home, sizeof(uint16_t) * (S > 0 ? S : 1)));
+    if (S) CK(cudaMemcpy(h->d_home, home.data(), sizeof(uint16_t) * S, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&h->d_normx, sizeof(float) * W));
+    CK(cudaMalloc(&h->d_normy, sizeof(float) * H));
+    CK(cudaMemcpy(h->d_normx, nx.data(), sizeof(float) * W, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_normy, ny.data(), sizeof(float) * H, cudaMemcpyHostToDevice));
+    size_t state_bytes = (size_t)p.tiles * p.nw * RW_TILE * 4;
+    CK(cudaMalloc(&h->d_state, state_bytes));
+    CK(cudaMemset(h->d_state, 0, state_bytes));
+    CK(cudaMalloc(&h->d_rng, (size_t)RW_RNG_WORDS * p.E_pad * 4));
+    CK(cudaMemset(h->d_rng, 0, (size_t)RW_RNG_WORDS * p.E_pad * 4));
+    CK(cudaMalloc(&h->d_err, 8));
+    CK(cudaMemset(h->d_err, 0, 8));
+    p.highway = (const uint8_t *)h->d_highway;
+    p.home_cell = (const uint16_t *)h->d_home;
+    p.normx = (const float *)h->d_normx;
+    p.normy = (const float *)h->d_normy;
+    p.state = (int32_t *)h->d_state;
+    p.rng = (uint32_t *)h->d_rng;
+    p.err_count = (unsigned long long *)h->d_err;
+
+    rw_info &inf = h->info;
+    memset(&inf, 0, sizeof(inf));
+    inf.num_envs = num_envs; inf.n_agents = n; inf.n_shelves = S; inf.obs_len = p.L; inf.act_width = p.A;
+    inf.request_queue_size = p.R; inf.grid_h = H; inf.grid_w = W; inf.device = device;
+    inf.state_words_per_env = p.nw; inf.envs_per_tile = RW_TILE;
+    inf.smem_bytes_per_warp = p.sm_warp_bytes; inf.warps_per_cta = p.warps_per_cta;
+    // S_state = 4*(5n + S + R + 2) + 16; B_step = n*L*4 + 2*S_state + (4n + 4n + 1); B_obs = n*L*4 + S_state
+    int64_t s_state = 4LL * (5 * n + S + p.R + 2) + 16;
+    inf.algorithmic_bytes_step = (int64_t)n * p.L * 4 + 2 * s_state + (8LL * n + 1);
+    inf.algorithmic_bytes_obs = (int64_t)n * p.L * 4 + s_state;
+    inf.packed_bytes_step = (int64_t)n * p.L * 4 + 2LL * p.nw * 4 + (4LL * n * p.A + 4LL * n + 1);
+    inf.packed_bytes_obs = (int64_t)n * p.L * 4 + (int64_t)p.nw * 4;
+    return RW_OK;
+}
+
+extern "C" {
+
+int rw_destroy(rw_handle *h) {
+    if (!h) return RW_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_highway); cudaFree(h->d_home); cudaFree(h->d_normx); cudaFree(h->d_normy);
+    cudaFree(h->d_state); cudaFree(h->d_rng); cudaFree(h->d_err);
+    cudaFree(h->d_actions); cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_done);
+    if (h->host_stream) cudaStreamDestroy(h->host_stream);
+    delete h;
+    return RW_OK;
+}
+
+int rw_get_info(const rw_handle *h, rw_info *out) {
+    if (!h || !out) return RW_EINVAL;
+    *out = h->info;
+    return RW_OK;
+}
+
+int rw_set_auto_reset(rw_handle *h, int enabled) {
+    if (!h) return RW_EINVAL;
+    h->p.auto_reset = enabled ? 1 : 0;
+    return RW_OK;
+}
+
+int rw_seed(rw_handle *h, const uint64_t *seeds_host, const uint8_t *mask_host, void *stream) {
+    if (!h || !seeds_host) return fail(h, RW_EINVAL, "rw_seed: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->device));
+    const int64_t E = h->p.E;
+    std::vector<uint32_t> staging((size_t)RW_RNG_WORDS * E);
+    uint32_t w[RW_RNG_WORDS];
+    for (int64_t e = 0; e < E; e++) {
+        if (mask_host && !mask_host[e]) continue;
+        rw_seed_words(seeds_host[e], w);
+        for (int k = 0; k < RW_RNG_WORDS; k++) staging[(size_t)k * E + e] = w[k];
+    }
+    uint32_t *d_staging = nullptr;
+    uint8_t *d_mask = nullptr;
+    CK(cudaMallocAsync((void **)&d_staging, staging.size() * 4, st));
+    CK(cudaMemcpyAsync(d_staging, staging.data(), staging.size() * 4, cudaMemcpyHostToDevice, st));
+    if (mask_host) {
+        CK(cudaMallocAsync((void **)&d_mask, (size_t)E, st));
+        CK(cudaMemcpyAsync(d_mask, mask_host, (size_t)E, cudaMemcpyHostToDevice, st));
+    }
+    CK(rw_launch_seed_scatter(h->p, d_staging, d_mask, st));
+    CK(cudaFreeAsync(d_staging, st));
+    if (d_mask) CK(cudaFreeAsync(d_mask, st));
+    CK(cudaStreamSynchronize(st));  // `staging` is pageable host memory that must outlive the copy
+    return RW_OK;
+}
+
+int rw_reset(rw_handle *h, const uint8_t *mask_dev, float *obs_dev, void *stream) {
+    if (!h) return RW_EINVAL;
+    CK(cudaSetDevice(h->device));
+    if (mask_dev && !h->ready) return fail(h, RW_ESTATE, "rw_reset: the first reset must cover all worlds (mask == NULL)");
+    CK(rw_launch_main(RW_MODE_RESET, h->p, nullptr, obs_dev, nullptr, nullptr, mask_dev, (cudaStream_t)stream));
+    h->ready = true;
+    return RW_OK;
+}
+
+int rw_step(rw_handle *h, const int32_t *actions_dev, float *obs_dev, float *reward_dev, uint8_t *done_dev, void *stream) {
+    if (!h) return RW_EINVAL;
+    if (!actions_dev || !reward_dev || !done_dev) return fail(h, RW_EINVAL, "rw_step: actions/reward/done are required");
+    if (!h->ready) return fail(h, RW_ESTATE, "rw_step before rw_reset / rw_set_state");
+    CK(cudaSetDevice(h->device));
+    CK(rw_launch_main(RW_MODE_STEP, h->p, actions_dev, obs_dev, reward_dev, done_dev, nullptr, (cudaStream_t)stream));
+    return RW_OK;
+}
+
+int rw_obs(rw_handle *h, float *obs_dev, void *stream) {
+    if (!h || !obs_dev) return fail(h, RW_EINVAL, "rw_obs: null argument");
+    if (!h->ready) return fail(h, RW_ESTATE, "rw_obs before rw_reset / rw_set_state");
+    CK(cudaSetDevice(h->device));
+    CK(rw_launch_main(RW_MODE_OBS, h->p, nullptr, obs_dev, nullptr, nullptr, nullptr, (cudaStream_t)stream));
+    return RW_OK;
+}
+
+int rw_get_state(rw_handle *h, const rw_state_view *dev, void *stream) {
+    if (!h || !dev) return RW_EINVAL;
+    CK(cudaSetDevice(h->device));
+    CK(rw_launch_get_state(h->p, dev, (cudaStream_t)stream));
+    return RW_OK;
+}
+
+int rw_set_state(rw_handle *h, const rw_state_view *dev, void *stream) {
+    if (!h || !dev) return RW_EINVAL;
+    if (!h->ready && !(dev->agent_x && dev->agent_y && dev->agent_dir && dev->agent_carry && dev->agent_has_delivered &&
+                       dev->shelf_x && dev->shelf_y && (dev->queue || h->p.R == 0) && dev->cur_steps && dev->cur_inactive))
+        return fail(h, RW_ESTATE, "rw_set_state on a fresh handle needs every field (rng optional)");
+    CK(cudaSetDevice(h->device));
+    CK(rw_launch_set_state(h->p, dev, (cudaStream_t)stream));
+    h->ready = true;
+    return RW_OK;
+}
+
+int rw_error_count(rw_handle *h, int64_t *out, void *stream) {
+    if (!h || !out) return RW_EINVAL;
+    CK(cudaSetDevice(h->device));
+    unsigned long long v = 0;
+    CK(cudaMemcpyAsync(&v, h->d_err, 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    *out = (int64_t)v;
+    return RW_OK;
+}
+
+int rw_random_actions(rw_handle *h, int32_t *actions_dev, uint64_t seed, uint64_t step, void *stream) {
+    if (!h || !actions_dev) return RW_EINVAL;
+    CK(cudaSetDevice(h->device));
+    CK(rw_launch_random_actions(h->p, actions_dev, seed, step, (cudaStream_t)stream));
+    return RW_OK;
+}
+
+static int ensure_host_staging(rw_handle *h) {
+    if (h->host_stream) return RW_OK;
+    const RwParams &p = h->p;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
+    CK(cudaMalloc((void **)&h->d_actions, (size_t)p.E * p.n * p.A * 4));
+    CK(cudaMalloc((void **)&h->d_obs, (size_t)p.E * p.n * p.L * 4));
+    CK(cudaMalloc((void **)&h->d_reward, (size_t)p.E * p.n * 4));
+    CK(cudaMalloc((void **)&h->d_done, (size_t)p.E));
+    return RW_OK;
+}
+
+int rw_step_host(rw_handle *h, const int32_t *actions_host, float *obs_host, float *reward_host, uint8_t *done_host) {
+    if (!h || !actions_host) return RW_EINVAL;
+    int rc = ensure_host_staging(h);
+    if (rc) return rc;
+    const RwParams &p = h->p;
+    cudaStream_t st = h->host_stream;
+    CK(cudaMemcpyAsync(h->d_actions, actions_host, (size_t)p.E * p.n * p.A * 4, cudaMemcpyHostToDevice, st));
+    rc = rw_step(h, h->d_actions, obs_host ? h->d_obs : nullptr, h->d_reward, h->d_done, st);
+    if (rc) return rc;
+    if (obs_host) CK(cudaMemcpyAsync(obs_host, h->d_obs, (size_t)p.E * p.n * p.L * 4, cudaMemcpyDeviceToHost, st));
+    if (reward_host) CK(cudaMemcpyAsync(reward_host, h->d_reward, (size_t)p.E * p.n * 4, cudaMemcpyDeviceToHost, st));
+    if (done_host) CK(cudaMemcpyAsync(done_host, h->d_done, (size_t)p.E, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return RW_OK;
+}
+
+int rw_reset_host(rw_handle *h, const uint64_t *seeds_host, float *obs_host) {
+    if (!h) return RW_EINVAL;
+    int rc = ensure_host_staging(h);
+    if (rc) return rc;
+    const RwParams &p = h->p;
+    cudaStream_t st = h->host_stream;
+    if (seeds_host) {
+        rc = rw_seed(h, seeds_host, nullptr, st);
+        if (rc) return rc;
+    }
+    rc = rw_reset(h, nullptr, obs_host ? h->d_obs : nullptr, st);
+    if (rc) return rc;
+    if (obs_host) CK(cudaMemcpyAsync(obs_host, h->d_obs, (size_t)p.E * p.n * p.L * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return RW_OK;
+}
+
+int rw_host_alloc(void **out, int64_t bytes) {
+    rw_handle *h = nullptr;
+    if (!out || bytes <= 0) return RW_EINVAL;
+    CK(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault));
+    return RW_OK;
+}
+
+int rw_host_free(void *ptr) {
+    rw_handle *h = nullptr;
+    CK(cudaFreeHost(ptr));
+    return RW_OK;
+}
+
+}  // extern "C"

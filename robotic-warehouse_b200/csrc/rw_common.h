@@ -1,0 +1,107 @@
+// rw_common.h -- shared (host + device) definitions of the packed world-state layout and kernel parameters.
+//
+// HBM layout ("tile" = 32 consecutive worlds = one warp's worth):
+//   state[tile][word][lane]  int32, lane fastest  -> one tile is ONE contiguous block of nw*128 bytes, moved
+//   with a single TMA bulk copy in each direction, and lane e reads word w at bank e (conflict free).
+// Words of one world (reference fields in brackets, rware/warehouse.py):
+//   w_agent + i      : agent i+1  = x | y<<8 | dir<<16 | has_delivered<<18 | carried_shelf_id<<19   [82-93]
+//   w_msg   + i      : agent i+1 message bits (only when msg_bits > 0)                               [89]
+//   w_shelf + k/2    : two uint16 cell indices (y*W+x) of shelves 2*(k/2)+1, +2                      [128-133]
+//   w_queue + q/2    : two uint16 shelf ids of request_queue[q]                                      [262-263]
+//   w_steps, w_inact : _cur_steps, _cur_inactive_steps                                               [249-250]
+// The numpy-compatible PCG64 generator state (10 words per world) is cold data and lives in a separate
+// struct-of-arrays rng[word][world] that is only touched by worlds that deliver or reset.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define RW_HD __host__ __device__ __forceinline__
+#define RW_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define RW_HD inline
+#define RW_HD_NOINLINE
+#endif
+
+#define RW_TILE 32
+#define RW_MAX_AGENTS 32
+#define RW_MAX_GOALS 16
+#define RW_MAX_MSG_BITS 16
+#define RW_RNG_WORDS 10
+#define RW_MAX_SHELVES 8191
+#define RW_REQ_BIT 0x8000u
+
+#define RW_ACT_NOOP 0
+#define RW_ACT_FORWARD 1
+#define RW_ACT_LEFT 2
+#define RW_ACT_RIGHT 3
+#define RW_ACT_TOGGLE 4
+
+#define RW_NXT_SINK 62u
+#define RW_NXT_SELF 63u
+
+struct RwDiv {  // exact x / d for 0 <= x < 2^16, 1 <= d < 2^16 via one mulhi
+    uint32_t d, magic;
+};
+
+struct RwParams {
+    // static configuration
+    int32_t H, W, cells, n, msg_bits, A, r, win, K, cellF, L, R, S;
+    int32_t reward_type, max_steps, max_inact, norm_coords, n_goals, auto_reset;
+    int32_t goal_cell[RW_MAX_GOALS];
+    // tile layout
+    int32_t nw, w_agent, w_msg, w_shelf, w_queue, w_steps, w_inact;
+    // static device tables
+    const uint8_t *highway;     // [cells]
+    const uint16_t *home_cell;  // [S]
+    const float *normx, *normy; // [W], [H]: float32(x / (W-1)), float32(y / (H-1))
+    // world state
+    int32_t *state;  // [tiles][nw][32]
+    uint32_t *rng;   // [RW_RNG_WORDS][E_pad]
+    unsigned long long *err_count;
+    int64_t E, E_pad;
+    int32_t tiles;
+    // per-warp shared memory carve-up (byte offsets from the warp's base)
+    int32_t sm_tile, sm_grid, sm_scratch, sm_obs, sm_bar, sm_warp_bytes;
+    int32_t grid_env_stride;  // bytes per world: uint16 shelf layer [cells] then uint8 agent layer [cells]
+    int32_t ga_off;
+    int32_t obs_chunk_envs, obs_chunk_bytes, obs_nbuf, obs_env_bytes;
+    int32_t warps_per_cta;
+    RwDiv divW, divN;
+    int32_t obs_bulk;  // 1: observation chunks leave through cp.async.bulk (16-byte aligned), 0: generic stores
+};
+
+RW_HD uint32_t rw_div(uint32_t x, const RwDiv &dv) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(x, dv.magic);
+#else
+    return (uint32_t)(((uint64_t)x * dv.magic) >> 32);
+#endif
+}
+
+// ---- agent word helpers
+RW_HD int rw_ax(uint32_t aw) { return (int)(aw & 0xffu); }
+RW_HD int rw_ay(uint32_t aw) { return (int)((aw >> 8) & 0xffu); }
+RW_HD int rw_adir(uint32_t aw) { return (int)((aw >> 16) & 3u); }
+RW_HD int rw_adeliv(uint32_t aw) { return (int)((aw >> 18) & 1u); }
+RW_HD int rw_acarry(uint32_t aw) { return (int)(aw >> 19); }
+RW_HD uint32_t rw_apack(int x, int y, int dir, int deliv, int carry) {
+    return (uint32_t)x | ((uint32_t)y << 8) | ((uint32_t)dir << 16) | ((uint32_t)deliv << 18) | ((uint32_t)carry << 19);
+}
+
+// per-world view used by the lane logic; `tile` already points at this world's lane
+struct RwLane {
+    int32_t *tile;   // word w at tile[w * RW_TILE]
+    uint16_t *gs;    // shelf layer: id | RW_REQ_BIT when requested
+    uint8_t *ga;     // agent layer: id or 0
+    uint32_t *sc;    // scratch, entry k at sc[k * RW_TILE]; 2*n entries
+};
+
+RW_HD uint32_t rw_agent(const RwParams &p, const RwLane &l, int i) { return (uint32_t)l.tile[(p.w_agent + i) * RW_TILE]; }
+RW_HD void rw_set_agent(const RwParams &p, const RwLane &l, int i, uint32_t aw) { l.tile[(p.w_agent + i) * RW_TILE] = (int32_t)aw; }
+RW_HD uint16_t *rw_half(int32_t *tile, int word0, int k) {
+    return reinterpret_cast<uint16_t *>(&tile[(word0 + (k >> 1)) * RW_TILE]) + (k & 1);
+}
+RW_HD int rw_shelf_cell(const RwParams &p, const RwLane &l, int k) { return *rw_half(l.tile, p.w_shelf, k); }
+RW_HD void rw_set_shelf_cell(const RwParams &p, const RwLane &l, int k, int cell) { *rw_half(l.tile, p.w_shelf, k) = (uint16_t)cell; }
+RW_HD int rw_queue(const RwParams &p, const RwLane &l, int q) { return *rw_half(l.tile, p.w_queue, q); }
+RW_HD void rw_set_queue(const RwParams &p, const RwLane &l, int q, int id) { *rw_half(l.tile, p.w_queue, q) = (uint16_t)id; }

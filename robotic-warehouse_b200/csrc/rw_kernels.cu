@@ -1,0 +1,299 @@
+// rw_kernels.cu -- sm_100a kernels of the batched RWARE step path.
+//
+// rw_main_kernel<MODE>: ONE launch does the whole env.step for every world:
+//   warp = tile of 32 worlds (rw_common.h).  Per warp:
+//     1. lane 0 issues one TMA bulk copy (cp.async.bulk.shared::cluster.global + mbarrier complete_tx) that lands the
+//        tile's packed state (nw*128 B, contiguous in HBM) in shared memory; meanwhile all lanes zero the tile's
+//        occupancy grids in shared memory;
+//     2. lane e advances world e (rw_logic.cuh): grid build, decode, proposals, collision resolution, apply,
+//        deliveries/resample, counters, optional auto-reset -- all on shared memory, no HBM traffic;
+//     3. the updated tile goes back with one TMA bulk store (cp.async.bulk.global.shared::cta);
+//     4. the observation gather runs with one lane per (world, agent), assembling [chunk][n][L] float32 blocks
+//        in shared memory that leave through double-buffered TMA bulk stores (the obs block of consecutive
+//        worlds is contiguous in the caller's [E][n][L] tensor).
+//   Rewards/done are tiny and written directly (coalesced).  HBM-bound integer work: no tensor cores.
+// MODE: 0 = step, 1 = observation gather only (state read + obs write), 2 = reset (+ obs).
+#include "rw_launch.h"
+#include "rw_logic.cuh"
+#include "../../include/rware_b200.h"
+
+// ---------------------------------------------------------------- PTX helpers (TMA bulk copies + mbarrier)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *gmem_dst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+// ---------------------------------------------------------------- the fused kernel
+template <int MODE>
+__global__ void __launch_bounds__(256) rw_main_kernel(const __grid_constant__ RwParams p, const int32_t *__restrict__ actions,
+                                                      float *__restrict__ obs, float *__restrict__ reward,
+                                                      uint8_t *__restrict__ done, const uint8_t *__restrict__ mask) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * p.warps_per_cta + warp;
+    if (tile >= p.tiles) return;
+    uint8_t *wb = smem + (size_t)warp * p.sm_warp_bytes;
+    int32_t *tilew = reinterpret_cast<int32_t *>(wb + p.sm_tile);
+    uint8_t *grid = wb + p.sm_grid;
+    uint32_t *scratch = reinterpret_cast<uint32_t *>(wb + p.sm_scratch);
+    float *obuf = reinterpret_cast<float *>(wb + p.sm_obs);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(wb + p.sm_bar);
+    const uint32_t tile_bytes = (uint32_t)p.nw * RW_TILE * 4u;
+    int32_t *gtile = p.state + (size_t)tile * p.nw * RW_TILE;
+
+    // ---- 1. state tile HBM -> shared memory through the TMA; zero the grids while it is in flight
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        mbar_expect_tx(bar, tile_bytes);
+        bulk_g2s(tilew, gtile, tile_bytes, bar);
+    }
+    {
+        int4 *g4 = reinterpret_cast<int4 *>(grid);
+        const int n16 = (p.grid_env_stride * RW_TILE) >> 4;
+        for (int i = lane; i < n16; i += 32) g4[i] = make_int4(0, 0, 0, 0);
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+
+    // ---- 2. lane e advances world e
+    const int64_t env = (int64_t)tile * RW_TILE + lane;
+    const bool valid = env < p.E;
+    RwLane l;
+    l.tile = tilew + lane;
+    l.gs = reinterpret_cast<uint16_t *>(grid + (size_t)lane * p.grid_env_stride);
+    l.ga = grid + (size_t)lane * p.grid_env_stride + p.ga_off;
+    l.sc = scratch + lane;
+    if (valid) {
+        if (MODE == RW_MODE_RESET) {
+            if (mask == nullptr || mask[env]) rw_reset_lane(p, l, env);
+        }
+        const bool overlap = rw_build_grid(p, l);
+        if (MODE == RW_MODE_STEP) {
+            bool d = rw_step_lane(p, l, actions + env * p.n * p.A, reward + env * p.n, env, overlap);
+            done[env] = d ? 1 : 0;
+            if (d && p.auto_reset) {
+                rw_reset_lane(p, l, env);
+                uint32_t *gz = reinterpret_cast<uint32_t *>(l.gs);
+                for (int i = 0; i < (p.grid_env_stride >> 2); i++) gz[i] = 0;
+                rw_build_grid(p, l);
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- 3. updated tile shared memory -> HBM
+    if (MODE != RW_MODE_OBS) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            bulk_s2g(gtile, tilew, tile_bytes);
+            bulk_commit();
+        }
+    }
+
+    // ---- 4. observation gather: one lane per (world, agent); chunks of C worlds staged in shared memory
+    if (obs != nullptr) {
+        const int C = p.obs_chunk_envs, n = p.n, L = p.L;
+        const int items = C * n;
+        const int64_t tile_env0 = (int64_t)tile * RW_TILE;
+        const bool full = tile_env0 + RW_TILE <= p.E;
+        int chunk = 0;
+        for (int c0 = 0; c0 < RW_TILE; c0 += C, chunk++) {
+            float *buf = obuf + (size_t)(chunk % p.obs_nbuf) * (p.obs_chunk_bytes >> 2);
+            if (chunk >= p.obs_nbuf) {  // the bulk store that last read this buffer must have drained it
+                if (lane == 0) {
+                    if (p.obs_nbuf == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+                }
+                __syncwarp();
+            }
+            for (int it = lane; it < items; it += 32) {
+                int el = (int)rw_div((uint32_t)it, p.divN);
+                int a = it - el * n;
+                int e = c0 + el;
+                if (e < RW_TILE && tile_env0 + e < p.E) {
+                    RwLane le;
+                    le.tile = tilew + e;
+                    le.gs = reinterpret_cast<uint16_t *>(grid + (size_t)e * p.grid_env_stride);
+                    le.ga = grid + (size_t)e * p.grid_env_stride + p.ga_off;
+                    le.sc = nullptr;
+                    rw_obs_agent(p, le, a, buf + (size_t)it * L);
+                }
+            }
+            float *gdst = obs + (tile_env0 + c0) * (int64_t)n * L;
+            if (full && p.obs_bulk && c0 + C <= RW_TILE) {
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    bulk_s2g(gdst, buf, (uint32_t)p.obs_chunk_bytes);
+                    bulk_commit();
+                }
+            } else {  // ragged tail / unaligned geometry: plain coalesced stores
+                __syncwarp();
+                int64_t envs_here = p.E - (tile_env0 + c0);
+                if (envs_here > C) envs_here = C;
+                if (envs_here > RW_TILE - c0) envs_here = RW_TILE - c0;
+                const int nf = (int)(envs_here > 0 ? envs_here : 0) * n * L;
+                for (int i = lane; i < nf; i += 32) gdst[i] = buf[i];
+                __syncwarp();
+            }
+        }
+    }
+    if (lane == 0) bulk_wait_read<0>();  // shared memory must stay valid until the TMA has read it
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------- cold-path kernels (state views, seeding, synthetic actions)
+__global__ void rw_get_state_kernel(const RwParams p, const rw_state_view v) {
+    int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= p.E) return;
+    int32_t *t = p.state + (size_t)(env >> 5) * p.nw * RW_TILE + (env & 31);
+    RwLane l{t, nullptr, nullptr, nullptr};
+    for (int i = 0; i < p.n; i++) {
+        uint32_t aw = rw_agent(p, l, i);
+        if (v.agent_x) v.agent_x[env * p.n + i] = rw_ax(aw);
+        if (v.agent_y) v.agent_y[env * p.n + i] = rw_ay(aw);
+        if (v.agent_dir) v.agent_dir[env * p.n + i] = rw_adir(aw);
+        if (v.agent_carry) v.agent_carry[env * p.n + i] = rw_acarry(aw);
+        if (v.agent_has_delivered) v.agent_has_delivered[env * p.n + i] = rw_adeliv(aw);
+        if (v.agent_msg && p.msg_bits) {
+            uint32_t bits = (uint32_t)t[(p.w_msg + i) * RW_TILE];
+            for (int b = 0; b < p.msg_bits; b++) v.agent_msg[(env * p.n + i) * p.msg_bits + b] = (bits >> b) & 1u;
+        }
+    }
+    for (int k = 0; k < p.S; k++) {
+        uint32_t c = (uint32_t)rw_shelf_cell(p, l, k);
+        uint32_t y = rw_div(c, p.divW);
+        if (v.shelf_x) v.shelf_x[env * p.S + k] = (int32_t)(c - y * p.W);
+        if (v.shelf_y) v.shelf_y[env * p.S + k] = (int32_t)y;
+    }
+    if (v.queue)
+        for (int q = 0; q < p.R; q++) v.queue[env * p.R + q] = rw_queue(p, l, q);
+    if (v.cur_steps) v.cur_steps[env] = t[p.w_steps * RW_TILE];
+    if (v.cur_inactive) v.cur_inactive[env] = t[p.w_inact * RW_TILE];
+    if (v.rng)
+        for (int w = 0; w < RW_RNG_WORDS; w++) v.rng[env * RW_RNG_WORDS + w] = p.rng[(size_t)w * p.E_pad + env];
+}
+
+__global__ void rw_set_state_kernel(const RwParams p, const rw_state_view v) {
+    int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= p.E) return;
+    int32_t *t = p.state + (size_t)(env >> 5) * p.nw * RW_TILE + (env & 31);
+    RwLane l{t, nullptr, nullptr, nullptr};
+    for (int i = 0; i < p.n; i++) {
+        uint32_t aw = rw_agent(p, l, i);
+        int x = v.agent_x ? v.agent_x[env * p.n + i] : rw_ax(aw);
+        int y = v.agent_y ? v.agent_y[env * p.n + i] : rw_ay(aw);
+        int d = v.agent_dir ? v.agent_dir[env * p.n + i] : rw_adir(aw);
+        int c = v.agent_carry ? v.agent_carry[env * p.n + i] : rw_acarry(aw);
+        int hd = v.agent_has_delivered ? (v.agent_has_delivered[env * p.n + i] != 0) : rw_adeliv(aw);
+        rw_set_agent(p, l, i, rw_apack(x & 0xff, y & 0xff, d & 3, hd, c & 0x1fff));
+        if (v.agent_msg && p.msg_bits) {
+            uint32_t bits = 0;
+            for (int b = 0; b < p.msg_bits; b++) bits |= (uint32_t)(v.agent_msg[(env * p.n + i) * p.msg_bits + b] & 1) << b;
+            t[(p.w_msg + i) * RW_TILE] = (int32_t)bits;
+        }
+    }
+    if (v.shelf_x && v.shelf_y)
+        for (int k = 0; k < p.S; k++) rw_set_shelf_cell(p, l, k, v.shelf_y[env * p.S + k] * p.W + v.shelf_x[env * p.S + k]);
+    if (v.queue)
+        for (int q = 0; q < p.R; q++) rw_set_queue(p, l, q, v.queue[env * p.R + q]);
+    if (v.cur_steps) t[p.w_steps * RW_TILE] = v.cur_steps[env];
+    if (v.cur_inactive) t[p.w_inact * RW_TILE] = v.cur_inactive[env];
+    if (v.rng)
+        for (int w = 0; w < RW_RNG_WORDS; w++) p.rng[(size_t)w * p.E_pad + env] = v.rng[env * RW_RNG_WORDS + w];
+}
+
+__global__ void rw_seed_scatter_kernel(const RwParams p, const uint32_t *__restrict__ staging, const uint8_t *__restrict__ mask) {
+    int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= p.E) return;
+    if (mask && !mask[env]) return;
+    for (int w = 0; w < RW_RNG_WORDS; w++) p.rng[(size_t)w * p.E_pad + env] = staging[(size_t)w * p.E + env];
+}
+
+__global__ void rw_random_actions_kernel(const RwParams p, int32_t *__restrict__ actions, uint64_t seed, uint64_t step) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = p.E * p.n;
+    if (idx >= total) return;
+    uint64_t z = seed * 0x9e3779b97f4a7c15ULL + step * 0xbf58476d1ce4e5b9ULL + (uint64_t)idx * 0x94d049bb133111ebULL;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    z ^= z >> 31;
+    actions[idx * p.A] = (int32_t)(((z >> 32) * 5ULL) >> 32);
+    for (int b = 0; b < p.msg_bits; b++) actions[idx * p.A + 1 + b] = (int32_t)((z >> b) & 1ULL);
+}
+
+// ---------------------------------------------------------------- launch wrappers
+cudaError_t rw_configure_kernels(int smem_bytes_per_cta) {
+    cudaError_t e;
+    e = cudaFuncSetAttribute(rw_main_kernel<RW_MODE_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_per_cta);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(rw_main_kernel<RW_MODE_OBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_per_cta);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(rw_main_kernel<RW_MODE_RESET>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_per_cta);
+}
+
+cudaError_t rw_launch_main(RwMode mode, const RwParams &p, const int32_t *actions, float *obs, float *reward, uint8_t *done,
+                           const uint8_t *mask, cudaStream_t stream) {
+    dim3 block(32 * p.warps_per_cta);
+    dim3 grid((p.tiles + p.warps_per_cta - 1) / p.warps_per_cta);
+    size_t smem = (size_t)p.sm_warp_bytes * p.warps_per_cta;
+    switch (mode) {
+        case RW_MODE_STEP: rw_main_kernel<RW_MODE_STEP><<<grid, block, smem, stream>>>(p, actions, obs, reward, done, mask); break;
+        case RW_MODE_OBS: rw_main_kernel<RW_MODE_OBS><<<grid, block, smem, stream>>>(p, actions, obs, reward, done, mask); break;
+        case RW_MODE_RESET: rw_main_kernel<RW_MODE_RESET><<<grid, block, smem, stream>>>(p, actions, obs, reward, done, mask); break;
+    }
+    return cudaGetLastError();
+}
+
+static inline dim3 per_env_grid(int64_t n) { return dim3((unsigned)((n + 255) / 256)); }
+
+cudaError_t rw_launch_get_state(const RwParams &p, const void *view, cudaStream_t stream) {
+    rw_get_state_kernel<<<per_env_grid(p.E), 256, 0, stream>>>(p, *static_cast<const rw_state_view *>(view));
+    return cudaGetLastError();
+}
+cudaError_t rw_launch_set_state(const RwParams &p, const void *view, cudaStream_t stream) {
+    rw_set_state_kernel<<<per_env_grid(p.E), 256, 0, stream>>>(p, *static_cast<const rw_state_view *>(view));
+    return cudaGetLastError();
+}
+cudaError_t rw_launch_seed_scatter(const RwParams &p, const uint32_t *staging, const uint8_t *mask, cudaStream_t stream) {
+    rw_seed_scatter_kernel<<<per_env_grid(p.E), 256, 0, stream>>>(p, staging, mask);
+    return cudaGetLastError();
+}
+cudaError_t rw_launch_random_actions(const RwParams &p, int32_t *actions, uint64_t seed, uint64_t step, cudaStream_t stream) {
+    rw_random_actions_kernel<<<per_env_grid(p.E * p.n), 256, 0, stream>>>(p, actions, seed, step);
+    return cudaGetLastError();
+}

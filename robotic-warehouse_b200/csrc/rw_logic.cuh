@@ -1,0 +1,640 @@
+// rw_logic.cuh -- per-world ("lane") logic of the fused RWARE step: action decode, move proposal, collision
+// resolution, apply, deliveries/resample, counters, reset, and the per-agent observation writer.
+//
+// One CUDA lane advances one world; a warp advances a tile of 32 worlds in lock step (rw_kernels.cu).  The
+// code is written against RwLane (rw_common.h) and contains no warp intrinsics, so the very same source is
+// also compiled for the host by tests/hostsim (a test-only twin used to debug the logic without a GPU).
+//
+// Semantics follow the reference (semitable/robotic-warehouse @ 96fbc64e, rware/warehouse.py; cited inline
+// as "ref:LINE") but not its formulation: the reference hands a cell graph to networkx; here the resolver
+// is agent-centric (every agent has at most one successor agent), see DESIGN.md section 4.
+#pragma once
+#include "rw_common.h"
+
+// ------------------------------------------------------------------------------------------------
+// numpy-compatible PCG64 (XSL-RR 128/64) + Lemire bounded draws, so that reset()/resample reproduce the
+// reference's np_random.choice(...) calls bit for bit (ref:781, 788, 797, 916).
+// numpy/random/src/pcg64/pcg64.h, numpy/random/src/distributions/distributions.c.
+struct RwPcg {
+    uint64_t s_lo, s_hi, i_lo, i_hi;
+    uint32_t has32, u32;
+};
+
+RW_HD uint64_t rw_mulhi64(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umul64hi(a, b);
+#else
+    return (uint64_t)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+
+RW_HD void rw_pcg_load(RwPcg &g, const uint32_t *rng, int64_t stride, int64_t env) {
+    const uint32_t *b = rng + env;
+    g.s_lo = (uint64_t)b[0 * stride] | ((uint64_t)b[1 * stride] << 32);
+    g.s_hi = (uint64_t)b[2 * stride] | ((uint64_t)b[3 * stride] << 32);
+    g.i_lo = (uint64_t)b[4 * stride] | ((uint64_t)b[5 * stride] << 32);
+    g.i_hi = (uint64_t)b[6 * stride] | ((uint64_t)b[7 * stride] << 32);
+    g.has32 = b[8 * stride];
+    g.u32 = b[9 * stride];
+}
+
+RW_HD void rw_pcg_store(const RwPcg &g, uint32_t *rng, int64_t stride, int64_t env) {
+    uint32_t *b = rng + env;
+    b[0 * stride] = (uint32_t)g.s_lo; b[1 * stride] = (uint32_t)(g.s_lo >> 32);
+    b[2 * stride] = (uint32_t)g.s_hi; b[3 * stride] = (uint32_t)(g.s_hi >> 32);
+    b[8 * stride] = g.has32;
+    b[9 * stride] = g.u32;
+}
+
+RW_HD uint64_t rw_pcg_next64(RwPcg &g) {
+    const uint64_t M_HI = 2549297995355413924ULL, M_LO = 4865540595714422341ULL;
+    uint64_t lo = g.s_lo * M_LO;
+    uint64_t hi = rw_mulhi64(g.s_lo, M_LO) + g.s_lo * M_HI + g.s_hi * M_LO;
+    uint64_t nlo = lo + g.i_lo;
+    hi += g.i_hi + (uint64_t)(nlo < lo);
+    g.s_lo = nlo;
+    g.s_hi = hi;
+    uint64_t x = hi ^ nlo;
+    unsigned rot = (unsigned)(hi >> 58);
+    return (x >> rot) | (x << ((64u - rot) & 63u));
+}
+
+RW_HD uint32_t rw_pcg_next32(RwPcg &g) {
+    if (g.has32) {
+        g.has32 = 0;
+        return g.u32;
+    }
+    uint64_t v = rw_pcg_next64(g);
+    g.has32 = 1;
+    g.u32 = (uint32_t)(v >> 32);
+    return (uint32_t)v;
+}
+
+// uniform on [0, rng] inclusive (buffered_bounded_lemire_uint32); rng == 0 consumes nothing
+RW_HD uint32_t rw_bounded(RwPcg &g, uint32_t rng) {
+    if (rng == 0) return 0;
+    const uint32_t rng_excl = rng + 1;
+    uint64_t m = (uint64_t)rw_pcg_next32(g) * rng_excl;
+    uint32_t leftover = (uint32_t)m;
+    if (leftover < rng_excl) {
+        const uint32_t threshold = (0xFFFFFFFFu - rng) % rng_excl;
+        while (leftover < threshold) {
+            m = (uint64_t)rw_pcg_next32(g) * rng_excl;
+            leftover = (uint32_t)m;
+        }
+    }
+    return (uint32_t)(m >> 32);
+}
+
+// ------------------------------------------------------------------------------------------------
+// occupancy grids (what ref:749-755 _recalc_grid keeps in self.grid), rebuilt in shared memory per step.
+// Precondition: this world's grid region is zero.  Returns true when two shelves share a cell (impossible in
+// play, reachable through state injection): the reference's grid then shows the highest id, and the step falls
+// back to a full rebuild after the moves instead of the incremental update.
+RW_HD bool rw_build_grid(const RwParams &p, const RwLane &l) {
+    bool overlap = false;
+    for (int k = 0; k < p.S; k++) {
+        int c = rw_shelf_cell(p, l, k);
+        overlap |= (l.gs[c] != 0);
+        l.gs[c] = (uint16_t)(k + 1);
+    }
+    for (int q = 0; q < p.R; q++) {
+        int id = rw_queue(p, l, q);
+        if (id) {
+            int c = rw_shelf_cell(p, l, id - 1);
+            if ((l.gs[c] & 0x7fffu) == (unsigned)id) l.gs[c] |= RW_REQ_BIT;
+        }
+    }
+    for (int i = 0; i < p.n; i++) {
+        uint32_t aw = rw_agent(p, l, i);
+        l.ga[rw_ay(aw) * p.W + rw_ax(aw)] = (uint8_t)(i + 1);
+    }
+    return overlap;
+}
+
+RW_HD bool rw_in_queue(const RwParams &p, const RwLane &l, int id) {
+    for (int q = 0; q < p.R; q++)
+        if (rw_queue(p, l, q) == id) return true;
+    return false;
+}
+
+// scratch accessors: entry 2i = start | target<<16, entry 2i+1 = meta
+RW_HD uint32_t &rw_st(const RwLane &l, int i) { return l.sc[(2 * i) * RW_TILE]; }
+RW_HD uint32_t &rw_meta(const RwLane &l, int i) { return l.sc[(2 * i + 1) * RW_TILE]; }
+// meta: act[0:3) nxt[3:9) h[9:15) sh[16:32)
+RW_HD uint32_t rw_m_act(uint32_t m) { return m & 7u; }
+RW_HD uint32_t rw_m_nxt(uint32_t m) { return (m >> 3) & 63u; }
+RW_HD uint32_t rw_m_h(uint32_t m) { return (m >> 9) & 63u; }
+
+// ------------------------------------------------------------------------------------------------
+// CPython 3.12 tuple hash of (x, y) and set insertion/iteration order (Objects/tupleobject.c:tuplehash,
+// Objects/setobject.c:set_add_entry / set_insert_clean / set_table_resize).  Needed only to order tied
+// contenders the way networkx's component copy does.
+RW_HD uint64_t rw_py_hash_xy(uint32_t x, uint32_t y) {
+    const uint64_t P1 = 11400714785074694791ULL, P2 = 14029467366897019727ULL, P5 = 2870177450012600261ULL;
+    uint64_t acc = P5;
+    acc += (uint64_t)x * P2;
+    acc = (acc << 31) | (acc >> 33);
+    acc *= P1;
+    acc += (uint64_t)y * P2;
+    acc = (acc << 31) | (acc >> 33);
+    acc *= P1;
+    acc += 2ULL ^ (P5 ^ 3527539ULL);
+    return acc == ~0ULL ? 1546275796ULL : acc;
+}
+
+struct RwPySet {  // keys are node ids < 64; tables never exceed 128 slots for <= 64 keys
+    uint8_t tab[128];
+    int mask, fill;
+};
+
+RW_HD void rw_pyset_init(RwPySet &s) {
+    s.mask = 7;
+    s.fill = 0;
+    for (int i = 0; i < 8; i++) s.tab[i] = 0xff;
+}
+
+RW_HD int rw_pyset_probe(const uint8_t *tab, int mask, uint64_t hash) {
+    uint64_t perturb = hash;
+    uint32_t i = (uint32_t)hash & (uint32_t)mask;
+    for (;;) {
+        if (tab[i] == 0xff) return (int)i;
+        if (i + 9 <= (uint32_t)mask) {
+            for (uint32_t j = 1; j <= 9; j++)
+                if (tab[i + j] == 0xff) return (int)(i + j);
+        }
+        perturb >>= 5;
+        i = (uint32_t)((uint64_t)i * 5 + 1 + perturb) & (uint32_t)mask;
+    }
+}
+
+template <class HashOf>
+RW_HD void rw_pyset_add(RwPySet &s, int key, HashOf hash_of) {
+    s.tab[rw_pyset_probe(s.tab, s.mask, hash_of(key))] = (uint8_t)key;
+    s.fill++;
+    if (s.fill * 5 < s.mask * 3) return;
+    int newsize = 8;
+    while (newsize <= s.fill * 4) newsize <<= 1;
+    uint8_t nt[128];
+    for (int i = 0; i < newsize; i++) nt[i] = 0xff;
+    for (int i = 0; i <= s.mask; i++)
+        if (s.tab[i] != 0xff) nt[rw_pyset_probe(nt, newsize - 1, hash_of(s.tab[i]))] = s.tab[i];
+    for (int i = 0; i < newsize; i++) s.tab[i] = nt[i];
+    s.mask = newsize - 1;
+}
+
+// Among the agents in `ties` (bit i = agent i; their start cells are tied predecessors of one cell), return the
+// one whose start cell comes first in the node order of networkx's G.subgraph(component).copy():
+// G insertion order when 2*|component| >= |G|, CPython set iteration order otherwise
+// (NX/classes/coreviews.py:293-300, 342-349; NX/algorithms/components/weakly_connected.py:61-66, 169-196).
+RW_HD_NOINLINE int rw_tie_first(const RwParams &p, const RwLane &l, uint32_t ties) {
+    const int n = p.n, m = 2 * n;
+    // node id of a cell := index of its first appearance in the sequence s_0, t_0, s_1, t_1, ... (DiGraph.add_edge
+    // inserts the start node, then the target node, ref:825-846)
+    uint8_t first[2 * RW_MAX_AGENTS];
+    uint64_t is_node = 0;
+    for (int k = 0; k < m; k++) {
+        uint32_t ck = (k & 1) ? (rw_st(l, k >> 1) >> 16) : (rw_st(l, k >> 1) & 0xffffu);
+        int f = k;
+        for (int j = 0; j < k; j++) {
+            uint32_t cj = (j & 1) ? (rw_st(l, j >> 1) >> 16) : (rw_st(l, j >> 1) & 0xffffu);
+            if (cj == ck) { f = j; break; }
+        }
+        first[k] = (uint8_t)f;
+        if (f == k) is_node |= 1ULL << k;
+    }
+    int nG = 0;
+    for (uint64_t b = is_node; b; b &= b - 1) nG++;
+    // weakly connected component containing the tied cells: flood fill over succ/pred
+    int cand0 = 0;
+    while (!((ties >> cand0) & 1u)) cand0++;
+    uint64_t member = 1ULL << first[2 * cand0], frontier = member;
+    while (frontier) {
+        uint64_t next = 0;
+        for (int a = 0; a < n; a++) {
+            uint64_t bs = 1ULL << first[2 * a], bt = 1ULL << first[2 * a + 1];
+            if (frontier & bs) next |= bt;
+            if (frontier & bt) next |= bs;
+        }
+        frontier = next & ~member;
+        member |= frontier;
+    }
+    int csize = 0;
+    for (uint64_t b = member; b; b &= b - 1) csize++;
+    if (2 * csize >= nG) {  // G insertion order
+        int best = -1, best_node = 1 << 30;
+        for (int a = 0; a < n; a++)
+            if (((ties >> a) & 1u) && first[2 * a] < best_node) { best_node = first[2 * a]; best = a; }
+        return best;
+    }
+    // CPython set order.  c = _plain_bfs(G, source = first node of the component in G order)
+    auto cell_of = [&](int node) -> uint32_t {
+        return (node & 1) ? (rw_st(l, node >> 1) >> 16) : (rw_st(l, node >> 1) & 0xffffu);
+    };
+    auto hash_of = [&](int node) -> uint64_t {
+        uint32_t c = cell_of(node);
+        uint32_t y = rw_div(c, p.divW);
+        return rw_py_hash_xy(c - y * (uint32_t)p.W, y);
+    };
+    int src = 0;
+    while (!((member >> src) & 1ULL)) src++;
+    RwPySet set1;
+    rw_pyset_init(set1);
+    uint64_t seen = 1ULL << src;
+    rw_pyset_add(set1, src, hash_of);
+    uint8_t level[2 * RW_MAX_AGENTS], nextl[2 * RW_MAX_AGENTS];
+    int nlevel = 1, nnext = 0;
+    level[0] = (uint8_t)src;
+    while (nlevel) {
+        nnext = 0;
+        for (int li = 0; li < nlevel; li++) {
+            int v = level[li];
+            uint32_t cv = cell_of(v);
+            int occ = l.ga[cv];  // agent standing on this cell (pre-move layer) owns its single out-edge
+            if (occ) {
+                int w = first[2 * (occ - 1) + 1];
+                if (!((seen >> w) & 1ULL)) { seen |= 1ULL << w; rw_pyset_add(set1, w, hash_of); nextl[nnext++] = (uint8_t)w; }
+            }
+            for (int a = 0; a < n; a++)  // G._pred[v] in edge (= agent) order
+                if ((rw_st(l, a) >> 16) == cv) {
+                    int w = first[2 * a];
+                    if (!((seen >> w) & 1ULL)) { seen |= 1ULL << w; rw_pyset_add(set1, w, hash_of); nextl[nnext++] = (uint8_t)w; }
+                }
+        }
+        for (int i = 0; i < nnext; i++) level[i] = nextl[i];
+        nlevel = nnext;
+    }
+    // show_nodes.nodes = set(nbunch_iter(c)): second set filled in the iteration order of the first
+    RwPySet set2;
+    rw_pyset_init(set2);
+    for (int i = 0; i <= set1.mask; i++)
+        if (set1.tab[i] != 0xff) rw_pyset_add(set2, set1.tab[i], hash_of);
+    for (int i = 0; i <= set2.mask; i++) {
+        int node = set2.tab[i];
+        if (node == 0xff) continue;
+        for (int a = 0; a < n; a++)
+            if (((ties >> a) & 1u) && first[2 * a] == node) return a;
+    }
+    return cand0;  // unreachable
+}
+
+// pick the contender with the greatest height; ties by rw_tie_first
+RW_HD int rw_pick(const RwParams &p, const RwLane &l, uint32_t cand) {
+    uint32_t best = 0, ties = 0;
+    int besth = -1;
+    for (uint32_t b = cand; b; b &= b - 1) {
+#if defined(__CUDA_ARCH__)
+        int k = __ffs((int)b) - 1;
+#else
+        int k = __builtin_ctz(b);
+#endif
+        int h = (int)rw_m_h(rw_meta(l, k));
+        if (h > besth) { besth = h; best = (uint32_t)k; ties = 1u << k; }
+        else if (h == besth) ties |= 1u << k;
+    }
+    if (ties & (ties - 1)) return rw_tie_first(p, l, ties);
+    return (int)best;
+}
+
+// ------------------------------------------------------------------------------------------------
+// request-queue resample on delivery (ref:915-917): candidates = shelves not in the queue in ascending id,
+// new = np_random.choice(candidates), replaces the delivered shelf in place.
+RW_HD_NOINLINE void rw_resample(const RwParams &p, const RwLane &l, int delivered_id, int64_t env) {
+    int distinct = 0;
+    for (int q = 0; q < p.R; q++) {
+        int id = rw_queue(p, l, q);
+        bool dup = false;
+        for (int j = 0; j < q; j++) dup |= (rw_queue(p, l, j) == id);
+        distinct += !dup;
+    }
+    int n_cand = p.S - distinct;
+    int new_id = delivered_id;  // S == R: the reference raises ValueError (empty population); we keep the shelf
+    if (n_cand > 0) {
+        RwPcg g;
+        rw_pcg_load(g, p.rng, p.E_pad, env);
+        int pick = (int)rw_bounded(g, (uint32_t)(n_cand - 1));
+        rw_pcg_store(g, p.rng, p.E_pad, env);
+        for (int s = 1; s <= p.S; s++) {
+            if (rw_in_queue(p, l, s)) continue;
+            if (pick-- == 0) { new_id = s; break; }
+        }
+    }
+    for (int q = 0; q < p.R; q++)
+        if (rw_queue(p, l, q) == delivered_id) { rw_set_queue(p, l, q, new_id); break; }
+    // requested bits of the two shelves involved
+    int cd = rw_shelf_cell(p, l, delivered_id - 1);
+    if ((l.gs[cd] & 0x7fffu) == (unsigned)delivered_id)
+        l.gs[cd] = (uint16_t)(delivered_id | (rw_in_queue(p, l, delivered_id) ? RW_REQ_BIT : 0u));
+    int cn = rw_shelf_cell(p, l, new_id - 1);
+    if ((l.gs[cn] & 0x7fffu) == (unsigned)new_id) l.gs[cn] |= RW_REQ_BIT;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warehouse.reset() for one world (ref:757-802), continuing the world's generator stream.  Does NOT touch
+// the occupancy grids (the caller rebuilds them).
+RW_HD_NOINLINE void rw_reset_lane(const RwParams &p, const RwLane &l, int64_t env) {
+    RwPcg g;
+    rw_pcg_load(g, p.rng, p.E_pad, env);
+    for (int k = 0; k < p.S; k++) rw_set_shelf_cell(p, l, k, p.home_cell[k]);  // ref:771-778
+    const int n = p.n;
+    // ref:781-785 np_random.choice(arange(H*W), size=n, replace=False): Floyd's algorithm then a shuffle
+    for (int k = 0; k < n; k++) {
+        uint32_t j = (uint32_t)(p.cells - n + k);
+        uint32_t val = rw_bounded(g, j);
+        bool found = false;
+        for (int q = 0; q < k; q++) found |= (l.sc[q * RW_TILE] == val);
+        l.sc[k * RW_TILE] = found ? j : val;
+    }
+    for (int i = n - 1; i >= 1; i--) {
+        uint32_t j = rw_bounded(g, (uint32_t)i);
+        uint32_t t = l.sc[i * RW_TILE];
+        l.sc[i * RW_TILE] = l.sc[j * RW_TILE];
+        l.sc[j * RW_TILE] = t;
+    }
+    for (int i = 0; i < n; i++) {  // ref:786-792: unravel_index -> (y, x); dirs from choice(Direction, size=n)
+        uint32_t loc = l.sc[i * RW_TILE];
+        uint32_t y = rw_div(loc, p.divW);
+        uint32_t dir = rw_bounded(g, 3);
+        rw_set_agent(p, l, i, rw_apack((int)(loc - y * (uint32_t)p.W), (int)y, (int)dir, 0, 0));
+        if (p.msg_bits) l.tile[(p.w_msg + i) * RW_TILE] = 0;
+    }
+    // ref:796-800 np_random.choice(self.shelfs, size=R, replace=False)
+    for (int k = 0; k < p.R; k++) {
+        uint32_t j = (uint32_t)(p.S - p.R + k);
+        uint32_t val = rw_bounded(g, j);
+        bool found = false;
+        for (int q = 0; q < k; q++) found |= ((uint32_t)rw_queue(p, l, q) == val + 1);
+        rw_set_queue(p, l, k, (int)((found ? j : val) + 1));
+    }
+    for (int i = p.R - 1; i >= 1; i--) {
+        int j = (int)rw_bounded(g, (uint32_t)i);
+        int t = rw_queue(p, l, i);
+        rw_set_queue(p, l, i, rw_queue(p, l, j));
+        rw_set_queue(p, l, j, t);
+    }
+    l.tile[p.w_steps * RW_TILE] = 0;  // ref:764-765
+    l.tile[p.w_inact * RW_TILE] = 0;
+    rw_pcg_store(g, p.rng, p.E_pad, env);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warehouse.step() for one world (ref:804-942), everything except the observation gather.
+// act: this world's actions [n][A]; reward: this world's [n] floats.  Returns done.
+// Precondition: grids built from the current state.  Postcondition: tile words and grids hold the
+// post-step state (post-move agents/shelves, post-resample request bits).
+RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, const int32_t *act, float *reward, int64_t env,
+                        bool overlap) {
+    const int n = p.n, W = p.W, H = p.H;
+    uint32_t commit = 0, dag = 0, bad = 0;
+    // ---- decode + proposals (ref:809-846)
+    for (int i = 0; i < n; i++) {
+        uint32_t aw = rw_agent(p, l, i);
+        int a = act[i * p.A];
+        if ((unsigned)a > 4u) { a = RW_ACT_NOOP; bad++; }
+        if (p.msg_bits) {
+            uint32_t bits = 0;
+            for (int b = 0; b < p.msg_bits; b++) bits |= (uint32_t)(act[i * p.A + 1 + b] & 1) << b;
+            l.tile[(p.w_msg + i) * RW_TILE] = (int32_t)bits;
+        }
+        int x = rw_ax(aw), y = rw_ay(aw), tx = x, ty = y;
+        if (a == RW_ACT_FORWARD) {  // Agent.req_location ref:102-116, clamped at the walls
+            int d = rw_adir(aw);
+            if (d == 0) ty = y > 0 ? y - 1 : 0;
+            else if (d == 1) ty = y < H - 1 ? y + 1 : H - 1;
+            else if (d == 2) tx = x > 0 ? x - 1 : 0;
+            else tx = x < W - 1 ? x + 1 : W - 1;
+        }
+        uint32_t s = (uint32_t)(y * W + x), t = (uint32_t)(ty * W + tx);
+        if (t != s && rw_acarry(aw) && (l.gs[t] & 0x7fffu)) {  // ref:829-844 carrier into a standing shelf
+            int o = l.ga[t];
+            if (!(o && rw_acarry(rw_agent(p, l, o - 1)))) { a = RW_ACT_NOOP; t = s; }
+        }
+        uint32_t nxt;
+        if (t == s) { nxt = RW_NXT_SELF; commit |= 1u << i; }
+        else { int o = l.ga[t]; nxt = o ? (uint32_t)(o - 1) : RW_NXT_SINK; }
+        rw_st(l, i) = s | (t << 16);
+        rw_meta(l, i) = (uint32_t)a | (nxt << 3);
+    }
+    if (bad) {
+#if defined(__CUDA_ARCH__)
+        atomicAdd(p.err_count, (unsigned long long)bad);
+#else
+        *p.err_count += bad;
+#endif
+    }
+    // ---- resolve (ref:848-876 restated agent-centrically)
+    uint32_t movers = ~commit & (n == 32 ? 0xffffffffu : ((1u << n) - 1u));
+    if (movers) {
+        for (uint32_t b = movers; b; b &= b - 1) {
+#if defined(__CUDA_ARCH__)
+            int i = __ffs((int)b) - 1;
+#else
+            int i = __builtin_ctz(b);
+#endif
+            uint32_t j = rw_m_nxt(rw_meta(l, i));
+            int hops = 1;
+            for (;;) {
+                if (j == RW_NXT_SINK) { dag |= 1u << i; break; }          // chain ends in a free cell
+                if (j == (uint32_t)i) { if (hops != 2) commit |= 1u << i; break; }  // on a cycle; 2-cycles (swaps) fail
+                uint32_t nj = rw_m_nxt(rw_meta(l, (int)j));
+                if (nj == RW_NXT_SELF || hops >= n) break;               // blocked by a stationary agent / feeds a cycle
+                j = nj;
+                hops++;
+            }
+        }
+        if (dag) {
+            // heights: h[j] = 1 + max h[i] over dag agents i stepping onto j's cell (dag.py:1073-1101 `dist`)
+            bool changed = true;
+            for (int round = 0; changed && round < n; round++) {
+                changed = false;
+                for (uint32_t b = dag; b; b &= b - 1) {
+#if defined(__CUDA_ARCH__)
+                    int i = __ffs((int)b) - 1;
+#else
+                    int i = __builtin_ctz(b);
+#endif
+                    uint32_t mi = rw_meta(l, i);
+                    uint32_t j = rw_m_nxt(mi);
+                    if (j >= RW_NXT_SINK) continue;
+                    uint32_t mj = rw_meta(l, (int)j);
+                    uint32_t hi1 = rw_m_h(mi) + 1;
+                    if (rw_m_h(mj) < hi1) { rw_meta(l, (int)j) = (mj & ~(63u << 9)) | (hi1 << 9); changed = true; }
+                }
+            }
+            // walk back from every sink cell along the longest path
+            uint32_t sinkers = 0;
+            for (uint32_t b = dag; b; b &= b - 1) {
+#if defined(__CUDA_ARCH__)
+                int i = __ffs((int)b) - 1;
+#else
+                int i = __builtin_ctz(b);
+#endif
+                if (rw_m_nxt(rw_meta(l, i)) == RW_NXT_SINK) sinkers |= 1u << i;
+            }
+            uint32_t handled = 0;
+            while (sinkers & ~handled) {
+                uint32_t rem = sinkers & ~handled;
+#if defined(__CUDA_ARCH__)
+                int i0 = __ffs((int)rem) - 1;
+#else
+                int i0 = __builtin_ctz(rem);
+#endif
+                uint32_t c = rw_st(l, i0) >> 16, cand = 0;
+                for (uint32_t b = rem; b; b &= b - 1) {
+#if defined(__CUDA_ARCH__)
+                    int k = __ffs((int)b) - 1;
+#else
+                    int k = __builtin_ctz(b);
+#endif
+                    if ((rw_st(l, k) >> 16) == c) cand |= 1u << k;
+                }
+                handled |= cand;
+                int cur = rw_pick(p, l, cand);
+                for (;;) {
+                    commit |= 1u << cur;
+                    if (rw_m_h(rw_meta(l, cur)) == 0) break;  // nobody steps onto cur's cell
+                    cand = 0;
+                    for (uint32_t b = dag; b; b &= b - 1) {
+#if defined(__CUDA_ARCH__)
+                        int k = __ffs((int)b) - 1;
+#else
+                        int k = __builtin_ctz(b);
+#endif
+                        if (rw_m_nxt(rw_meta(l, k)) == (uint32_t)cur) cand |= 1u << k;
+                    }
+                    cur = rw_pick(p, l, cand);
+                }
+            }
+        }
+    }
+    // ---- apply (ref:878-899).  Failed agents become NOOP (ref:871-876).
+    uint64_t rew_lo = 0, rew_hi = 0;  // per-agent reward in half units, 4 bits each
+    int rew_global = 0;
+    uint32_t moved = 0;
+    for (int i = 0; i < n; i++) {
+        uint32_t m = rw_meta(l, i);
+        uint32_t a = rw_m_act(m);
+        if (a == RW_ACT_NOOP) continue;
+        uint32_t aw = rw_agent(p, l, i);
+        uint32_t st = rw_st(l, i);
+        uint32_t s = st & 0xffffu, t = st >> 16;
+        if (a == RW_ACT_FORWARD) {
+            if (!((commit >> i) & 1u) || t == s) continue;
+            moved |= 1u << i;
+            l.ga[s] = 0;
+            if (rw_acarry(aw)) {  // lift the carried shelf's grid entry; it is put down at t in the second pass
+                rw_meta(l, i) = (m & 0xffffu) | ((uint32_t)l.gs[s] << 16);
+                l.gs[s] = 0;
+            }
+        } else if (a == RW_ACT_LEFT || a == RW_ACT_RIGHT) {  // Agent.req_direction ref:118-125
+            uint32_t d = (uint32_t)rw_adir(aw);
+            uint32_t nd = ((a == RW_ACT_RIGHT ? 0x4Bu : 0x1Eu) >> (2 * d)) & 3u;
+            rw_set_agent(p, l, i, (aw & ~(3u << 16)) | (nd << 16));
+        } else {  // TOGGLE_LOAD ref:889-899
+            if (!rw_acarry(aw)) {
+                uint32_t id = l.gs[s] & 0x7fffu;
+                if (id) rw_set_agent(p, l, i, aw | (id << 19));
+            } else if (!p.highway[s]) {
+                if (rw_adeliv(aw) && p.reward_type == 2) {
+                    if (i < 16) rew_lo += 1ULL << (4 * i); else rew_hi += 1ULL << (4 * (i - 16));
+                }
+                rw_set_agent(p, l, i, aw & 0x3ffffu & ~(1u << 18));
+            }
+        }
+    }
+    for (uint32_t b = moved; b; b &= b - 1) {
+#if defined(__CUDA_ARCH__)
+        int i = __ffs((int)b) - 1;
+#else
+        int i = __builtin_ctz(b);
+#endif
+        uint32_t aw = rw_agent(p, l, i);
+        uint32_t t = rw_st(l, i) >> 16;
+        uint32_t ty = rw_div(t, p.divW), tx = t - ty * (uint32_t)W;
+        rw_set_agent(p, l, i, (aw & ~0xffffu) | tx | (ty << 8));
+        l.ga[t] = (uint8_t)(i + 1);
+        int carry = rw_acarry(aw);
+        if (carry) {
+            l.gs[t] = (uint16_t)(rw_meta(l, i) >> 16);
+            rw_set_shelf_cell(p, l, carry - 1, (int)t);
+        }
+    }
+    if (overlap) {  // degenerate injected state: redo ref:901 _recalc_grid literally
+        uint32_t *gz = reinterpret_cast<uint32_t *>(l.gs);
+        for (int i = 0; i < (p.grid_env_stride >> 2); i++) gz[i] = 0;
+        rw_build_grid(p, l);
+    }
+    // ---- deliveries (ref:903-927)
+    bool delivered = false;
+    for (int gi = 0; gi < p.n_goals; gi++) {
+        int c = p.goal_cell[gi];
+        uint32_t sh = l.gs[c];
+        if (!(sh & RW_REQ_BIT)) continue;
+        int id = (int)(sh & 0x7fffu);
+        delivered = true;
+        rw_resample(p, l, id, env);
+        int o = l.ga[c];
+        int ai = o ? o - 1 : n - 1;  // python's rewards[-1] when nobody stands on the goal
+        if (p.reward_type == 0) rew_global++;
+        else {
+            uint64_t add = (p.reward_type == 1) ? 2ULL : 1ULL;
+            if (ai < 16) rew_lo += add << (4 * ai); else rew_hi += add << (4 * (ai - 16));
+            if (p.reward_type == 2) rw_set_agent(p, l, ai, rw_agent(p, l, ai) | (1u << 18));
+        }
+    }
+    for (int i = 0; i < n; i++) {
+        uint32_t half = (uint32_t)(((i < 16 ? rew_lo >> (4 * i) : rew_hi >> (4 * (i - 16))) & 15ULL)) + 2u * (uint32_t)rew_global;
+        reward[i] = 0.5f * (float)half;
+    }
+    // ---- counters / termination (ref:929-941)
+    int inact = delivered ? 0 : l.tile[p.w_inact * RW_TILE] + 1;
+    int steps = l.tile[p.w_steps * RW_TILE] + 1;
+    l.tile[p.w_inact * RW_TILE] = inact;
+    l.tile[p.w_steps * RW_TILE] = steps;
+    return (p.max_inact && inact >= p.max_inact) || (p.max_steps && steps >= p.max_steps);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Flattened observation of agent i of the world in `l` (ref:598-674; layout SURVEY.md App. C) -> out[L].
+RW_HD void rw_obs_agent(const RwParams &p, const RwLane &l, int i, float *out) {
+    uint32_t aw = rw_agent(p, l, i);
+    int x = rw_ax(aw), y = rw_ay(aw), d = rw_adir(aw);
+    int W = p.W, H = p.H;
+    out[0] = p.norm_coords ? p.normx[x] : (float)x;  // ref:636-643
+    out[1] = p.norm_coords ? p.normy[y] : (float)y;
+    out[2] = rw_acarry(aw) ? 1.0f : 0.0f;
+    out[3] = d == 0 ? 1.0f : 0.0f;                    // ref:644-646
+    out[4] = d == 1 ? 1.0f : 0.0f;
+    out[5] = d == 2 ? 1.0f : 0.0f;
+    out[6] = d == 3 ? 1.0f : 0.0f;
+    out[7] = p.highway[y * W + x] ? 1.0f : 0.0f;      // ref:647
+    float *o = out + 8;
+    const int r = p.r, mb = p.msg_bits;
+    for (int dy = -r; dy <= r; dy++) {                 // ref:628-629 rows outer, columns inner
+        int yy = y + dy;
+        bool yin = (unsigned)yy < (unsigned)H;
+        for (int dx = -r; dx <= r; dx++) {
+            int xx = x + dx;
+            uint32_t ida = 0, sh = 0;
+            if (yin && (unsigned)xx < (unsigned)W) {   // zero padding outside the map (ref:606-626)
+                int c = yy * W + xx;
+                ida = l.ga[c];
+                sh = l.gs[c];
+            }
+            uint32_t od = 0, bits = 0;
+            if (ida) {
+                od = (uint32_t)rw_adir(rw_agent(p, l, (int)ida - 1));
+                if (mb) bits = (uint32_t)l.tile[(p.w_msg + (int)ida - 1) * RW_TILE];
+            }
+            o[0] = ida ? 1.0f : 0.0f;                  // ref:656-667: empty cell reads as direction one-hot [1,0,0,0]
+            o[1] = od == 0 ? 1.0f : 0.0f;
+            o[2] = od == 1 ? 1.0f : 0.0f;
+            o[3] = od == 2 ? 1.0f : 0.0f;
+            o[4] = od == 3 ? 1.0f : 0.0f;
+            for (int b = 0; b < mb; b++) o[5 + b] = (float)((bits >> b) & 1u);
+            o[5 + mb] = (sh & 0x7fffu) ? 1.0f : 0.0f;  // ref:668-673
+            o[6 + mb] = (sh & RW_REQ_BIT) ? 1.0f : 0.0f;
+            o += 7 + mb;
+        }
+    }
+}

@@ -1,0 +1,114 @@
+"""Observation/action spaces.  gymnasium's are used when gymnasium is importable; otherwise a minimal, API-compatible
+subset (Discrete, MultiDiscrete, Box, Tuple with sample/contains/==) so that the package does not hard-depend on it
+(the reference does: rware/warehouse.py:5-6, 255-260, 505-522)."""
+import numpy as np
+
+try:  # pragma: no cover - depends on the environment
+    import gymnasium as _gym
+    from gymnasium.spaces import Box, Discrete, MultiDiscrete, Tuple  # noqa: F401
+    HAVE_GYMNASIUM = True
+except Exception:  # gymnasium absent
+    _gym = None
+    HAVE_GYMNASIUM = False
+
+    class _Space:
+        _rng = None
+
+        @property
+        def np_random(self):
+            if self._rng is None:
+                self._rng = np.random.default_rng()
+            return self._rng
+
+        def seed(self, seed=None):
+            self._rng = np.random.default_rng(seed)
+
+        def __contains__(self, x):
+            return self.contains(x)
+
+    class Discrete(_Space):
+        def __init__(self, n):
+            self.n = int(n)
+            self.shape = ()
+            self.dtype = np.dtype(np.int64)
+
+        def sample(self):
+            return int(self.np_random.integers(self.n))
+
+        def contains(self, x):
+            try:
+                return 0 <= int(x) < self.n and float(x) == int(x)
+            except (TypeError, ValueError):
+                return False
+
+        def __eq__(self, other):
+            return isinstance(other, Discrete) and other.n == self.n
+
+        def __repr__(self):
+            return f"Discrete({self.n})"
+
+    class MultiDiscrete(_Space):
+        def __init__(self, nvec):
+            self.nvec = np.asarray(nvec, dtype=np.int64)
+            self.shape = self.nvec.shape
+            self.dtype = np.dtype(np.int64)
+
+        def sample(self):
+            return (self.np_random.random(self.nvec.shape) * self.nvec).astype(np.int64)
+
+        def contains(self, x):
+            x = np.asarray(x)
+            return x.shape == self.shape and bool(np.all(x >= 0) and np.all(x < self.nvec))
+
+        def __eq__(self, other):
+            return isinstance(other, MultiDiscrete) and self.shape == other.shape and bool(np.all(self.nvec == other.nvec))
+
+        def __repr__(self):
+            return f"MultiDiscrete({self.nvec.tolist()})"
+
+    class Box(_Space):
+        def __init__(self, low, high, shape=None, dtype=np.float32):
+            self.dtype = np.dtype(dtype)
+            self.shape = tuple(shape) if shape is not None else np.broadcast(np.asarray(low), np.asarray(high)).shape
+            self.low = np.broadcast_to(np.asarray(low, dtype=np.float64), self.shape).astype(self.dtype)
+            self.high = np.broadcast_to(np.asarray(high, dtype=np.float64), self.shape).astype(self.dtype)
+
+        def sample(self):
+            lo = np.where(np.isfinite(self.low), self.low, -1e6)
+            hi = np.where(np.isfinite(self.high), self.high, 1e6)
+            return self.np_random.uniform(lo, hi).astype(self.dtype)
+
+        def contains(self, x):
+            x = np.asarray(x)
+            return x.shape == self.shape and bool(np.all(x >= self.low) and np.all(x <= self.high))
+
+        def __eq__(self, other):
+            return isinstance(other, Box) and self.shape == other.shape and self.dtype == other.dtype
+
+        def __repr__(self):
+            return f"Box({self.shape}, {self.dtype})"
+
+    class Tuple(_Space):
+        def __init__(self, spaces):
+            self.spaces = tuple(spaces)
+
+        def sample(self):
+            return tuple(s.sample() for s in self.spaces)
+
+        def contains(self, x):
+            return len(x) == len(self.spaces) and all(s.contains(v) for s, v in zip(self.spaces, x))
+
+        def __getitem__(self, i):
+            return self.spaces[i]
+
+        def __len__(self):
+            return len(self.spaces)
+
+        def __iter__(self):
+            return iter(self.spaces)
+
+        def __eq__(self, other):
+            return isinstance(other, Tuple) and self.spaces == other.spaces
+
+        def __repr__(self):
+            return "Tuple(" + ", ".join(map(repr, self.spaces)) + ")"

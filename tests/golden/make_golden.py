@@ -1,0 +1,166 @@
+"""Generates tests/golden/*.npz from the UNMODIFIED reference (build container only; /root/reference is not on the
+GPU box).  Run:  python tests/golden/make_golden.py
+
+Each fixture is a whole trajectory of one reference world: constructor kwargs, reset seed, the action stream, the
+state injections ("teleports" that make deliveries happen under random actions), and per step the complete world
+state, rewards, done, the generator state and a SHA-256 of the float32 observations.  The replay harness
+(tests/replay.py) drives the oracle, the host twin and the CUDA path through the same trajectory and demands
+bit-exact agreement on every field.
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle", "refharness"))
+import refenv  # noqa: E402
+
+STATE_KEYS = ("agent_x", "agent_y", "agent_dir", "agent_carry", "agent_deliv", "agent_msg", "shelf_x", "shelf_y",
+              "queue", "counters", "rng")
+
+
+def kw(cols, height, rows, n, msg, sr, rq, inact, maxs, rt, **extra):
+    d = dict(shelf_columns=cols, column_height=height, shelf_rows=rows, n_agents=n, msg_bits=msg, sensor_range=sr,
+             request_queue_size=rq, max_inactivity_steps=inact, max_steps=maxs, reward_type=rt)
+    d.update(extra)
+    return d
+
+
+def record(wh, name, kwargs, steps, p_forward, teleport_every, seed, reseed_on_done=True):
+    env = wh.Warehouse(**{**kwargs, "reward_type": wh.RewardType(kwargs["reward_type"])})
+    rs = np.random.default_rng(seed + 4242)
+    n, mb = kwargs["n_agents"], kwargs["msg_bits"]
+    obs, _ = env.reset(seed=seed)
+    obs0 = np.stack(obs).astype(np.float32)
+    st0 = refenv.ref_state(env)
+    probs = np.full(5, (1 - p_forward) / 4)
+    probs[1] = p_forward
+    actions = np.zeros((steps, n, 1 + mb), np.int8)
+    states = {k: [] for k in STATE_KEYS}
+    rewards, dones, obs_sha, obs_keep = [], [], [], {}
+    inject_step, inject_state = [], []
+    resets = []  # (step index after which reset happened, seed or -1)
+    for t in range(steps):
+        if teleport_every and t % teleport_every == teleport_every - 1:
+            st = refenv.ref_state(env)
+            a = int(rs.integers(n))
+            gx, gy = env.goals[int(rs.integers(len(env.goals)))]
+            free = (gy > 0 and not any(st["agent_x"][i] == gx and st["agent_y"][i] in (gy - 1, gy) for i in range(n) if i != a)
+                    and len(st["queue"]) > 0)
+            if free:
+                sid = int(st["queue"][int(rs.integers(len(st["queue"])))])
+                if not any(st["agent_carry"][i] == sid for i in range(n) if i != a):
+                    st["agent_carry"][a] = sid
+                    st["agent_x"][a], st["agent_y"][a], st["agent_dir"][a] = gx, gy - 1, 1
+                    st["shelf_x"][sid - 1], st["shelf_y"][sid - 1] = gx, gy - 1
+                    refenv.ref_set_state(env, wh, st)
+                    inject_step.append(t)
+                    inject_state.append({k: np.array(v) for k, v in st.items() if k != "rng"})
+                    actions[t, a, 0] = -1  # marker: forced FORWARD below
+        acts = rs.choice(5, size=n, p=probs).astype(np.int8)
+        forced = np.where(actions[t, :, 0] == -1)[0]
+        acts[forced] = 1
+        actions[t, :, 0] = acts
+        if mb:
+            actions[t, :, 1:] = rs.integers(0, 2, size=(n, mb))
+            ref_actions = [list(map(int, row)) for row in actions[t]]
+        else:
+            ref_actions = [int(a) for a in acts]
+        obs, rew, done, _, _ = env.step(ref_actions)
+        o = np.stack(obs).astype(np.float32)
+        obs_sha.append(np.frombuffer(hashlib.sha256(o.tobytes()).digest(), np.uint8))
+        if t < 8 or t % 97 == 0:
+            obs_keep[t] = o
+        st = refenv.ref_state(env)
+        for k in STATE_KEYS:
+            states[k].append(st[k])
+        rewards.append(np.asarray(rew, np.float64))
+        dones.append(bool(done))
+        if done:
+            s2 = int(rs.integers(1 << 30)) if (reseed_on_done and rs.random() < 0.5) else -1
+            obs, _ = env.reset(seed=None if s2 < 0 else s2)
+            resets.append((t, s2))
+            st = refenv.ref_state(env)
+            # state right after the reset, stored under a separate key family
+            inject_step.append(-(t + 1))  # negative: "expected state after reset following step t"
+            inject_state.append({k: np.array(v) for k, v in st.items()})
+            obs_keep[-(t + 1)] = np.stack(obs).astype(np.float32)
+    out = dict(
+        kwargs=json.dumps({k: (v if not hasattr(v, "value") else v.value) for k, v in kwargs.items()}),
+        seed=seed, actions=actions, obs0=obs0, rewards=np.stack(rewards), dones=np.array(dones),
+        obs_sha=np.stack(obs_sha), obs_keep_steps=np.array(sorted(obs_keep)), resets=np.array(resets, np.int64).reshape(-1, 2),
+        highways=np.asarray(env.highways, np.uint8), goals=np.asarray(env.goals, np.int32),
+        inject_steps=np.array(inject_step, np.int64))
+    for t in sorted(obs_keep):
+        out[f"obs_{t}"] = obs_keep[t]
+    for k in STATE_KEYS:
+        out[f"st0_{k}"] = st0[k]
+        out[f"st_{k}"] = np.stack(states[k]).astype(np.uint32 if k == "rng" else np.int16)
+    for i, stt in enumerate(inject_state):
+        for k, v in stt.items():
+            out[f"inj{i}_{k}"] = v.astype(np.uint32 if k == "rng" else np.int16)
+    path = os.path.join(HERE, f"traj_{name}.npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: {steps} steps, {len(inject_step)} injections/resets, {sum(map(float, np.stack(rewards).sum(1) > 0))} rewarded steps, "
+          f"{os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def known_answers(gym):
+    """SHA-256 over obs0 then per step obs || rewards(f64) || done, registered ids, seed 0."""
+    out = {}
+    for id_, extra in [("rware-tiny-2ag-v2", {}), ("rware-tiny-4ag-v2", {}), ("rware-small-4ag-v2", {}),
+                       ("rware-medium-8ag-hard-v2", {}), ("rware-large-16ag-v2", {"sensor_range": 2})]:
+        env = gym.make(id_, **extra)
+        obs, _ = env.reset(seed=0)
+        h = hashlib.sha256(np.stack(obs).astype(np.float32).tobytes())
+        n = env.n_agents
+        acts = np.random.default_rng(12345).integers(0, 5, size=(500, n))
+        total = 0.0
+        for t in range(500):
+            obs, rew, done, _, _ = env.step([int(a) for a in acts[t]])
+            total += float(np.sum(rew))
+            h.update(np.stack(obs).astype(np.float32).tobytes() + np.asarray(rew, np.float64).tobytes() + bytes([done]))
+        st = refenv.ref_state(env)
+        out[id_ + ("" if not extra else "+sensor_range=2")] = dict(
+            sha256=h.hexdigest(), extra=extra, reward_sum=total,
+            final_agents=[[int(st["agent_x"][i]), int(st["agent_y"][i]), int(st["agent_dir"][i]), int(st["agent_carry"][i])]
+                          for i in range(n)])
+        print(id_, h.hexdigest())
+    with open(os.path.join(HERE, "known_answers.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
+def layouts(wh):
+    """Highway bitmaps / goals / grid sizes of the registered sizes plus a few odd ones (warehouse.py:294-350)."""
+    out = {}
+    for cols, rows, height in [(3, 1, 8), (3, 2, 8), (5, 2, 8), (5, 3, 8), (1, 1, 1), (7, 4, 3), (9, 1, 15), (3, 3, 8)]:
+        env = wh.Warehouse(cols, height, rows, 1, 0, 1, 1, None, None, wh.RewardType.GLOBAL)
+        out[f"{cols}_{rows}_{height}_highways"] = np.asarray(env.highways, np.uint8)
+        out[f"{cols}_{rows}_{height}_goals"] = np.asarray(env.goals, np.int32)
+    np.savez_compressed(os.path.join(HERE, "layouts.npz"), **out)
+
+
+def main():
+    gym, wh = refenv.load_reference()
+    G, I, T = 0, 1, 2
+    record(wh, "tiny2_indiv", kw(3, 8, 1, 2, 0, 1, 2, None, 500, I), 700, 0.3, 9, seed=0)
+    record(wh, "tiny4_indiv", kw(3, 8, 1, 4, 0, 1, 4, None, 500, I), 1100, 0.3, 7, seed=1)
+    record(wh, "small4_global", kw(3, 8, 2, 4, 0, 1, 4, 40, 500, G), 700, 0.5, 5, seed=2)
+    record(wh, "medium8_hard_twostage", kw(5, 8, 2, 8, 0, 1, 4, 60, 500, T), 800, 0.68, 5, seed=3)
+    record(wh, "large16_r2", kw(5, 8, 3, 16, 0, 2, 16, None, 500, I), 700, 0.68, 9, seed=4)
+    record(wh, "tiny19_twostage", kw(3, 8, 1, 19, 0, 1, 9, 40, 300, T), 900, 0.68, 5, seed=5)
+    record(wh, "tiny10_msg3_norm", kw(3, 8, 1, 10, 3, 1, 5, None, 200, G, normalised_coordinates=True), 500, 0.6, 6, seed=6)
+    record(wh, "dense8_h2", kw(3, 2, 1, 8, 0, 1, 3, None, 200, I), 700, 0.75, 4, seed=7)
+    record(wh, "custom_layout", dict(kw(1, 1, 1, 5, 1, 2, 3, 30, 150, T),
+                                     layout="..x..x..\n.xx..xx.\n........\n.x.gg.x.\n..x..x.."), 500, 0.6, 3, seed=8)
+    record(wh, "tiny1_hard_r0", kw(3, 8, 1, 1, 0, 1, 0, None, 100, I), 250, 0.5, 0, seed=9)
+    known_answers(gym)
+    layouts(wh)
+
+
+if __name__ == "__main__":
+    main()

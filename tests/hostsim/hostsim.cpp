@@ -1,0 +1,178 @@
+// hostsim.cpp -- TEST-ONLY host twin of the fused CUDA kernel.
+//
+// Compiles the product's per-world logic (robotic-warehouse_b200/csrc/rw_logic.cuh, the same source the GPU runs)
+// with g++ and drives it over the same packed tile layout, emulating what one warp does for its 32 worlds with a
+// plain loop over lanes.  It exists so that the agent-centric resolver, the reset sampler and the observation
+// writer can be debugged against the oracle on machines without a GPU (`pytest -m "not gpu"`).  It is NOT a CPU
+// fallback: nothing in the product package loads it, and the product raises when the CUDA library is missing.
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../robotic-warehouse_b200/csrc/rw_host_layout.h"
+#include "../../robotic-warehouse_b200/csrc/rw_logic.cuh"
+
+struct Sim {
+    RwParams p;
+    std::vector<uint8_t> highway;
+    std::vector<uint16_t> home;
+    std::vector<float> nx, ny;
+    std::vector<int32_t> state;
+    std::vector<uint32_t> rng;
+    unsigned long long err = 0;
+    // one warp's shared memory
+    std::vector<uint8_t> smem;
+};
+
+static RwLane lane_view(Sim *s, int lane) {
+    const RwParams &p = s->p;
+    uint8_t *wb = s->smem.data();
+    RwLane l;
+    l.tile = reinterpret_cast<int32_t *>(wb + p.sm_tile) + lane;
+    l.gs = reinterpret_cast<uint16_t *>(wb + p.sm_grid + (size_t)lane * p.grid_env_stride);
+    l.ga = wb + p.sm_grid + (size_t)lane * p.grid_env_stride + p.ga_off;
+    l.sc = reinterpret_cast<uint32_t *>(wb + p.sm_scratch) + lane;
+    return l;
+}
+
+extern "C" {
+
+Sim *sim_create(const rw_config *cfg, int64_t num_envs) {
+    Sim *s = new Sim();
+    int cells = cfg->grid_h * cfg->grid_w;
+    s->highway.assign(cfg->highways, cfg->highways + cells);
+    for (int c = 0; c < cells; c++)
+        if (!cfg->highways[c]) s->home.push_back((uint16_t)c);
+    rw_fill_params(s->p, *cfg, num_envs, (int)s->home.size());
+    RwParams &p = s->p;
+    s->nx.resize(p.W);
+    s->ny.resize(p.H);
+    for (int x = 0; x < p.W; x++) s->nx[x] = p.W > 1 ? (float)((double)x / (double)(p.W - 1)) : 0.0f;
+    for (int y = 0; y < p.H; y++) s->ny[y] = p.H > 1 ? (float)((double)y / (double)(p.H - 1)) : 0.0f;
+    s->state.assign((size_t)p.tiles * p.nw * RW_TILE, 0);
+    s->rng.assign((size_t)RW_RNG_WORDS * p.E_pad, 0);
+    s->smem.assign((size_t)p.sm_warp_bytes, 0);
+    p.highway = s->highway.data();
+    p.home_cell = s->home.data();
+    p.normx = s->nx.data();
+    p.normy = s->ny.data();
+    p.state = s->state.data();
+    p.rng = s->rng.data();
+    p.err_count = &s->err;
+    return s;
+}
+
+void sim_destroy(Sim *s) { delete s; }
+int sim_obs_len(Sim *s) { return s->p.L; }
+int sim_n_shelves(Sim *s) { return s->p.S; }
+void sim_set_auto_reset(Sim *s, int on) { s->p.auto_reset = on; }
+long long sim_error_count(Sim *s) { return (long long)s->err; }
+
+void sim_seed(Sim *s, const uint64_t *seeds, const uint8_t *mask) {
+    uint32_t w[RW_RNG_WORDS];
+    for (int64_t e = 0; e < s->p.E; e++) {
+        if (mask && !mask[e]) continue;
+        rw_seed_words(seeds[e], w);
+        for (int k = 0; k < RW_RNG_WORDS; k++) s->rng[(size_t)k * s->p.E_pad + e] = w[k];
+    }
+}
+
+// mode 0 step, 1 obs, 2 reset -- mirrors rw_main_kernel<MODE>
+void sim_run(Sim *s, int mode, const int32_t *actions, float *obs, float *reward, uint8_t *done, const uint8_t *mask) {
+    const RwParams &p = s->p;
+    for (int tile = 0; tile < p.tiles; tile++) {
+        uint8_t *wb = s->smem.data();
+        int32_t *tilew = reinterpret_cast<int32_t *>(wb + p.sm_tile);
+        int32_t *gtile = p.state + (size_t)tile * p.nw * RW_TILE;
+        memcpy(tilew, gtile, (size_t)p.nw * RW_TILE * 4);
+        memset(wb + p.sm_grid, 0, (size_t)p.grid_env_stride * RW_TILE);
+        for (int lane = 0; lane < RW_TILE; lane++) {
+            int64_t env = (int64_t)tile * RW_TILE + lane;
+            if (env >= p.E) continue;
+            RwLane l = lane_view(s, lane);
+            if (mode == 2 && (!mask || mask[env])) rw_reset_lane(p, l, env);
+            bool overlap = rw_build_grid(p, l);
+            if (mode == 0) {
+                bool d = rw_step_lane(p, l, actions + env * p.n * p.A, reward + env * p.n, env, overlap);
+                done[env] = d;
+                if (d && p.auto_reset) {
+                    rw_reset_lane(p, l, env);
+                    memset(l.gs, 0, (size_t)p.grid_env_stride);
+                    rw_build_grid(p, l);
+                }
+            }
+        }
+        if (mode != 1) memcpy(gtile, tilew, (size_t)p.nw * RW_TILE * 4);
+        if (obs)
+            for (int lane = 0; lane < RW_TILE; lane++) {
+                int64_t env = (int64_t)tile * RW_TILE + lane;
+                if (env >= p.E) continue;
+                RwLane l = lane_view(s, lane);
+                for (int a = 0; a < p.n; a++) rw_obs_agent(p, l, a, obs + (env * p.n + a) * p.L);
+            }
+    }
+}
+
+// plain-array state access, same field conventions as rw_state_view (host pointers here)
+void sim_get_state(Sim *s, const rw_state_view *v) {
+    const RwParams &p = s->p;
+    for (int64_t env = 0; env < p.E; env++) {
+        int32_t *t = p.state + (size_t)(env >> 5) * p.nw * RW_TILE + (env & 31);
+        RwLane l{t, nullptr, nullptr, nullptr};
+        for (int i = 0; i < p.n; i++) {
+            uint32_t aw = rw_agent(p, l, i);
+            if (v->agent_x) v->agent_x[env * p.n + i] = rw_ax(aw);
+            if (v->agent_y) v->agent_y[env * p.n + i] = rw_ay(aw);
+            if (v->agent_dir) v->agent_dir[env * p.n + i] = rw_adir(aw);
+            if (v->agent_carry) v->agent_carry[env * p.n + i] = rw_acarry(aw);
+            if (v->agent_has_delivered) v->agent_has_delivered[env * p.n + i] = rw_adeliv(aw);
+            if (v->agent_msg && p.msg_bits)
+                for (int b = 0; b < p.msg_bits; b++)
+                    v->agent_msg[(env * p.n + i) * p.msg_bits + b] = ((uint32_t)t[(p.w_msg + i) * RW_TILE] >> b) & 1u;
+        }
+        for (int k = 0; k < p.S; k++) {
+            int c = rw_shelf_cell(p, l, k);
+            if (v->shelf_x) v->shelf_x[env * p.S + k] = c % p.W;
+            if (v->shelf_y) v->shelf_y[env * p.S + k] = c / p.W;
+        }
+        if (v->queue)
+            for (int q = 0; q < p.R; q++) v->queue[env * p.R + q] = rw_queue(p, l, q);
+        if (v->cur_steps) v->cur_steps[env] = t[p.w_steps * RW_TILE];
+        if (v->cur_inactive) v->cur_inactive[env] = t[p.w_inact * RW_TILE];
+        if (v->rng)
+            for (int w = 0; w < RW_RNG_WORDS; w++) v->rng[env * RW_RNG_WORDS + w] = p.rng[(size_t)w * p.E_pad + env];
+    }
+}
+
+void sim_set_state(Sim *s, const rw_state_view *v) {
+    const RwParams &p = s->p;
+    for (int64_t env = 0; env < p.E; env++) {
+        int32_t *t = p.state + (size_t)(env >> 5) * p.nw * RW_TILE + (env & 31);
+        RwLane l{t, nullptr, nullptr, nullptr};
+        for (int i = 0; i < p.n; i++) {
+            uint32_t aw = rw_agent(p, l, i);
+            int x = v->agent_x ? v->agent_x[env * p.n + i] : rw_ax(aw);
+            int y = v->agent_y ? v->agent_y[env * p.n + i] : rw_ay(aw);
+            int d = v->agent_dir ? v->agent_dir[env * p.n + i] : rw_adir(aw);
+            int c = v->agent_carry ? v->agent_carry[env * p.n + i] : rw_acarry(aw);
+            int hd = v->agent_has_delivered ? (v->agent_has_delivered[env * p.n + i] != 0) : rw_adeliv(aw);
+            rw_set_agent(p, l, i, rw_apack(x & 0xff, y & 0xff, d & 3, hd, c & 0x1fff));
+            if (v->agent_msg && p.msg_bits) {
+                uint32_t bits = 0;
+                for (int b = 0; b < p.msg_bits; b++) bits |= (uint32_t)(v->agent_msg[(env * p.n + i) * p.msg_bits + b] & 1) << b;
+                t[(p.w_msg + i) * RW_TILE] = (int32_t)bits;
+            }
+        }
+        if (v->shelf_x && v->shelf_y)
+            for (int k = 0; k < p.S; k++) rw_set_shelf_cell(p, l, k, v->shelf_y[env * p.S + k] * p.W + v->shelf_x[env * p.S + k]);
+        if (v->queue)
+            for (int q = 0; q < p.R; q++) rw_set_queue(p, l, q, v->queue[env * p.R + q]);
+        if (v->cur_steps) t[p.w_steps * RW_TILE] = v->cur_steps[env];
+        if (v->cur_inactive) t[p.w_inact * RW_TILE] = v->cur_inactive[env];
+        if (v->rng)
+            for (int w = 0; w < RW_RNG_WORDS; w++) p.rng[(size_t)w * p.E_pad + env] = v->rng[env * RW_RNG_WORDS + w];
+    }
+}
+
+}  // extern "C"
