@@ -109,18 +109,22 @@ static int create_impl(rw_handle *h, const rw_config *cfg, int64_t num_envs, int
     if (p.sm_warp_bytes > smem_cap)
         return fail(h, RW_EINVAL, "configuration needs " + std::to_string(p.sm_warp_bytes) +
                                       " B of shared memory per warp, device allows " + std::to_string(smem_cap));
-    {   // warps per CTA: keep CTAs small so that several fit per SM; env var override for tuning
-        int per_sm = (int)prop.sharedMemPerMultiprocessor / (p.sm_warp_bytes + 1024);
-        if (per_sm < 1) per_sm = 1;
-        int wpc = per_sm >= 8 ? 4 : (per_sm >= 4 ? 2 : 1);
+    {   // warps (= tiles) per CTA: as many as the shared memory of one SM holds, so that a CTA fills an SM and, when the
+        // batch allows, the whole launch is a single wave; small batches spread over the SMs instead
+        int fit = (smem_cap - 1024) / p.sm_warp_bytes;
+        if (fit > 16) fit = 16;
+        if (fit < 1) fit = 1;
+        int spread = (p.tiles + prop.multiProcessorCount - 1) / prop.multiProcessorCount;
+        int wpc = spread < fit ? spread : fit;
         const char *ev = getenv("RWARE_B200_WARPS_PER_CTA");
         if (ev) wpc = atoi(ev);
         if (wpc < 1) wpc = 1;
-        if (wpc > 8) wpc = 8;
+        if (wpc > 16) wpc = 16;
         while (wpc > 1 && wpc * p.sm_warp_bytes > smem_cap) wpc--;
         p.warps_per_cta = wpc;
     }
-    CK(rw_configure_kernels(p.sm_warp_bytes * p.warps_per_cta));
+    if (getenv("RWARE_B200_FORCE_DYNAMIC")) rw_force_dynamic_kernels(atoi(getenv("RWARE_B200_FORCE_DYNAMIC")) != 0);
+    CK(rw_configure_kernels(p, p.sm_warp_bytes * p.warps_per_cta));
 
     // static tables
     std::vector<float> nx(W), ny(H);

@@ -28,7 +28,14 @@
 #define RW_MAX_MSG_BITS 16
 #define RW_RNG_WORDS 10
 #define RW_MAX_SHELVES 8191
-#define RW_REQ_BIT 0x8000u
+// occupancy grid byte (shared memory, rebuilt every step): bits 0-5 id of the agent standing on the cell (0 = none),
+// bit 6 a shelf is on the cell (standing or carried), bit 7 that shelf is in the request queue
+#define RW_G_AGENT 0x3fu
+#define RW_G_SHELF 0x40u
+#define RW_G_REQ 0x80u
+// bit 31 of the w_inact word: two shelves share a cell somewhere in this world (only reachable through state
+// injection); such worlds take the literal "_recalc_grid" slow path
+#define RW_OVERLAP_BIT 0x80000000u
 
 #define RW_ACT_NOOP 0
 #define RW_ACT_FORWARD 1
@@ -62,8 +69,8 @@ struct RwParams {
     int32_t tiles;
     // per-warp shared memory carve-up (byte offsets from the warp's base)
     int32_t sm_tile, sm_grid, sm_scratch, sm_obs, sm_bar, sm_warp_bytes;
-    int32_t grid_env_stride;  // bytes per world: uint16 shelf layer [cells] then uint8 agent layer [cells]
-    int32_t ga_off;
+    int32_t grid_env_stride;  // bytes per world of the occupancy grid: one byte per cell (see RW_G_*)
+    int32_t ga_off;           // unused (kept for layout stability)
     int32_t obs_chunk_envs, obs_chunk_bytes, obs_nbuf, obs_env_bytes;
     int32_t warps_per_cta;
     RwDiv divW, divN;
@@ -71,6 +78,7 @@ struct RwParams {
 };
 
 RW_HD uint32_t rw_div(uint32_t x, const RwDiv &dv) {
+    if (dv.magic == 0) return x;  // d == 1 (ceil(2^32 / 1) does not fit 32 bits)
 #if defined(__CUDA_ARCH__)
     return __umulhi(x, dv.magic);
 #else
@@ -91,9 +99,30 @@ RW_HD uint32_t rw_apack(int x, int y, int dir, int deliv, int carry) {
 // per-world view used by the lane logic; `tile` already points at this world's lane
 struct RwLane {
     int32_t *tile;   // word w at tile[w * RW_TILE]
-    uint16_t *gs;    // shelf layer: id | RW_REQ_BIT when requested
-    uint8_t *ga;     // agent layer: id or 0
+    uint8_t *g;      // occupancy grid of this world, one byte per cell (RW_G_*)
     uint32_t *sc;    // scratch, entry k at sc[k * RW_TILE]; 2*n entries
+};
+
+// Compile-time specialisation of the layout-dependent constants.  RwDynamic reads them from RwParams; RwStatic<...>
+// bakes in the registered warehouse sizes so that the cell loops unroll and the index arithmetic folds.
+struct RwDynamic {
+    static constexpr bool is_static = false;
+    RW_HD static int H(const RwParams &p) { return p.H; }
+    RW_HD static int W(const RwParams &p) { return p.W; }
+    RW_HD static int S(const RwParams &p) { return p.S; }
+    RW_HD static int r(const RwParams &p) { return p.r; }
+    RW_HD static int mb(const RwParams &p) { return p.msg_bits; }
+    RW_HD static uint32_t div_w(const RwParams &p, uint32_t c) { return rw_div(c, p.divW); }
+};
+template <int H_, int W_, int S_, int R_, int MB_>
+struct RwStatic {
+    static constexpr bool is_static = true;
+    RW_HD static int H(const RwParams &) { return H_; }
+    RW_HD static int W(const RwParams &) { return W_; }
+    RW_HD static int S(const RwParams &) { return S_; }
+    RW_HD static int r(const RwParams &) { return R_; }
+    RW_HD static int mb(const RwParams &) { return MB_; }
+    RW_HD static uint32_t div_w(const RwParams &, uint32_t c) { return c / (uint32_t)W_; }
 };
 
 RW_HD uint32_t rw_agent(const RwParams &p, const RwLane &l, int i) { return (uint32_t)l.tile[(p.w_agent + i) * RW_TILE]; }

@@ -2,6 +2,7 @@
 // twin (tests/hostsim): the packed tile layout / shared-memory carve-up for a configuration, and the
 // numpy-compatible seeding SeedSequence(seed) -> PCG64 (numpy/random/bit_generator.pyx, pcg64.h).
 #pragma once
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/rware_b200.h"
@@ -92,10 +93,10 @@ static inline void rw_fill_params(RwParams &p, const rw_config &c, int64_t num_e
     p.divN = rw_make_div((uint32_t)n);
 
     // shared memory carve-up per warp
-    int stride = rw_round_up(3 * cells, 4);
+    int stride = rw_round_up(cells, 4);       // one byte per cell
     if (((stride / 4) & 1) == 0) stride += 4;  // odd word stride: same-cell accesses of the 32 lanes hit 32 banks
     p.grid_env_stride = stride;
-    p.ga_off = 2 * cells;
+    p.ga_off = 0;
     p.obs_env_bytes = n * p.L * 4;
     // chunk of C worlds per staged observation block: C*n lanes of work, C*n*L*4 bytes, 16-byte multiple for the TMA
     {
@@ -113,13 +114,22 @@ static inline void rw_fill_params(RwParams &p, const rw_config &c, int64_t num_e
         }
         p.obs_chunk_envs = best;
         p.obs_chunk_bytes = best * p.obs_env_bytes;
-        p.obs_nbuf = (RW_TILE / best > 1) ? 2 : 1;
+        // one staging buffer by default: shared memory per warp decides how many tiles are resident per SM, which matters
+        // more than overlapping a warp's own TMA store with its next chunk (other warps cover it)
+        p.obs_nbuf = 1;
+        const char *ev = getenv("RWARE_B200_OBS_NBUF");
+        if (ev && atoi(ev) == 2 && RW_TILE / best > 1) p.obs_nbuf = 2;
     }
     int off = 0;
     p.sm_tile = off; off += p.nw * RW_TILE * 4; off = rw_round_up(off, 128);
     p.sm_grid = off; off += stride * RW_TILE; off = rw_round_up(off, 16);
-    p.sm_scratch = off; off += 2 * n * RW_TILE * 4; off = rw_round_up(off, 128);
-    p.sm_obs = off; off += rw_round_up(p.obs_chunk_bytes, 128) * p.obs_nbuf;
+    // the resolver scratch (2n words per world) is dead before the observation gather starts: it aliases the staging buffer
+    p.sm_scratch = off;
+    p.sm_obs = off;
+    {
+        int obs_bytes = rw_round_up(p.obs_chunk_bytes, 128) * p.obs_nbuf, scratch_bytes = 2 * n * RW_TILE * 4;
+        off += obs_bytes > scratch_bytes ? obs_bytes : scratch_bytes;
+    }
     p.sm_bar = off; off += 8;
     p.sm_warp_bytes = rw_round_up(off, 128);
 

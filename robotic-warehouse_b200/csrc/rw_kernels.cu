@@ -57,8 +57,8 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
 // ---------------------------------------------------------------- the fused kernel
-template <int MODE>
-__global__ void __launch_bounds__(256) rw_main_kernel(const __grid_constant__ RwParams p, const int32_t *__restrict__ actions,
+template <int MODE, class C>
+__global__ void __launch_bounds__(512) rw_main_kernel(const __grid_constant__ RwParams p, const int32_t *__restrict__ actions,
                                                       float *__restrict__ obs, float *__restrict__ reward,
                                                       uint8_t *__restrict__ done, const uint8_t *__restrict__ mask) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -94,22 +94,21 @@ __global__ void __launch_bounds__(256) rw_main_kernel(const __grid_constant__ Rw
     const bool valid = env < p.E;
     RwLane l;
     l.tile = tilew + lane;
-    l.gs = reinterpret_cast<uint16_t *>(grid + (size_t)lane * p.grid_env_stride);
-    l.ga = grid + (size_t)lane * p.grid_env_stride + p.ga_off;
+    l.g = grid + (size_t)lane * p.grid_env_stride;
     l.sc = scratch + lane;
     if (valid) {
         if (MODE == RW_MODE_RESET) {
-            if (mask == nullptr || mask[env]) rw_reset_lane(p, l, env);
+            if (mask == nullptr || mask[env]) rw_reset_lane<C>(p, l, env);
         }
-        const bool overlap = rw_build_grid(p, l);
+        rw_build_grid<C>(p, l);
         if (MODE == RW_MODE_STEP) {
-            bool d = rw_step_lane(p, l, actions + env * p.n * p.A, reward + env * p.n, env, overlap);
+            bool d = rw_step_lane<C>(p, l, actions + env * p.n * p.A, reward + env * p.n, env);
             done[env] = d ? 1 : 0;
             if (d && p.auto_reset) {
-                rw_reset_lane(p, l, env);
-                uint32_t *gz = reinterpret_cast<uint32_t *>(l.gs);
+                rw_reset_lane<C>(p, l, env);
+                uint32_t *gz = reinterpret_cast<uint32_t *>(l.g);
                 for (int i = 0; i < (p.grid_env_stride >> 2); i++) gz[i] = 0;
-                rw_build_grid(p, l);
+                rw_build_grid<C>(p, l);
             }
         }
     }
@@ -127,12 +126,12 @@ __global__ void __launch_bounds__(256) rw_main_kernel(const __grid_constant__ Rw
 
     // ---- 4. observation gather: one lane per (world, agent); chunks of C worlds staged in shared memory
     if (obs != nullptr) {
-        const int C = p.obs_chunk_envs, n = p.n, L = p.L;
-        const int items = C * n;
+        const int CH = p.obs_chunk_envs, n = p.n, L = p.L;
+        const int items = CH * n;
         const int64_t tile_env0 = (int64_t)tile * RW_TILE;
         const bool full = tile_env0 + RW_TILE <= p.E;
         int chunk = 0;
-        for (int c0 = 0; c0 < RW_TILE; c0 += C, chunk++) {
+        for (int c0 = 0; c0 < RW_TILE; c0 += CH, chunk++) {
             float *buf = obuf + (size_t)(chunk % p.obs_nbuf) * (p.obs_chunk_bytes >> 2);
             if (chunk >= p.obs_nbuf) {  // the bulk store that last read this buffer must have drained it
                 if (lane == 0) {
@@ -147,14 +146,13 @@ __global__ void __launch_bounds__(256) rw_main_kernel(const __grid_constant__ Rw
                 if (e < RW_TILE && tile_env0 + e < p.E) {
                     RwLane le;
                     le.tile = tilew + e;
-                    le.gs = reinterpret_cast<uint16_t *>(grid + (size_t)e * p.grid_env_stride);
-                    le.ga = grid + (size_t)e * p.grid_env_stride + p.ga_off;
+                    le.g = grid + (size_t)e * p.grid_env_stride;
                     le.sc = nullptr;
-                    rw_obs_agent(p, le, a, buf + (size_t)it * L);
+                    rw_obs_agent<C>(p, le, a, buf + (size_t)it * L);
                 }
             }
             float *gdst = obs + (tile_env0 + c0) * (int64_t)n * L;
-            if (full && p.obs_bulk && c0 + C <= RW_TILE) {
+            if (full && p.obs_bulk && c0 + CH <= RW_TILE) {
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
@@ -164,7 +162,7 @@ __global__ void __launch_bounds__(256) rw_main_kernel(const __grid_constant__ Rw
             } else {  // ragged tail / unaligned geometry: plain coalesced stores
                 __syncwarp();
                 int64_t envs_here = p.E - (tile_env0 + c0);
-                if (envs_here > C) envs_here = C;
+                if (envs_here > CH) envs_here = CH;
                 if (envs_here > RW_TILE - c0) envs_here = RW_TILE - c0;
                 const int nf = (int)(envs_here > 0 ? envs_here : 0) * n * L;
                 for (int i = lane; i < nf; i += 32) gdst[i] = buf[i];
@@ -181,7 +179,7 @@ __global__ void rw_get_state_kernel(const RwParams p, const rw_state_view v) {
     int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= p.E) return;
     int32_t *t = p.state + (size_t)(env >> 5) * p.nw * RW_TILE + (env & 31);
-    RwLane l{t, nullptr, nullptr, nullptr};
+    RwLane l{t, nullptr, nullptr};
     for (int i = 0; i < p.n; i++) {
         uint32_t aw = rw_agent(p, l, i);
         if (v.agent_x) v.agent_x[env * p.n + i] = rw_ax(aw);
@@ -203,7 +201,7 @@ __global__ void rw_get_state_kernel(const RwParams p, const rw_state_view v) {
     if (v.queue)
         for (int q = 0; q < p.R; q++) v.queue[env * p.R + q] = rw_queue(p, l, q);
     if (v.cur_steps) v.cur_steps[env] = t[p.w_steps * RW_TILE];
-    if (v.cur_inactive) v.cur_inactive[env] = t[p.w_inact * RW_TILE];
+    if (v.cur_inactive) v.cur_inactive[env] = (int32_t)((uint32_t)t[p.w_inact * RW_TILE] & ~RW_OVERLAP_BIT);
     if (v.rng)
         for (int w = 0; w < RW_RNG_WORDS; w++) v.rng[env * RW_RNG_WORDS + w] = p.rng[(size_t)w * p.E_pad + env];
 }
@@ -212,7 +210,7 @@ __global__ void rw_set_state_kernel(const RwParams p, const rw_state_view v) {
     int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= p.E) return;
     int32_t *t = p.state + (size_t)(env >> 5) * p.nw * RW_TILE + (env & 31);
-    RwLane l{t, nullptr, nullptr, nullptr};
+    RwLane l{t, nullptr, nullptr};
     for (int i = 0; i < p.n; i++) {
         uint32_t aw = rw_agent(p, l, i);
         int x = v.agent_x ? v.agent_x[env * p.n + i] : rw_ax(aw);
@@ -232,7 +230,15 @@ __global__ void rw_set_state_kernel(const RwParams p, const rw_state_view v) {
     if (v.queue)
         for (int q = 0; q < p.R; q++) rw_set_queue(p, l, q, v.queue[env * p.R + q]);
     if (v.cur_steps) t[p.w_steps * RW_TILE] = v.cur_steps[env];
-    if (v.cur_inactive) t[p.w_inact * RW_TILE] = v.cur_inactive[env];
+    if (v.cur_inactive) t[p.w_inact * RW_TILE] = v.cur_inactive[env] & 0x7fffffff;
+    // flag worlds where two shelves share a cell (cold path, O(S^2)); see RW_OVERLAP_BIT
+    bool overlap = false;
+    for (int k = 1; k < p.S && !overlap; k++) {
+        int c = rw_shelf_cell(p, l, k);
+        for (int j = 0; j < k; j++) overlap |= (rw_shelf_cell(p, l, j) == c);
+    }
+    uint32_t wi = (uint32_t)t[p.w_inact * RW_TILE] & ~RW_OVERLAP_BIT;
+    t[p.w_inact * RW_TILE] = (int32_t)(wi | (overlap ? RW_OVERLAP_BIT : 0u));
     if (v.rng)
         for (int w = 0; w < RW_RNG_WORDS; w++) p.rng[(size_t)w * p.E_pad + env] = v.rng[env * RW_RNG_WORDS + w];
 }
@@ -257,13 +263,45 @@ __global__ void rw_random_actions_kernel(const RwParams p, int32_t *__restrict__
 }
 
 // ---------------------------------------------------------------- launch wrappers
-cudaError_t rw_configure_kernels(int smem_bytes_per_cta) {
-    cudaError_t e;
-    e = cudaFuncSetAttribute(rw_main_kernel<RW_MODE_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_per_cta);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(rw_main_kernel<RW_MODE_OBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_per_cta);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(rw_main_kernel<RW_MODE_RESET>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_per_cta);
+// Static specialisations: the four registered warehouse sizes (rware/__init__.py:7-12 with column_height 8) at
+// sensor range 1 and 2 without message bits; every other geometry runs the RwDynamic instantiation.
+#define RW_STATIC_CONFIGS(X) \
+    X(11, 10, 32, 1) X(20, 10, 80, 1) X(20, 16, 144, 1) X(29, 16, 224, 1) \
+    X(11, 10, 32, 2) X(20, 10, 80, 2) X(20, 16, 144, 2) X(29, 16, 224, 2)
+
+typedef void (*rw_kernel_fn)(const RwParams, const int32_t *, float *, float *, uint8_t *, const uint8_t *);
+
+template <class C>
+static rw_kernel_fn kernel_for_mode(RwMode mode) {
+    switch (mode) {
+        case RW_MODE_STEP: return rw_main_kernel<RW_MODE_STEP, C>;
+        case RW_MODE_OBS: return rw_main_kernel<RW_MODE_OBS, C>;
+        default: return rw_main_kernel<RW_MODE_RESET, C>;
+    }
+}
+
+static rw_kernel_fn select_kernel(RwMode mode, const RwParams &p, bool force_dynamic) {
+    if (!force_dynamic && p.msg_bits == 0) {
+#define X(H_, W_, S_, R_) \
+    if (p.H == H_ && p.W == W_ && p.S == S_ && p.r == R_) return kernel_for_mode<RwStatic<H_, W_, S_, R_, 0>>(mode);
+        RW_STATIC_CONFIGS(X)
+#undef X
+    }
+    return kernel_for_mode<RwDynamic>(mode);
+}
+
+static bool g_force_dynamic = false;
+void rw_force_dynamic_kernels(bool on) { g_force_dynamic = on; }
+
+cudaError_t rw_configure_kernels(const RwParams &p, int smem_bytes_per_cta) {
+    for (int m = 0; m < 3; m++) {
+        for (int dyn = 0; dyn < 2; dyn++) {
+            cudaError_t e = cudaFuncSetAttribute((const void *)select_kernel((RwMode)m, p, dyn != 0),
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_per_cta);
+            if (e != cudaSuccess) return e;
+        }
+    }
+    return cudaSuccess;
 }
 
 cudaError_t rw_launch_main(RwMode mode, const RwParams &p, const int32_t *actions, float *obs, float *reward, uint8_t *done,
@@ -271,11 +309,7 @@ cudaError_t rw_launch_main(RwMode mode, const RwParams &p, const int32_t *action
     dim3 block(32 * p.warps_per_cta);
     dim3 grid((p.tiles + p.warps_per_cta - 1) / p.warps_per_cta);
     size_t smem = (size_t)p.sm_warp_bytes * p.warps_per_cta;
-    switch (mode) {
-        case RW_MODE_STEP: rw_main_kernel<RW_MODE_STEP><<<grid, block, smem, stream>>>(p, actions, obs, reward, done, mask); break;
-        case RW_MODE_OBS: rw_main_kernel<RW_MODE_OBS><<<grid, block, smem, stream>>>(p, actions, obs, reward, done, mask); break;
-        case RW_MODE_RESET: rw_main_kernel<RW_MODE_RESET><<<grid, block, smem, stream>>>(p, actions, obs, reward, done, mask); break;
-    }
+    select_kernel(mode, p, g_force_dynamic)<<<grid, block, smem, stream>>>(p, actions, obs, reward, done, mask);
     return cudaGetLastError();
 }
 

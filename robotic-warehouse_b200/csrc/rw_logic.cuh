@@ -87,35 +87,78 @@ RW_HD uint32_t rw_bounded(RwPcg &g, uint32_t rng) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// occupancy grids (what ref:749-755 _recalc_grid keeps in self.grid), rebuilt in shared memory per step.
-// Precondition: this world's grid region is zero.  Returns true when two shelves share a cell (impossible in
-// play, reachable through state injection): the reference's grid then shows the highest id, and the step falls
-// back to a full rebuild after the moves instead of the incremental update.
-RW_HD bool rw_build_grid(const RwParams &p, const RwLane &l) {
-    bool overlap = false;
-    for (int k = 0; k < p.S; k++) {
-        int c = rw_shelf_cell(p, l, k);
-        overlap |= (l.gs[c] != 0);
-        l.gs[c] = (uint16_t)(k + 1);
+// occupancy grid (what ref:749-755 _recalc_grid keeps in self.grid), rebuilt in shared memory every step as one
+// byte per cell.  Precondition: this world's grid region is zero.
+RW_HD int rw_ffs32(uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)b) - 1;
+#else
+    return __builtin_ctz(b);
+#endif
+}
+
+// id of the shelf the reference's grid shows on `cell`: the highest id standing there (ref:751-752), 0 if none
+template <class C>
+RW_HD int rw_shelf_at(const RwParams &p, const RwLane &l, uint32_t cell) {
+    const int S = C::S(p);
+    int id = 0;
+#pragma unroll 4
+    for (int k2 = 0; k2 < (S >> 1); k2++) {
+        uint32_t w = (uint32_t)l.tile[(p.w_shelf + k2) * RW_TILE];
+        if ((w & 0xffffu) == cell) id = 2 * k2 + 1;
+        if ((w >> 16) == cell) id = 2 * k2 + 2;
     }
-    for (int q = 0; q < p.R; q++) {
-        int id = rw_queue(p, l, q);
-        if (id) {
-            int c = rw_shelf_cell(p, l, id - 1);
-            if ((l.gs[c] & 0x7fffu) == (unsigned)id) l.gs[c] |= RW_REQ_BIT;
-        }
+    if (S & 1) {
+        uint32_t w = (uint32_t)l.tile[(p.w_shelf + (S >> 1)) * RW_TILE];
+        if ((w & 0xffffu) == cell) id = S;
     }
-    for (int i = 0; i < p.n; i++) {
-        uint32_t aw = rw_agent(p, l, i);
-        l.ga[rw_ay(aw) * p.W + rw_ax(aw)] = (uint8_t)(i + 1);
-    }
-    return overlap;
+    return id;
 }
 
 RW_HD bool rw_in_queue(const RwParams &p, const RwLane &l, int id) {
     for (int q = 0; q < p.R; q++)
         if (rw_queue(p, l, q) == id) return true;
     return false;
+}
+
+template <class C>
+RW_HD void rw_build_grid(const RwParams &p, const RwLane &l) {
+    const int S = C::S(p);
+#pragma unroll 4
+    for (int k2 = 0; k2 < (S >> 1); k2++) {  // two shelves per state word
+        uint32_t w = (uint32_t)l.tile[(p.w_shelf + k2) * RW_TILE];
+        l.g[w & 0xffffu] = (uint8_t)RW_G_SHELF;
+        l.g[w >> 16] = (uint8_t)RW_G_SHELF;
+    }
+    if (S & 1) l.g[(uint32_t)l.tile[(p.w_shelf + (S >> 1)) * RW_TILE] & 0xffffu] = (uint8_t)RW_G_SHELF;
+    const bool overlap = ((uint32_t)l.tile[p.w_inact * RW_TILE] & RW_OVERLAP_BIT) != 0;
+    for (int q = 0; q < p.R; q++) {
+        int id = rw_queue(p, l, q);
+        if (!id) continue;
+        uint32_t c = (uint32_t)rw_shelf_cell(p, l, id - 1);
+        // with overlapping shelves the reference's grid shows the highest id on the cell; only that one counts
+        if (!overlap || rw_shelf_at<C>(p, l, c) == id) l.g[c] |= (uint8_t)RW_G_REQ;
+    }
+    for (int i = 0; i < p.n; i++) {
+        uint32_t aw = rw_agent(p, l, i);
+        uint32_t c = (uint32_t)(rw_ay(aw) * C::W(p) + rw_ax(aw));
+        l.g[c] = (uint8_t)((l.g[c] & (RW_G_SHELF | RW_G_REQ)) | (uint32_t)(i + 1));
+    }
+}
+
+// literal _recalc_grid for worlds flagged with overlapping shelves; also refreshes the flag (O(S^2), cold)
+template <class C>
+RW_HD_NOINLINE void rw_rebuild_grid_slow(const RwParams &p, const RwLane &l) {
+    uint32_t *gz = reinterpret_cast<uint32_t *>(l.g);
+    for (int i = 0; i < (p.grid_env_stride >> 2); i++) gz[i] = 0;
+    bool overlap = false;
+    for (int k = 0; k < C::S(p) && !overlap; k++) {
+        int c = rw_shelf_cell(p, l, k);
+        for (int j = 0; j < k; j++) overlap |= (rw_shelf_cell(p, l, j) == c);
+    }
+    uint32_t w = (uint32_t)l.tile[p.w_inact * RW_TILE];
+    l.tile[p.w_inact * RW_TILE] = (int32_t)((w & ~RW_OVERLAP_BIT) | (overlap ? RW_OVERLAP_BIT : 0u));
+    rw_build_grid<C>(p, l);
 }
 
 // scratch accessors: entry 2i = start | target<<16, entry 2i+1 = meta
@@ -187,6 +230,7 @@ RW_HD void rw_pyset_add(RwPySet &s, int key, HashOf hash_of) {
 // one whose start cell comes first in the node order of networkx's G.subgraph(component).copy():
 // G insertion order when 2*|component| >= |G|, CPython set iteration order otherwise
 // (NX/classes/coreviews.py:293-300, 342-349; NX/algorithms/components/weakly_connected.py:61-66, 169-196).
+template <class C>
 RW_HD_NOINLINE int rw_tie_first(const RwParams &p, const RwLane &l, uint32_t ties) {
     const int n = p.n, m = 2 * n;
     // node id of a cell := index of its first appearance in the sequence s_0, t_0, s_1, t_1, ... (DiGraph.add_edge
@@ -206,8 +250,7 @@ RW_HD_NOINLINE int rw_tie_first(const RwParams &p, const RwLane &l, uint32_t tie
     int nG = 0;
     for (uint64_t b = is_node; b; b &= b - 1) nG++;
     // weakly connected component containing the tied cells: flood fill over succ/pred
-    int cand0 = 0;
-    while (!((ties >> cand0) & 1u)) cand0++;
+    int cand0 = rw_ffs32(ties);
     uint64_t member = 1ULL << first[2 * cand0], frontier = member;
     while (frontier) {
         uint64_t next = 0;
@@ -233,8 +276,8 @@ RW_HD_NOINLINE int rw_tie_first(const RwParams &p, const RwLane &l, uint32_t tie
     };
     auto hash_of = [&](int node) -> uint64_t {
         uint32_t c = cell_of(node);
-        uint32_t y = rw_div(c, p.divW);
-        return rw_py_hash_xy(c - y * (uint32_t)p.W, y);
+        uint32_t y = C::div_w(p, c);
+        return rw_py_hash_xy(c - y * (uint32_t)C::W(p), y);
     };
     int src = 0;
     while (!((member >> src) & 1ULL)) src++;
@@ -250,7 +293,7 @@ RW_HD_NOINLINE int rw_tie_first(const RwParams &p, const RwLane &l, uint32_t tie
         for (int li = 0; li < nlevel; li++) {
             int v = level[li];
             uint32_t cv = cell_of(v);
-            int occ = l.ga[cv];  // agent standing on this cell (pre-move layer) owns its single out-edge
+            int occ = l.g[cv] & RW_G_AGENT;  // agent standing on this cell (pre-move grid) owns its single out-edge
             if (occ) {
                 int w = first[2 * (occ - 1) + 1];
                 if (!((seen >> w) & 1ULL)) { seen |= 1ULL << w; rw_pyset_add(set1, w, hash_of); nextl[nnext++] = (uint8_t)w; }
@@ -279,27 +322,26 @@ RW_HD_NOINLINE int rw_tie_first(const RwParams &p, const RwLane &l, uint32_t tie
 }
 
 // pick the contender with the greatest height; ties by rw_tie_first
+template <class C>
 RW_HD int rw_pick(const RwParams &p, const RwLane &l, uint32_t cand) {
     uint32_t best = 0, ties = 0;
     int besth = -1;
     for (uint32_t b = cand; b; b &= b - 1) {
-#if defined(__CUDA_ARCH__)
-        int k = __ffs((int)b) - 1;
-#else
-        int k = __builtin_ctz(b);
-#endif
+        int k = rw_ffs32(b);
         int h = (int)rw_m_h(rw_meta(l, k));
         if (h > besth) { besth = h; best = (uint32_t)k; ties = 1u << k; }
         else if (h == besth) ties |= 1u << k;
     }
-    if (ties & (ties - 1)) return rw_tie_first(p, l, ties);
+    if (ties & (ties - 1)) return rw_tie_first<C>(p, l, ties);
     return (int)best;
 }
 
 // ------------------------------------------------------------------------------------------------
 // request-queue resample on delivery (ref:915-917): candidates = shelves not in the queue in ascending id,
 // new = np_random.choice(candidates), replaces the delivered shelf in place.
+template <class C>
 RW_HD_NOINLINE void rw_resample(const RwParams &p, const RwLane &l, int delivered_id, int64_t env) {
+    const int S = C::S(p);
     int distinct = 0;
     for (int q = 0; q < p.R; q++) {
         int id = rw_queue(p, l, q);
@@ -307,39 +349,44 @@ RW_HD_NOINLINE void rw_resample(const RwParams &p, const RwLane &l, int delivere
         for (int j = 0; j < q; j++) dup |= (rw_queue(p, l, j) == id);
         distinct += !dup;
     }
-    int n_cand = p.S - distinct;
+    int n_cand = S - distinct;
     int new_id = delivered_id;  // S == R: the reference raises ValueError (empty population); we keep the shelf
     if (n_cand > 0) {
         RwPcg g;
         rw_pcg_load(g, p.rng, p.E_pad, env);
         int pick = (int)rw_bounded(g, (uint32_t)(n_cand - 1));
         rw_pcg_store(g, p.rng, p.E_pad, env);
-        for (int s = 1; s <= p.S; s++) {
+        for (int s = 1; s <= S; s++) {
             if (rw_in_queue(p, l, s)) continue;
             if (pick-- == 0) { new_id = s; break; }
         }
     }
     for (int q = 0; q < p.R; q++)
         if (rw_queue(p, l, q) == delivered_id) { rw_set_queue(p, l, q, new_id); break; }
-    // requested bits of the two shelves involved
-    int cd = rw_shelf_cell(p, l, delivered_id - 1);
-    if ((l.gs[cd] & 0x7fffu) == (unsigned)delivered_id)
-        l.gs[cd] = (uint16_t)(delivered_id | (rw_in_queue(p, l, delivered_id) ? RW_REQ_BIT : 0u));
-    int cn = rw_shelf_cell(p, l, new_id - 1);
-    if ((l.gs[cn] & 0x7fffu) == (unsigned)new_id) l.gs[cn] |= RW_REQ_BIT;
+    if ((uint32_t)l.tile[p.w_inact * RW_TILE] & RW_OVERLAP_BIT) {
+        rw_rebuild_grid_slow<C>(p, l);
+        return;
+    }
+    // request bits of the two shelves involved
+    uint32_t cd = (uint32_t)rw_shelf_cell(p, l, delivered_id - 1);
+    if (!rw_in_queue(p, l, delivered_id)) l.g[cd] &= (uint8_t)~RW_G_REQ;
+    l.g[rw_shelf_cell(p, l, new_id - 1)] |= (uint8_t)RW_G_REQ;
 }
 
 // ------------------------------------------------------------------------------------------------
 // Warehouse.reset() for one world (ref:757-802), continuing the world's generator stream.  Does NOT touch
-// the occupancy grids (the caller rebuilds them).
+// the occupancy grid (the caller rebuilds it).
+template <class C>
 RW_HD_NOINLINE void rw_reset_lane(const RwParams &p, const RwLane &l, int64_t env) {
     RwPcg g;
     rw_pcg_load(g, p.rng, p.E_pad, env);
-    for (int k = 0; k < p.S; k++) rw_set_shelf_cell(p, l, k, p.home_cell[k]);  // ref:771-778
+    const int S = C::S(p), W = C::W(p);
+    for (int k = 0; k < S; k++) rw_set_shelf_cell(p, l, k, p.home_cell[k]);  // ref:771-778
     const int n = p.n;
     // ref:781-785 np_random.choice(arange(H*W), size=n, replace=False): Floyd's algorithm then a shuffle
+    const int cells = C::H(p) * W;
     for (int k = 0; k < n; k++) {
-        uint32_t j = (uint32_t)(p.cells - n + k);
+        uint32_t j = (uint32_t)(cells - n + k);
         uint32_t val = rw_bounded(g, j);
         bool found = false;
         for (int q = 0; q < k; q++) found |= (l.sc[q * RW_TILE] == val);
@@ -353,14 +400,14 @@ RW_HD_NOINLINE void rw_reset_lane(const RwParams &p, const RwLane &l, int64_t en
     }
     for (int i = 0; i < n; i++) {  // ref:786-792: unravel_index -> (y, x); dirs from choice(Direction, size=n)
         uint32_t loc = l.sc[i * RW_TILE];
-        uint32_t y = rw_div(loc, p.divW);
+        uint32_t y = C::div_w(p, loc);
         uint32_t dir = rw_bounded(g, 3);
-        rw_set_agent(p, l, i, rw_apack((int)(loc - y * (uint32_t)p.W), (int)y, (int)dir, 0, 0));
-        if (p.msg_bits) l.tile[(p.w_msg + i) * RW_TILE] = 0;
+        rw_set_agent(p, l, i, rw_apack((int)(loc - y * (uint32_t)W), (int)y, (int)dir, 0, 0));
+        if (C::mb(p)) l.tile[(p.w_msg + i) * RW_TILE] = 0;
     }
     // ref:796-800 np_random.choice(self.shelfs, size=R, replace=False)
     for (int k = 0; k < p.R; k++) {
-        uint32_t j = (uint32_t)(p.S - p.R + k);
+        uint32_t j = (uint32_t)(S - p.R + k);
         uint32_t val = rw_bounded(g, j);
         bool found = false;
         for (int q = 0; q < k; q++) found |= ((uint32_t)rw_queue(p, l, q) == val + 1);
@@ -373,27 +420,27 @@ RW_HD_NOINLINE void rw_reset_lane(const RwParams &p, const RwLane &l, int64_t en
         rw_set_queue(p, l, j, t);
     }
     l.tile[p.w_steps * RW_TILE] = 0;  // ref:764-765
-    l.tile[p.w_inact * RW_TILE] = 0;
+    l.tile[p.w_inact * RW_TILE] = 0;  // (also clears the overlap flag: every shelf is back on its own home cell)
     rw_pcg_store(g, p.rng, p.E_pad, env);
 }
 
 // ------------------------------------------------------------------------------------------------
 // Warehouse.step() for one world (ref:804-942), everything except the observation gather.
 // act: this world's actions [n][A]; reward: this world's [n] floats.  Returns done.
-// Precondition: grids built from the current state.  Postcondition: tile words and grids hold the
+// Precondition: grid built from the current state.  Postcondition: tile words and grid hold the
 // post-step state (post-move agents/shelves, post-resample request bits).
-RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, const int32_t *act, float *reward, int64_t env,
-                        bool overlap) {
-    const int n = p.n, W = p.W, H = p.H;
+template <class C>
+RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, const int32_t *act, float *reward, int64_t env) {
+    const int n = p.n, W = C::W(p), H = C::H(p), mb = C::mb(p), A = 1 + mb;
     uint32_t commit = 0, dag = 0, bad = 0;
     // ---- decode + proposals (ref:809-846)
     for (int i = 0; i < n; i++) {
         uint32_t aw = rw_agent(p, l, i);
-        int a = act[i * p.A];
+        int a = act[i * A];
         if ((unsigned)a > 4u) { a = RW_ACT_NOOP; bad++; }
-        if (p.msg_bits) {
+        if (mb) {
             uint32_t bits = 0;
-            for (int b = 0; b < p.msg_bits; b++) bits |= (uint32_t)(act[i * p.A + 1 + b] & 1) << b;
+            for (int b = 0; b < mb; b++) bits |= (uint32_t)(act[i * A + 1 + b] & 1) << b;
             l.tile[(p.w_msg + i) * RW_TILE] = (int32_t)bits;
         }
         int x = rw_ax(aw), y = rw_ay(aw), tx = x, ty = y;
@@ -405,13 +452,18 @@ RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, const int32_t *act, 
             else tx = x < W - 1 ? x + 1 : W - 1;
         }
         uint32_t s = (uint32_t)(y * W + x), t = (uint32_t)(ty * W + tx);
-        if (t != s && rw_acarry(aw) && (l.gs[t] & 0x7fffu)) {  // ref:829-844 carrier into a standing shelf
-            int o = l.ga[t];
-            if (!(o && rw_acarry(rw_agent(p, l, o - 1)))) { a = RW_ACT_NOOP; t = s; }
-        }
         uint32_t nxt;
         if (t == s) { nxt = RW_NXT_SELF; commit |= 1u << i; }
-        else { int o = l.ga[t]; nxt = o ? (uint32_t)(o - 1) : RW_NXT_SINK; }
+        else {
+            uint32_t gt = l.g[t];
+            uint32_t o = gt & RW_G_AGENT;
+            // ref:829-844 a carrier may not enter a cell holding a shelf unless an agent there carries it
+            if (rw_acarry(aw) && (gt & RW_G_SHELF) && !(o && rw_acarry(rw_agent(p, l, (int)o - 1)))) {
+                a = RW_ACT_NOOP; t = s; nxt = RW_NXT_SELF; commit |= 1u << i;
+            } else {
+                nxt = o ? o - 1 : RW_NXT_SINK;
+            }
+        }
         rw_st(l, i) = s | (t << 16);
         rw_meta(l, i) = (uint32_t)a | (nxt << 3);
     }
@@ -426,11 +478,7 @@ RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, const int32_t *act, 
     uint32_t movers = ~commit & (n == 32 ? 0xffffffffu : ((1u << n) - 1u));
     if (movers) {
         for (uint32_t b = movers; b; b &= b - 1) {
-#if defined(__CUDA_ARCH__)
-            int i = __ffs((int)b) - 1;
-#else
-            int i = __builtin_ctz(b);
-#endif
+            int i = rw_ffs32(b);
             uint32_t j = rw_m_nxt(rw_meta(l, i));
             int hops = 1;
             for (;;) {
@@ -448,11 +496,7 @@ RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, const int32_t *act, 
             for (int round = 0; changed && round < n; round++) {
                 changed = false;
                 for (uint32_t b = dag; b; b &= b - 1) {
-#if defined(__CUDA_ARCH__)
-                    int i = __ffs((int)b) - 1;
-#else
-                    int i = __builtin_ctz(b);
-#endif
+                    int i = rw_ffs32(b);
                     uint32_t mi = rw_meta(l, i);
                     uint32_t j = rw_m_nxt(mi);
                     if (j >= RW_NXT_SINK) continue;
@@ -464,50 +508,35 @@ RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, const int32_t *act, 
             // walk back from every sink cell along the longest path
             uint32_t sinkers = 0;
             for (uint32_t b = dag; b; b &= b - 1) {
-#if defined(__CUDA_ARCH__)
-                int i = __ffs((int)b) - 1;
-#else
-                int i = __builtin_ctz(b);
-#endif
+                int i = rw_ffs32(b);
                 if (rw_m_nxt(rw_meta(l, i)) == RW_NXT_SINK) sinkers |= 1u << i;
             }
             uint32_t handled = 0;
             while (sinkers & ~handled) {
                 uint32_t rem = sinkers & ~handled;
-#if defined(__CUDA_ARCH__)
-                int i0 = __ffs((int)rem) - 1;
-#else
-                int i0 = __builtin_ctz(rem);
-#endif
+                int i0 = rw_ffs32(rem);
                 uint32_t c = rw_st(l, i0) >> 16, cand = 0;
                 for (uint32_t b = rem; b; b &= b - 1) {
-#if defined(__CUDA_ARCH__)
-                    int k = __ffs((int)b) - 1;
-#else
-                    int k = __builtin_ctz(b);
-#endif
+                    int k = rw_ffs32(b);
                     if ((rw_st(l, k) >> 16) == c) cand |= 1u << k;
                 }
                 handled |= cand;
-                int cur = rw_pick(p, l, cand);
+                int cur = (cand & (cand - 1)) ? rw_pick<C>(p, l, cand) : i0;
                 for (;;) {
                     commit |= 1u << cur;
                     if (rw_m_h(rw_meta(l, cur)) == 0) break;  // nobody steps onto cur's cell
                     cand = 0;
                     for (uint32_t b = dag; b; b &= b - 1) {
-#if defined(__CUDA_ARCH__)
-                        int k = __ffs((int)b) - 1;
-#else
-                        int k = __builtin_ctz(b);
-#endif
+                        int k = rw_ffs32(b);
                         if (rw_m_nxt(rw_meta(l, k)) == (uint32_t)cur) cand |= 1u << k;
                     }
-                    cur = rw_pick(p, l, cand);
+                    cur = rw_pick<C>(p, l, cand);
                 }
             }
         }
     }
     // ---- apply (ref:878-899).  Failed agents become NOOP (ref:871-876).
+    const bool overlap = ((uint32_t)l.tile[p.w_inact * RW_TILE] & RW_OVERLAP_BIT) != 0;
     uint64_t rew_lo = 0, rew_hi = 0;  // per-agent reward in half units, 4 bits each
     int rew_global = 0;
     uint32_t moved = 0;
@@ -521,10 +550,12 @@ RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, const int32_t *act, 
         if (a == RW_ACT_FORWARD) {
             if (!((commit >> i) & 1u) || t == s) continue;
             moved |= 1u << i;
-            l.ga[s] = 0;
-            if (rw_acarry(aw)) {  // lift the carried shelf's grid entry; it is put down at t in the second pass
-                rw_meta(l, i) = (m & 0xffffu) | ((uint32_t)l.gs[s] << 16);
-                l.gs[s] = 0;
+            uint32_t gsb = l.g[s];
+            if (rw_acarry(aw)) {  // lift the carried shelf's bits; they are put down at t in the second pass
+                rw_meta(l, i) = (m & 0xffffu) | ((gsb & (RW_G_SHELF | RW_G_REQ)) << 16);
+                l.g[s] = 0;
+            } else {
+                l.g[s] = (uint8_t)(gsb & (RW_G_SHELF | RW_G_REQ));
             }
         } else if (a == RW_ACT_LEFT || a == RW_ACT_RIGHT) {  // Agent.req_direction ref:118-125
             uint32_t d = (uint32_t)rw_adir(aw);
@@ -532,8 +563,7 @@ RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, const int32_t *act, 
             rw_set_agent(p, l, i, (aw & ~(3u << 16)) | (nd << 16));
         } else {  // TOGGLE_LOAD ref:889-899
             if (!rw_acarry(aw)) {
-                uint32_t id = l.gs[s] & 0x7fffu;
-                if (id) rw_set_agent(p, l, i, aw | (id << 19));
+                if (l.g[s] & RW_G_SHELF) rw_set_agent(p, l, i, aw | ((uint32_t)rw_shelf_at<C>(p, l, s) << 19));
             } else if (!p.highway[s]) {
                 if (rw_adeliv(aw) && p.reward_type == 2) {
                     if (i < 16) rew_lo += 1ULL << (4 * i); else rew_hi += 1ULL << (4 * (i - 16));
@@ -543,37 +573,29 @@ RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, const int32_t *act, 
         }
     }
     for (uint32_t b = moved; b; b &= b - 1) {
-#if defined(__CUDA_ARCH__)
-        int i = __ffs((int)b) - 1;
-#else
-        int i = __builtin_ctz(b);
-#endif
+        int i = rw_ffs32(b);
         uint32_t aw = rw_agent(p, l, i);
         uint32_t t = rw_st(l, i) >> 16;
-        uint32_t ty = rw_div(t, p.divW), tx = t - ty * (uint32_t)W;
+        uint32_t ty = C::div_w(p, t), tx = t - ty * (uint32_t)W;
         rw_set_agent(p, l, i, (aw & ~0xffffu) | tx | (ty << 8));
-        l.ga[t] = (uint8_t)(i + 1);
         int carry = rw_acarry(aw);
         if (carry) {
-            l.gs[t] = (uint16_t)(rw_meta(l, i) >> 16);
+            l.g[t] = (uint8_t)((uint32_t)(i + 1) | (rw_meta(l, i) >> 16));
             rw_set_shelf_cell(p, l, carry - 1, (int)t);
+        } else {
+            l.g[t] = (uint8_t)((l.g[t] & (RW_G_SHELF | RW_G_REQ)) | (uint32_t)(i + 1));
         }
     }
-    if (overlap) {  // degenerate injected state: redo ref:901 _recalc_grid literally
-        uint32_t *gz = reinterpret_cast<uint32_t *>(l.gs);
-        for (int i = 0; i < (p.grid_env_stride >> 2); i++) gz[i] = 0;
-        rw_build_grid(p, l);
-    }
+    if (overlap && moved) rw_rebuild_grid_slow<C>(p, l);  // degenerate injected state: redo ref:901 literally
     // ---- deliveries (ref:903-927)
     bool delivered = false;
     for (int gi = 0; gi < p.n_goals; gi++) {
-        int c = p.goal_cell[gi];
-        uint32_t sh = l.gs[c];
-        if (!(sh & RW_REQ_BIT)) continue;
-        int id = (int)(sh & 0x7fffu);
+        uint32_t c = (uint32_t)p.goal_cell[gi];
+        uint32_t gb = l.g[c];
+        if ((gb & (RW_G_SHELF | RW_G_REQ)) != (RW_G_SHELF | RW_G_REQ)) continue;
         delivered = true;
-        rw_resample(p, l, id, env);
-        int o = l.ga[c];
+        rw_resample<C>(p, l, rw_shelf_at<C>(p, l, c), env);
+        int o = (int)(gb & RW_G_AGENT);
         int ai = o ? o - 1 : n - 1;  // python's rewards[-1] when nobody stands on the goal
         if (p.reward_type == 0) rew_global++;
         else {
@@ -587,19 +609,21 @@ RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, const int32_t *act, 
         reward[i] = 0.5f * (float)half;
     }
     // ---- counters / termination (ref:929-941)
-    int inact = delivered ? 0 : l.tile[p.w_inact * RW_TILE] + 1;
+    uint32_t wi = (uint32_t)l.tile[p.w_inact * RW_TILE];
+    int inact = delivered ? 0 : (int)(wi & ~RW_OVERLAP_BIT) + 1;
     int steps = l.tile[p.w_steps * RW_TILE] + 1;
-    l.tile[p.w_inact * RW_TILE] = inact;
+    l.tile[p.w_inact * RW_TILE] = (int32_t)((uint32_t)inact | (wi & RW_OVERLAP_BIT));
     l.tile[p.w_steps * RW_TILE] = steps;
     return (p.max_inact && inact >= p.max_inact) || (p.max_steps && steps >= p.max_steps);
 }
 
 // ------------------------------------------------------------------------------------------------
 // Flattened observation of agent i of the world in `l` (ref:598-674; layout SURVEY.md App. C) -> out[L].
+template <class C>
 RW_HD void rw_obs_agent(const RwParams &p, const RwLane &l, int i, float *out) {
     uint32_t aw = rw_agent(p, l, i);
-    int x = rw_ax(aw), y = rw_ay(aw), d = rw_adir(aw);
-    int W = p.W, H = p.H;
+    const int x = rw_ax(aw), y = rw_ay(aw), d = rw_adir(aw);
+    const int W = C::W(p), H = C::H(p);
     out[0] = p.norm_coords ? p.normx[x] : (float)x;  // ref:636-643
     out[1] = p.norm_coords ? p.normy[y] : (float)y;
     out[2] = rw_acarry(aw) ? 1.0f : 0.0f;
@@ -609,31 +633,29 @@ RW_HD void rw_obs_agent(const RwParams &p, const RwLane &l, int i, float *out) {
     out[6] = d == 3 ? 1.0f : 0.0f;
     out[7] = p.highway[y * W + x] ? 1.0f : 0.0f;      // ref:647
     float *o = out + 8;
-    const int r = p.r, mb = p.msg_bits;
+    const int r = C::r(p), mb = C::mb(p);
+    const uint8_t *gc = l.g + (y * W + x);
+#pragma unroll
     for (int dy = -r; dy <= r; dy++) {                 // ref:628-629 rows outer, columns inner
-        int yy = y + dy;
-        bool yin = (unsigned)yy < (unsigned)H;
+        const bool yin = (unsigned)(y + dy) < (unsigned)H;
+#pragma unroll
         for (int dx = -r; dx <= r; dx++) {
-            int xx = x + dx;
-            uint32_t ida = 0, sh = 0;
-            if (yin && (unsigned)xx < (unsigned)W) {   // zero padding outside the map (ref:606-626)
-                int c = yy * W + xx;
-                ida = l.ga[c];
-                sh = l.gs[c];
-            }
+            uint32_t gb = 0;                           // zero padding outside the map (ref:606-626)
+            if (yin && (unsigned)(x + dx) < (unsigned)W) gb = gc[dy * W + dx];
+            const uint32_t ida = gb & RW_G_AGENT;
             uint32_t od = 0, bits = 0;
             if (ida) {
                 od = (uint32_t)rw_adir(rw_agent(p, l, (int)ida - 1));
                 if (mb) bits = (uint32_t)l.tile[(p.w_msg + (int)ida - 1) * RW_TILE];
             }
-            o[0] = ida ? 1.0f : 0.0f;                  // ref:656-667: empty cell reads as direction one-hot [1,0,0,0]
+            o[0] = ida ? 1.0f : 0.0f;                  // ref:656-667: an empty cell reads as direction one-hot [1,0,0,0]
             o[1] = od == 0 ? 1.0f : 0.0f;
             o[2] = od == 1 ? 1.0f : 0.0f;
             o[3] = od == 2 ? 1.0f : 0.0f;
             o[4] = od == 3 ? 1.0f : 0.0f;
             for (int b = 0; b < mb; b++) o[5 + b] = (float)((bits >> b) & 1u);
-            o[5 + mb] = (sh & 0x7fffu) ? 1.0f : 0.0f;  // ref:668-673
-            o[6 + mb] = (sh & RW_REQ_BIT) ? 1.0f : 0.0f;
+            o[5 + mb] = (gb & RW_G_SHELF) ? 1.0f : 0.0f;  // ref:668-673
+            o[6 + mb] = (gb & RW_G_REQ) ? 1.0f : 0.0f;
             o += 7 + mb;
         }
     }

@@ -30,8 +30,7 @@ static RwLane lane_view(Sim *s, int lane) {
     uint8_t *wb = s->smem.data();
     RwLane l;
     l.tile = reinterpret_cast<int32_t *>(wb + p.sm_tile) + lane;
-    l.gs = reinterpret_cast<uint16_t *>(wb + p.sm_grid + (size_t)lane * p.grid_env_stride);
-    l.ga = wb + p.sm_grid + (size_t)lane * p.grid_env_stride + p.ga_off;
+    l.g = wb + p.sm_grid + (size_t)lane * p.grid_env_stride;
     l.sc = reinterpret_cast<uint32_t *>(wb + p.sm_scratch) + lane;
     return l;
 }
@@ -78,8 +77,11 @@ void sim_seed(Sim *s, const uint64_t *seeds, const uint8_t *mask) {
     }
 }
 
-// mode 0 step, 1 obs, 2 reset -- mirrors rw_main_kernel<MODE>
-void sim_run(Sim *s, int mode, const int32_t *actions, float *obs, float *reward, uint8_t *done, const uint8_t *mask) {
+}  // extern "C"
+
+// mode 0 step, 1 obs, 2 reset -- mirrors rw_main_kernel<MODE, C>
+template <class C>
+static void sim_run_t(Sim *s, int mode, const int32_t *actions, float *obs, float *reward, uint8_t *done, const uint8_t *mask) {
     const RwParams &p = s->p;
     for (int tile = 0; tile < p.tiles; tile++) {
         uint8_t *wb = s->smem.data();
@@ -91,15 +93,15 @@ void sim_run(Sim *s, int mode, const int32_t *actions, float *obs, float *reward
             int64_t env = (int64_t)tile * RW_TILE + lane;
             if (env >= p.E) continue;
             RwLane l = lane_view(s, lane);
-            if (mode == 2 && (!mask || mask[env])) rw_reset_lane(p, l, env);
-            bool overlap = rw_build_grid(p, l);
+            if (mode == 2 && (!mask || mask[env])) rw_reset_lane<C>(p, l, env);
+            rw_build_grid<C>(p, l);
             if (mode == 0) {
-                bool d = rw_step_lane(p, l, actions + env * p.n * p.A, reward + env * p.n, env, overlap);
+                bool d = rw_step_lane<C>(p, l, actions + env * p.n * p.A, reward + env * p.n, env);
                 done[env] = d;
                 if (d && p.auto_reset) {
-                    rw_reset_lane(p, l, env);
-                    memset(l.gs, 0, (size_t)p.grid_env_stride);
-                    rw_build_grid(p, l);
+                    rw_reset_lane<C>(p, l, env);
+                    memset(l.g, 0, (size_t)p.grid_env_stride);
+                    rw_build_grid<C>(p, l);
                 }
             }
         }
@@ -109,9 +111,30 @@ void sim_run(Sim *s, int mode, const int32_t *actions, float *obs, float *reward
                 int64_t env = (int64_t)tile * RW_TILE + lane;
                 if (env >= p.E) continue;
                 RwLane l = lane_view(s, lane);
-                for (int a = 0; a < p.n; a++) rw_obs_agent(p, l, a, obs + (env * p.n + a) * p.L);
+                for (int a = 0; a < p.n; a++) rw_obs_agent<C>(p, l, a, obs + (env * p.n + a) * p.L);
             }
     }
+}
+
+#define RW_STATIC_CONFIGS(X) \
+    X(11, 10, 32, 1) X(20, 10, 80, 1) X(20, 16, 144, 1) X(29, 16, 224, 1) \
+    X(11, 10, 32, 2) X(20, 10, 80, 2) X(20, 16, 144, 2) X(29, 16, 224, 2)
+
+extern "C" {
+
+static int g_force_dynamic = 0;
+void sim_force_dynamic(int on) { g_force_dynamic = on; }
+
+// same dispatch rule as rw_kernels.cu:select_kernel
+void sim_run(Sim *s, int mode, const int32_t *actions, float *obs, float *reward, uint8_t *done, const uint8_t *mask) {
+    const RwParams &p = s->p;
+    if (!g_force_dynamic && p.msg_bits == 0) {
+#define X(H_, W_, S_, R_) \
+    if (p.H == H_ && p.W == W_ && p.S == S_ && p.r == R_) return sim_run_t<RwStatic<H_, W_, S_, R_, 0>>(s, mode, actions, obs, reward, done, mask);
+        RW_STATIC_CONFIGS(X)
+#undef X
+    }
+    sim_run_t<RwDynamic>(s, mode, actions, obs, reward, done, mask);
 }
 
 // plain-array state access, same field conventions as rw_state_view (host pointers here)
@@ -119,7 +142,7 @@ void sim_get_state(Sim *s, const rw_state_view *v) {
     const RwParams &p = s->p;
     for (int64_t env = 0; env < p.E; env++) {
         int32_t *t = p.state + (size_t)(env >> 5) * p.nw * RW_TILE + (env & 31);
-        RwLane l{t, nullptr, nullptr, nullptr};
+        RwLane l{t, nullptr, nullptr};
         for (int i = 0; i < p.n; i++) {
             uint32_t aw = rw_agent(p, l, i);
             if (v->agent_x) v->agent_x[env * p.n + i] = rw_ax(aw);
@@ -139,7 +162,7 @@ void sim_get_state(Sim *s, const rw_state_view *v) {
         if (v->queue)
             for (int q = 0; q < p.R; q++) v->queue[env * p.R + q] = rw_queue(p, l, q);
         if (v->cur_steps) v->cur_steps[env] = t[p.w_steps * RW_TILE];
-        if (v->cur_inactive) v->cur_inactive[env] = t[p.w_inact * RW_TILE];
+        if (v->cur_inactive) v->cur_inactive[env] = (int32_t)((uint32_t)t[p.w_inact * RW_TILE] & ~RW_OVERLAP_BIT);
         if (v->rng)
             for (int w = 0; w < RW_RNG_WORDS; w++) v->rng[env * RW_RNG_WORDS + w] = p.rng[(size_t)w * p.E_pad + env];
     }
@@ -149,7 +172,7 @@ void sim_set_state(Sim *s, const rw_state_view *v) {
     const RwParams &p = s->p;
     for (int64_t env = 0; env < p.E; env++) {
         int32_t *t = p.state + (size_t)(env >> 5) * p.nw * RW_TILE + (env & 31);
-        RwLane l{t, nullptr, nullptr, nullptr};
+        RwLane l{t, nullptr, nullptr};
         for (int i = 0; i < p.n; i++) {
             uint32_t aw = rw_agent(p, l, i);
             int x = v->agent_x ? v->agent_x[env * p.n + i] : rw_ax(aw);
@@ -169,7 +192,14 @@ void sim_set_state(Sim *s, const rw_state_view *v) {
         if (v->queue)
             for (int q = 0; q < p.R; q++) rw_set_queue(p, l, q, v->queue[env * p.R + q]);
         if (v->cur_steps) t[p.w_steps * RW_TILE] = v->cur_steps[env];
-        if (v->cur_inactive) t[p.w_inact * RW_TILE] = v->cur_inactive[env];
+        if (v->cur_inactive) t[p.w_inact * RW_TILE] = v->cur_inactive[env] & 0x7fffffff;
+        bool overlap = false;
+        for (int k = 1; k < p.S && !overlap; k++) {
+            int c = rw_shelf_cell(p, l, k);
+            for (int j = 0; j < k; j++) overlap |= (rw_shelf_cell(p, l, j) == c);
+        }
+        uint32_t wi = (uint32_t)t[p.w_inact * RW_TILE] & ~RW_OVERLAP_BIT;
+        t[p.w_inact * RW_TILE] = (int32_t)(wi | (overlap ? RW_OVERLAP_BIT : 0u));
         if (v->rng)
             for (int w = 0; w < RW_RNG_WORDS; w++) p.rng[(size_t)w * p.E_pad + env] = v->rng[env * RW_RNG_WORDS + w];
     }
