@@ -224,6 +224,20 @@ def main():
     warm_ms = s0.elapsed_time(s1)
     clocks = sampler.stop() if rank == 0 else None
 
+    # the observation gather alone (rw_obs: state read + obs write), same flush + per-launch event protocol
+    obs_ms = []
+    for i in range(min(args.steps, 50)):
+        if not args.no_flush:
+            flush.fill_(i & 0xff)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        vec.observations()
+        b.record()
+        obs_ms.append((a, b))
+    torch.cuda.synchronize()
+    obs_ms = [a.elapsed_time(b) for a, b in obs_ms]
+    obs_kernel_ms = sum(obs_ms) / len(obs_ms)
+
     # end to end through the host-buffer C-ABI entry point
     e2e_steps = args.e2e_steps
     h_act = torch.empty((E, n, A), dtype=torch.int32).pin_memory()
@@ -241,10 +255,10 @@ def main():
         vec.backend.step_host(h_act, h_obs, h_rew, h_done)  # synchronises internally
     e2e_s = time.perf_counter() - t0
 
-    tot = torch.tensor([total_ms, warm_ms, e2e_s], dtype=torch.float64, device=dev)
+    tot = torch.tensor([total_ms, warm_ms, e2e_s, obs_kernel_ms], dtype=torch.float64, device=dev)
     if dist:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-    total_ms, warm_ms, e2e_s = (float(x) for x in tot.tolist())
+    total_ms, warm_ms, e2e_s, obs_kernel_ms = (float(x) for x in tot.tolist())
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -281,6 +295,11 @@ def main():
                      "algorithmic_bytes_per_env_step": b_step, "layout_bytes_per_env_step": b_packed,
                      "achieved_layout_bytes": b_packed * E / (kernel_ms * 1e-3) / 1e9,
                      "kernel_us": kernel_ms * 1e3},
+        "obs_gather": {"kernel": "rw_main_kernel<OBS>", "kernel_us": obs_kernel_ms * 1e3,
+                       "algorithmic_bytes_per_env": int(info["algorithmic_bytes_obs"]),
+                       "achieved_gbs": int(info["algorithmic_bytes_obs"]) * E / (obs_kernel_ms * 1e-3) / 1e9,
+                       "frac_of_hbm_peak": int(info["algorithmic_bytes_obs"]) * E / (obs_kernel_ms * 1e-3) / 1e9 / peak,
+                       "layout_bytes_per_env": int(info["packed_bytes_obs"])},
         "e2e": {"value": world * E * e2e_steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": E * n * A * 4,
                 "d2h_bytes_per_step": E * n * L * 4 + E * n * 4 + E, "steps": e2e_steps,
                 "api": "rw_step_host (pinned host buffers, copies + kernel + sync inside the timed region)"},

@@ -21,7 +21,7 @@ struct rw_handle {
     int device;
     bool ready;  // worlds hold a valid state (after rw_reset / rw_set_state)
     std::string err;
-    void *d_highway = nullptr, *d_home = nullptr, *d_normx = nullptr, *d_normy = nullptr;
+    void *d_highway = nullptr, *d_home = nullptr, *d_home_id = nullptr, *d_normx = nullptr, *d_normy = nullptr;
     void *d_state = nullptr, *d_rng = nullptr, *d_err = nullptr;
     // staging for the *_host entry points
     int32_t *d_actions = nullptr;
@@ -106,12 +106,12 @@ static int create_impl(rw_handle *h, const rw_config *cfg, int64_t num_envs, int
     CK(cudaSetDevice(device));
     CK(cudaGetDeviceProperties(&prop, device));
     const int smem_cap = (int)prop.sharedMemPerBlockOptin;
-    if (p.sm_warp_bytes > smem_cap)
+    if (p.sm_cta_bytes + p.sm_warp_bytes > smem_cap)
         return fail(h, RW_EINVAL, "configuration needs " + std::to_string(p.sm_warp_bytes) +
                                       " B of shared memory per warp, device allows " + std::to_string(smem_cap));
     {   // warps (= tiles) per CTA: as many as the shared memory of one SM holds, so that a CTA fills an SM and, when the
         // batch allows, the whole launch is a single wave; small batches spread over the SMs instead
-        int fit = (smem_cap - 1024) / p.sm_warp_bytes;
+        int fit = (smem_cap - p.sm_cta_bytes) / p.sm_warp_bytes;
         if (fit > 16) fit = 16;
         if (fit < 1) fit = 1;
         int spread = (p.tiles + prop.multiProcessorCount - 1) / prop.multiProcessorCount;
@@ -120,11 +120,11 @@ static int create_impl(rw_handle *h, const rw_config *cfg, int64_t num_envs, int
         if (ev) wpc = atoi(ev);
         if (wpc < 1) wpc = 1;
         if (wpc > 16) wpc = 16;
-        while (wpc > 1 && wpc * p.sm_warp_bytes > smem_cap) wpc--;
+        while (wpc > 1 && p.sm_cta_bytes + wpc * p.sm_warp_bytes > smem_cap) wpc--;
         p.warps_per_cta = wpc;
     }
     if (getenv("RWARE_B200_FORCE_DYNAMIC")) rw_force_dynamic_kernels(atoi(getenv("RWARE_B200_FORCE_DYNAMIC")) != 0);
-    CK(rw_configure_kernels(p, p.sm_warp_bytes * p.warps_per_cta));
+    CK(rw_configure_kernels(p, p.sm_cta_bytes + p.sm_warp_bytes * p.warps_per_cta));
 
     // static tables
     std::vector<float> nx(W), ny(H);
@@ -134,6 +134,12 @@ static int create_impl(rw_handle *h, const rw_config *cfg, int64_t num_envs, int
     CK(cudaMemcpy(h->d_highway, cfg->highways, cells, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&h->d_home, sizeof(uint16_t) * (S > 0 ? S : 1)));
     if (S) CK(cudaMemcpy(h->d_home, home.data(), sizeof(uint16_t) * S, cudaMemcpyHostToDevice));
+    {
+        std::vector<uint16_t> home_id(cells, 0);
+        for (int k = 0; k < S; k++) home_id[home[k]] = (uint16_t)(k + 1);
+        CK(cudaMalloc(&h->d_home_id, sizeof(uint16_t) * cells));
+        CK(cudaMemcpy(h->d_home_id, home_id.data(), sizeof(uint16_t) * cells, cudaMemcpyHostToDevice));
+    }
     CK(cudaMalloc(&h->d_normx, sizeof(float) * W));
     CK(cudaMalloc(&h->d_normy, sizeof(float) * H));
     CK(cudaMemcpy(h->d_normx, nx.data(), sizeof(float) * W, cudaMemcpyHostToDevice));
@@ -147,6 +153,7 @@ static int create_impl(rw_handle *h, const rw_config *cfg, int64_t num_envs, int
     CK(cudaMemset(h->d_err, 0, 8));
     p.highway = (const uint8_t *)h->d_highway;
     p.home_cell = (const uint16_t *)h->d_home;
+    p.home_id = (const uint16_t *)h->d_home_id;
     p.normx = (const float *)h->d_normx;
     p.normy = (const float *)h->d_normy;
     p.state = (int32_t *)h->d_state;
@@ -173,7 +180,7 @@ extern "C" {
 int rw_destroy(rw_handle *h) {
     if (!h) return RW_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->d_highway); cudaFree(h->d_home); cudaFree(h->d_normx); cudaFree(h->d_normy);
+    cudaFree(h->d_highway); cudaFree(h->d_home); cudaFree(h->d_home_id); cudaFree(h->d_normx); cudaFree(h->d_normy);
     cudaFree(h->d_state); cudaFree(h->d_rng); cudaFree(h->d_err);
     cudaFree(h->d_actions); cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_done);
     if (h->host_stream) cudaStreamDestroy(h->host_stream);

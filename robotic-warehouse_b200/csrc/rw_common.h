@@ -60,6 +60,7 @@ struct RwParams {
     // static device tables
     const uint8_t *highway;     // [cells]
     const uint16_t *home_cell;  // [S]
+    const uint16_t *home_id;    // [cells]: inverse of home_cell (0 = highway)
     const float *normx, *normy; // [W], [H]: float32(x / (W-1)), float32(y / (H-1))
     // world state
     int32_t *state;  // [tiles][nw][32]
@@ -69,6 +70,8 @@ struct RwParams {
     int32_t tiles;
     // per-warp shared memory carve-up (byte offsets from the warp's base)
     int32_t sm_tile, sm_grid, sm_scratch, sm_obs, sm_bar, sm_warp_bytes;
+    int32_t sm_cta_bytes;  // CTA-shared prologue region: highway[cells] u8 then home_id[cells] u16 (device only)
+    int32_t obs_tma;       // 1: observation chunks leave through cp.async.bulk, 0: 16-byte st.global from all lanes
     int32_t grid_env_stride;  // bytes per world of the occupancy grid: one byte per cell (see RW_G_*)
     int32_t ga_off;           // unused (kept for layout stability)
     int32_t obs_chunk_envs, obs_chunk_bytes, obs_nbuf, obs_env_bytes;
@@ -101,6 +104,8 @@ struct RwLane {
     int32_t *tile;   // word w at tile[w * RW_TILE]
     uint8_t *g;      // occupancy grid of this world, one byte per cell (RW_G_*)
     uint32_t *sc;    // scratch, entry k at sc[k * RW_TILE]; 2*n entries
+    const uint8_t *highway;   // [cells] 1 = highway (CTA-shared copy in shared memory on the device)
+    const uint16_t *home_id;  // [cells] id of the shelf whose home is this cell, 0 for highways (CTA-shared copy)
 };
 
 // Compile-time specialisation of the layout-dependent constants.  RwDynamic reads them from RwParams; RwStatic<...>

@@ -64,45 +64,56 @@ __global__ void __launch_bounds__(512) rw_main_kernel(const __grid_constant__ Rw
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x * p.warps_per_cta + warp;
-    if (tile >= p.tiles) return;
-    uint8_t *wb = smem + (size_t)warp * p.sm_warp_bytes;
+    const bool active = tile < p.tiles;
+    uint8_t *wb = smem + p.sm_cta_bytes + (size_t)warp * p.sm_warp_bytes;
     int32_t *tilew = reinterpret_cast<int32_t *>(wb + p.sm_tile);
     uint8_t *grid = wb + p.sm_grid;
     uint32_t *scratch = reinterpret_cast<uint32_t *>(wb + p.sm_scratch);
     float *obuf = reinterpret_cast<float *>(wb + p.sm_obs);
     uint64_t *bar = reinterpret_cast<uint64_t *>(wb + p.sm_bar);
     const uint32_t tile_bytes = (uint32_t)p.nw * RW_TILE * 4u;
-    int32_t *gtile = p.state + (size_t)tile * p.nw * RW_TILE;
+    int32_t *gtile = p.state + (size_t)(active ? tile : 0) * p.nw * RW_TILE;
+    const int64_t env = (int64_t)tile * RW_TILE + lane;
+    const bool valid = active && env < p.E;
+    RwLane l;
+    l.tile = tilew + lane;
+    l.g = grid + (size_t)lane * p.grid_env_stride;
+    l.sc = scratch + lane;
+    uint8_t *s_highway = smem;
+    uint16_t *s_home_id = reinterpret_cast<uint16_t *>(smem + ((p.cells + 1) & ~1));
+    l.highway = s_highway;
+    l.home_id = s_home_id;
 
-    // ---- 1. state tile HBM -> shared memory through the TMA; zero the grids while it is in flight
-    if (lane == 0) {
+    // ---- 1. state tile HBM -> shared memory through the TMA; while it is in flight: CTA-shared static tables,
+    //         this world's actions (global loads issued back to back) and zeroing of the occupancy grids
+    if (active && lane == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
         mbar_expect_tx(bar, tile_bytes);
         bulk_g2s(tilew, gtile, tile_bytes, bar);
     }
-    {
+    for (int i = threadIdx.x; i < p.cells; i += blockDim.x) {
+        s_highway[i] = p.highway[i];
+        s_home_id[i] = p.home_id[i];
+    }
+    if (MODE == RW_MODE_STEP && valid) rw_load_actions<C>(p, l, actions + env * p.n * p.A);
+    if (active) {
         int4 *g4 = reinterpret_cast<int4 *>(grid);
         const int n16 = (p.grid_env_stride * RW_TILE) >> 4;
         for (int i = lane; i < n16; i += 32) g4[i] = make_int4(0, 0, 0, 0);
     }
-    __syncwarp();
+    __syncthreads();
+    if (!active) return;
     mbar_wait(bar, 0);
 
     // ---- 2. lane e advances world e
-    const int64_t env = (int64_t)tile * RW_TILE + lane;
-    const bool valid = env < p.E;
-    RwLane l;
-    l.tile = tilew + lane;
-    l.g = grid + (size_t)lane * p.grid_env_stride;
-    l.sc = scratch + lane;
     if (valid) {
         if (MODE == RW_MODE_RESET) {
             if (mask == nullptr || mask[env]) rw_reset_lane<C>(p, l, env);
         }
         rw_build_grid<C>(p, l);
         if (MODE == RW_MODE_STEP) {
-            bool d = rw_step_lane<C>(p, l, actions + env * p.n * p.A, reward + env * p.n, env);
+            bool d = rw_step_lane<C>(p, l, reward + env * p.n, env);
             done[env] = d ? 1 : 0;
             if (d && p.auto_reset) {
                 rw_reset_lane<C>(p, l, env);
@@ -148,17 +159,27 @@ __global__ void __launch_bounds__(512) rw_main_kernel(const __grid_constant__ Rw
                     le.tile = tilew + e;
                     le.g = grid + (size_t)e * p.grid_env_stride;
                     le.sc = nullptr;
+                    le.highway = s_highway;
+                    le.home_id = s_home_id;
                     rw_obs_agent<C>(p, le, a, buf + (size_t)it * L);
                 }
             }
             float *gdst = obs + (tile_env0 + c0) * (int64_t)n * L;
-            if (full && p.obs_bulk && c0 + CH <= RW_TILE) {
+            if (full && p.obs_bulk && c0 + CH <= RW_TILE && p.obs_tma) {
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
                     bulk_s2g(gdst, buf, (uint32_t)p.obs_chunk_bytes);
                     bulk_commit();
                 }
+            } else if (full && p.obs_bulk && c0 + CH <= RW_TILE) {  // 16-byte coalesced stores: 512 B per warp instruction
+                __syncwarp();
+                const int4 *src = reinterpret_cast<const int4 *>(buf);
+                int4 *dst = reinterpret_cast<int4 *>(gdst);
+                const int n16 = p.obs_chunk_bytes >> 4;
+#pragma unroll 4
+                for (int i = lane; i < n16; i += 32) __stcs(dst + i, src[i]);
+                __syncwarp();
             } else {  // ragged tail / unaligned geometry: plain coalesced stores
                 __syncwarp();
                 int64_t envs_here = p.E - (tile_env0 + c0);
@@ -179,7 +200,7 @@ __global__ void rw_get_state_kernel(const RwParams p, const rw_state_view v) {
     int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= p.E) return;
     int32_t *t = p.state + (size_t)(env >> 5) * p.nw * RW_TILE + (env & 31);
-    RwLane l{t, nullptr, nullptr};
+    RwLane l{t, nullptr, nullptr, nullptr, nullptr};
     for (int i = 0; i < p.n; i++) {
         uint32_t aw = rw_agent(p, l, i);
         if (v.agent_x) v.agent_x[env * p.n + i] = rw_ax(aw);
@@ -210,7 +231,7 @@ __global__ void rw_set_state_kernel(const RwParams p, const rw_state_view v) {
     int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= p.E) return;
     int32_t *t = p.state + (size_t)(env >> 5) * p.nw * RW_TILE + (env & 31);
-    RwLane l{t, nullptr, nullptr};
+    RwLane l{t, nullptr, nullptr, nullptr, nullptr};
     for (int i = 0; i < p.n; i++) {
         uint32_t aw = rw_agent(p, l, i);
         int x = v.agent_x ? v.agent_x[env * p.n + i] : rw_ax(aw);
@@ -308,7 +329,7 @@ cudaError_t rw_launch_main(RwMode mode, const RwParams &p, const int32_t *action
                            const uint8_t *mask, cudaStream_t stream) {
     dim3 block(32 * p.warps_per_cta);
     dim3 grid((p.tiles + p.warps_per_cta - 1) / p.warps_per_cta);
-    size_t smem = (size_t)p.sm_warp_bytes * p.warps_per_cta;
+    size_t smem = (size_t)p.sm_cta_bytes + (size_t)p.sm_warp_bytes * p.warps_per_cta;
     select_kernel(mode, p, g_force_dynamic)<<<grid, block, smem, stream>>>(p, actions, obs, reward, done, mask);
     return cudaGetLastError();
 }

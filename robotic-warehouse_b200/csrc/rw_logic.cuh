@@ -101,7 +101,11 @@ RW_HD int rw_ffs32(uint32_t b) {
 template <class C>
 RW_HD int rw_shelf_at(const RwParams &p, const RwLane &l, uint32_t cell) {
     const int S = C::S(p);
-    int id = 0;
+    // fast path: without overlaps a cell holds at most one shelf, and almost always it is the one whose home it is
+    int id = l.home_id[cell];
+    if (id && (uint32_t)rw_shelf_cell(p, l, id - 1) == cell && !((uint32_t)l.tile[p.w_inact * RW_TILE] & RW_OVERLAP_BIT))
+        return id;
+    id = 0;
 #pragma unroll 4
     for (int k2 = 0; k2 < (S >> 1); k2++) {
         uint32_t w = (uint32_t)l.tile[(p.w_shelf + k2) * RW_TILE];
@@ -429,20 +433,38 @@ RW_HD_NOINLINE void rw_reset_lane(const RwParams &p, const RwLane &l, int64_t en
 // act: this world's actions [n][A]; reward: this world's [n] floats.  Returns done.
 // Precondition: grid built from the current state.  Postcondition: tile words and grid hold the
 // post-step state (post-move agents/shelves, post-resample request bits).
+// Action decode (ref:809-814), hoisted out of the step so that the global loads are issued back to back while
+// the state tile is still in flight: scratch entry 2i+1 <- action | message bits << 8.  Invalid values become NOOP.
 template <class C>
-RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, const int32_t *act, float *reward, int64_t env) {
-    const int n = p.n, W = C::W(p), H = C::H(p), mb = C::mb(p), A = 1 + mb;
-    uint32_t commit = 0, dag = 0, bad = 0;
-    // ---- decode + proposals (ref:809-846)
+RW_HD void rw_load_actions(const RwParams &p, const RwLane &l, const int32_t *act) {
+    const int n = p.n, mb = C::mb(p), A = 1 + mb;
+    uint32_t bad = 0;
     for (int i = 0; i < n; i++) {
-        uint32_t aw = rw_agent(p, l, i);
         int a = act[i * A];
         if ((unsigned)a > 4u) { a = RW_ACT_NOOP; bad++; }
-        if (mb) {
-            uint32_t bits = 0;
-            for (int b = 0; b < mb; b++) bits |= (uint32_t)(act[i * A + 1 + b] & 1) << b;
-            l.tile[(p.w_msg + i) * RW_TILE] = (int32_t)bits;
-        }
+        uint32_t bits = 0;
+        for (int b = 0; b < mb; b++) bits |= (uint32_t)(act[i * A + 1 + b] & 1) << b;
+        rw_meta(l, i) = (uint32_t)a | (bits << 8);
+    }
+    if (bad) {
+#if defined(__CUDA_ARCH__)
+        atomicAdd(p.err_count, (unsigned long long)bad);
+#else
+        *p.err_count += bad;
+#endif
+    }
+}
+
+template <class C>
+RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, float *reward, int64_t env) {
+    const int n = p.n, W = C::W(p), H = C::H(p), mb = C::mb(p);
+    uint32_t commit = 0, dag = 0;
+    // ---- proposals (ref:825-846); actions were decoded into the scratch by rw_load_actions
+    for (int i = 0; i < n; i++) {
+        uint32_t aw = rw_agent(p, l, i);
+        uint32_t pre = rw_meta(l, i);
+        int a = (int)(pre & 7u);
+        if (mb) l.tile[(p.w_msg + i) * RW_TILE] = (int32_t)(pre >> 8);
         int x = rw_ax(aw), y = rw_ay(aw), tx = x, ty = y;
         if (a == RW_ACT_FORWARD) {  // Agent.req_location ref:102-116, clamped at the walls
             int d = rw_adir(aw);
@@ -466,13 +488,6 @@ RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, const int32_t *act, 
         }
         rw_st(l, i) = s | (t << 16);
         rw_meta(l, i) = (uint32_t)a | (nxt << 3);
-    }
-    if (bad) {
-#if defined(__CUDA_ARCH__)
-        atomicAdd(p.err_count, (unsigned long long)bad);
-#else
-        *p.err_count += bad;
-#endif
     }
     // ---- resolve (ref:848-876 restated agent-centrically)
     uint32_t movers = ~commit & (n == 32 ? 0xffffffffu : ((1u << n) - 1u));
@@ -564,7 +579,7 @@ RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, const int32_t *act, 
         } else {  // TOGGLE_LOAD ref:889-899
             if (!rw_acarry(aw)) {
                 if (l.g[s] & RW_G_SHELF) rw_set_agent(p, l, i, aw | ((uint32_t)rw_shelf_at<C>(p, l, s) << 19));
-            } else if (!p.highway[s]) {
+            } else if (!l.highway[s]) {
                 if (rw_adeliv(aw) && p.reward_type == 2) {
                     if (i < 16) rew_lo += 1ULL << (4 * i); else rew_hi += 1ULL << (4 * (i - 16));
                 }
@@ -631,7 +646,7 @@ RW_HD void rw_obs_agent(const RwParams &p, const RwLane &l, int i, float *out) {
     out[4] = d == 1 ? 1.0f : 0.0f;
     out[5] = d == 2 ? 1.0f : 0.0f;
     out[6] = d == 3 ? 1.0f : 0.0f;
-    out[7] = p.highway[y * W + x] ? 1.0f : 0.0f;      // ref:647
+    out[7] = l.highway[y * W + x] ? 1.0f : 0.0f;      // ref:647
     float *o = out + 8;
     const int r = C::r(p), mb = C::mb(p);
     const uint8_t *gc = l.g + (y * W + x);

@@ -16,7 +16,7 @@
 struct Sim {
     RwParams p;
     std::vector<uint8_t> highway;
-    std::vector<uint16_t> home;
+    std::vector<uint16_t> home, home_id;
     std::vector<float> nx, ny;
     std::vector<int32_t> state;
     std::vector<uint32_t> rng;
@@ -32,6 +32,8 @@ static RwLane lane_view(Sim *s, int lane) {
     l.tile = reinterpret_cast<int32_t *>(wb + p.sm_tile) + lane;
     l.g = wb + p.sm_grid + (size_t)lane * p.grid_env_stride;
     l.sc = reinterpret_cast<uint32_t *>(wb + p.sm_scratch) + lane;
+    l.highway = s->highway.data();
+    l.home_id = s->home_id.data();
     return l;
 }
 
@@ -43,6 +45,8 @@ Sim *sim_create(const rw_config *cfg, int64_t num_envs) {
     s->highway.assign(cfg->highways, cfg->highways + cells);
     for (int c = 0; c < cells; c++)
         if (!cfg->highways[c]) s->home.push_back((uint16_t)c);
+    s->home_id.assign(cells, 0);
+    for (size_t k = 0; k < s->home.size(); k++) s->home_id[s->home[k]] = (uint16_t)(k + 1);
     rw_fill_params(s->p, *cfg, num_envs, (int)s->home.size());
     RwParams &p = s->p;
     s->nx.resize(p.W);
@@ -54,6 +58,7 @@ Sim *sim_create(const rw_config *cfg, int64_t num_envs) {
     s->smem.assign((size_t)p.sm_warp_bytes, 0);
     p.highway = s->highway.data();
     p.home_cell = s->home.data();
+    p.home_id = s->home_id.data();
     p.normx = s->nx.data();
     p.normy = s->ny.data();
     p.state = s->state.data();
@@ -96,7 +101,8 @@ static void sim_run_t(Sim *s, int mode, const int32_t *actions, float *obs, floa
             if (mode == 2 && (!mask || mask[env])) rw_reset_lane<C>(p, l, env);
             rw_build_grid<C>(p, l);
             if (mode == 0) {
-                bool d = rw_step_lane<C>(p, l, actions + env * p.n * p.A, reward + env * p.n, env);
+                rw_load_actions<C>(p, l, actions + env * p.n * p.A);
+                bool d = rw_step_lane<C>(p, l, reward + env * p.n, env);
                 done[env] = d;
                 if (d && p.auto_reset) {
                     rw_reset_lane<C>(p, l, env);
@@ -142,7 +148,7 @@ void sim_get_state(Sim *s, const rw_state_view *v) {
     const RwParams &p = s->p;
     for (int64_t env = 0; env < p.E; env++) {
         int32_t *t = p.state + (size_t)(env >> 5) * p.nw * RW_TILE + (env & 31);
-        RwLane l{t, nullptr, nullptr};
+        RwLane l{t, nullptr, nullptr, nullptr, nullptr};
         for (int i = 0; i < p.n; i++) {
             uint32_t aw = rw_agent(p, l, i);
             if (v->agent_x) v->agent_x[env * p.n + i] = rw_ax(aw);
@@ -172,7 +178,7 @@ void sim_set_state(Sim *s, const rw_state_view *v) {
     const RwParams &p = s->p;
     for (int64_t env = 0; env < p.E; env++) {
         int32_t *t = p.state + (size_t)(env >> 5) * p.nw * RW_TILE + (env & 31);
-        RwLane l{t, nullptr, nullptr};
+        RwLane l{t, nullptr, nullptr, nullptr, nullptr};
         for (int i = 0; i < p.n; i++) {
             uint32_t aw = rw_agent(p, l, i);
             int x = v->agent_x ? v->agent_x[env * p.n + i] : rw_ax(aw);
