@@ -112,6 +112,9 @@ struct RwLane {
 // bakes in the registered warehouse sizes so that the cell loops unroll and the index arithmetic folds.
 struct RwDynamic {
     static constexpr bool is_static = false;
+    static constexpr bool full_static = false;
+    RW_HD static int n(const RwParams &p) { return p.n; }
+    RW_HD static int R(const RwParams &p) { return p.R; }
     RW_HD static int H(const RwParams &p) { return p.H; }
     RW_HD static int W(const RwParams &p) { return p.W; }
     RW_HD static int S(const RwParams &p) { return p.S; }
@@ -119,9 +122,13 @@ struct RwDynamic {
     RW_HD static int mb(const RwParams &p) { return p.msg_bits; }
     RW_HD static uint32_t div_w(const RwParams &p, uint32_t c) { return rw_div(c, p.divW); }
 };
-template <int H_, int W_, int S_, int R_, int MB_>
+// N_ / RQ_ = 0 keep the number of agents / the request-queue size dynamic
+template <int H_, int W_, int S_, int R_, int MB_, int N_ = 0, int RQ_ = -1>
 struct RwStatic {
     static constexpr bool is_static = true;
+    static constexpr bool full_static = (N_ > 0 && RQ_ >= 0);
+    RW_HD static int n(const RwParams &p) { return N_ > 0 ? N_ : p.n; }
+    RW_HD static int R(const RwParams &p) { return RQ_ >= 0 ? RQ_ : p.R; }
     RW_HD static int H(const RwParams &) { return H_; }
     RW_HD static int W(const RwParams &) { return W_; }
     RW_HD static int S(const RwParams &) { return S_; }
@@ -130,12 +137,34 @@ struct RwStatic {
     RW_HD static uint32_t div_w(const RwParams &, uint32_t c) { return c / (uint32_t)W_; }
 };
 
-RW_HD uint32_t rw_agent(const RwParams &p, const RwLane &l, int i) { return (uint32_t)l.tile[(p.w_agent + i) * RW_TILE]; }
-RW_HD void rw_set_agent(const RwParams &p, const RwLane &l, int i, uint32_t aw) { l.tile[(p.w_agent + i) * RW_TILE] = (int32_t)aw; }
+// tile word offsets of one world (compile-time constants for fully static configurations)
+struct RwOff {
+    int n, R, w_msg, w_shelf, w_queue, w_steps, w_inact;
+};
+template <class C>
+RW_HD RwOff rw_off(const RwParams &p) {
+    RwOff o;
+    o.n = C::n(p);
+    o.R = C::R(p);
+    if (C::full_static) {
+        const int mb = C::mb(p), S = C::S(p);
+        o.w_msg = o.n;
+        o.w_shelf = o.n + (mb ? o.n : 0);
+        o.w_queue = o.w_shelf + (S + 1) / 2;
+        o.w_steps = o.w_queue + (o.R + 1) / 2;
+        o.w_inact = o.w_steps + 1;
+    } else {
+        o.w_msg = p.w_msg; o.w_shelf = p.w_shelf; o.w_queue = p.w_queue; o.w_steps = p.w_steps; o.w_inact = p.w_inact;
+    }
+    return o;
+}
+
+RW_HD uint32_t rw_agent(const RwLane &l, int i) { return (uint32_t)l.tile[i * RW_TILE]; }  // w_agent == 0
+RW_HD void rw_set_agent(const RwLane &l, int i, uint32_t aw) { l.tile[i * RW_TILE] = (int32_t)aw; }
 RW_HD uint16_t *rw_half(int32_t *tile, int word0, int k) {
     return reinterpret_cast<uint16_t *>(&tile[(word0 + (k >> 1)) * RW_TILE]) + (k & 1);
 }
-RW_HD int rw_shelf_cell(const RwParams &p, const RwLane &l, int k) { return *rw_half(l.tile, p.w_shelf, k); }
-RW_HD void rw_set_shelf_cell(const RwParams &p, const RwLane &l, int k, int cell) { *rw_half(l.tile, p.w_shelf, k) = (uint16_t)cell; }
-RW_HD int rw_queue(const RwParams &p, const RwLane &l, int q) { return *rw_half(l.tile, p.w_queue, q); }
-RW_HD void rw_set_queue(const RwParams &p, const RwLane &l, int q, int id) { *rw_half(l.tile, p.w_queue, q) = (uint16_t)id; }
+RW_HD int rw_shelf_cell(const RwOff &o, const RwLane &l, int k) { return *rw_half(l.tile, o.w_shelf, k); }
+RW_HD void rw_set_shelf_cell(const RwOff &o, const RwLane &l, int k, int cell) { *rw_half(l.tile, o.w_shelf, k) = (uint16_t)cell; }
+RW_HD int rw_queue(const RwOff &o, const RwLane &l, int q) { return *rw_half(l.tile, o.w_queue, q); }
+RW_HD void rw_set_queue(const RwOff &o, const RwLane &l, int q, int id) { *rw_half(l.tile, o.w_queue, q) = (uint16_t)id; }

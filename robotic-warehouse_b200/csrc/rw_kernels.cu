@@ -201,8 +201,9 @@ __global__ void rw_get_state_kernel(const RwParams p, const rw_state_view v) {
     if (env >= p.E) return;
     int32_t *t = p.state + (size_t)(env >> 5) * p.nw * RW_TILE + (env & 31);
     RwLane l{t, nullptr, nullptr, nullptr, nullptr};
+    const RwOff o = rw_off<RwDynamic>(p);
     for (int i = 0; i < p.n; i++) {
-        uint32_t aw = rw_agent(p, l, i);
+        uint32_t aw = rw_agent(l, i);
         if (v.agent_x) v.agent_x[env * p.n + i] = rw_ax(aw);
         if (v.agent_y) v.agent_y[env * p.n + i] = rw_ay(aw);
         if (v.agent_dir) v.agent_dir[env * p.n + i] = rw_adir(aw);
@@ -214,13 +215,13 @@ __global__ void rw_get_state_kernel(const RwParams p, const rw_state_view v) {
         }
     }
     for (int k = 0; k < p.S; k++) {
-        uint32_t c = (uint32_t)rw_shelf_cell(p, l, k);
+        uint32_t c = (uint32_t)rw_shelf_cell(o, l, k);
         uint32_t y = rw_div(c, p.divW);
         if (v.shelf_x) v.shelf_x[env * p.S + k] = (int32_t)(c - y * p.W);
         if (v.shelf_y) v.shelf_y[env * p.S + k] = (int32_t)y;
     }
     if (v.queue)
-        for (int q = 0; q < p.R; q++) v.queue[env * p.R + q] = rw_queue(p, l, q);
+        for (int q = 0; q < p.R; q++) v.queue[env * p.R + q] = rw_queue(o, l, q);
     if (v.cur_steps) v.cur_steps[env] = t[p.w_steps * RW_TILE];
     if (v.cur_inactive) v.cur_inactive[env] = (int32_t)((uint32_t)t[p.w_inact * RW_TILE] & ~RW_OVERLAP_BIT);
     if (v.rng)
@@ -232,14 +233,15 @@ __global__ void rw_set_state_kernel(const RwParams p, const rw_state_view v) {
     if (env >= p.E) return;
     int32_t *t = p.state + (size_t)(env >> 5) * p.nw * RW_TILE + (env & 31);
     RwLane l{t, nullptr, nullptr, nullptr, nullptr};
+    const RwOff o = rw_off<RwDynamic>(p);
     for (int i = 0; i < p.n; i++) {
-        uint32_t aw = rw_agent(p, l, i);
+        uint32_t aw = rw_agent(l, i);
         int x = v.agent_x ? v.agent_x[env * p.n + i] : rw_ax(aw);
         int y = v.agent_y ? v.agent_y[env * p.n + i] : rw_ay(aw);
         int d = v.agent_dir ? v.agent_dir[env * p.n + i] : rw_adir(aw);
         int c = v.agent_carry ? v.agent_carry[env * p.n + i] : rw_acarry(aw);
         int hd = v.agent_has_delivered ? (v.agent_has_delivered[env * p.n + i] != 0) : rw_adeliv(aw);
-        rw_set_agent(p, l, i, rw_apack(x & 0xff, y & 0xff, d & 3, hd, c & 0x1fff));
+        rw_set_agent(l, i, rw_apack(x & 0xff, y & 0xff, d & 3, hd, c & 0x1fff));
         if (v.agent_msg && p.msg_bits) {
             uint32_t bits = 0;
             for (int b = 0; b < p.msg_bits; b++) bits |= (uint32_t)(v.agent_msg[(env * p.n + i) * p.msg_bits + b] & 1) << b;
@@ -247,16 +249,16 @@ __global__ void rw_set_state_kernel(const RwParams p, const rw_state_view v) {
         }
     }
     if (v.shelf_x && v.shelf_y)
-        for (int k = 0; k < p.S; k++) rw_set_shelf_cell(p, l, k, v.shelf_y[env * p.S + k] * p.W + v.shelf_x[env * p.S + k]);
+        for (int k = 0; k < p.S; k++) rw_set_shelf_cell(o, l, k, v.shelf_y[env * p.S + k] * p.W + v.shelf_x[env * p.S + k]);
     if (v.queue)
-        for (int q = 0; q < p.R; q++) rw_set_queue(p, l, q, v.queue[env * p.R + q]);
+        for (int q = 0; q < p.R; q++) rw_set_queue(o, l, q, v.queue[env * p.R + q]);
     if (v.cur_steps) t[p.w_steps * RW_TILE] = v.cur_steps[env];
     if (v.cur_inactive) t[p.w_inact * RW_TILE] = v.cur_inactive[env] & 0x7fffffff;
     // flag worlds where two shelves share a cell (cold path, O(S^2)); see RW_OVERLAP_BIT
     bool overlap = false;
     for (int k = 1; k < p.S && !overlap; k++) {
-        int c = rw_shelf_cell(p, l, k);
-        for (int j = 0; j < k; j++) overlap |= (rw_shelf_cell(p, l, j) == c);
+        int c = rw_shelf_cell(o, l, k);
+        for (int j = 0; j < k; j++) overlap |= (rw_shelf_cell(o, l, j) == c);
     }
     uint32_t wi = (uint32_t)t[p.w_inact * RW_TILE] & ~RW_OVERLAP_BIT;
     t[p.w_inact * RW_TILE] = (int32_t)(wi | (overlap ? RW_OVERLAP_BIT : 0u));
@@ -286,9 +288,7 @@ __global__ void rw_random_actions_kernel(const RwParams p, int32_t *__restrict__
 // ---------------------------------------------------------------- launch wrappers
 // Static specialisations: the four registered warehouse sizes (rware/__init__.py:7-12 with column_height 8) at
 // sensor range 1 and 2 without message bits; every other geometry runs the RwDynamic instantiation.
-#define RW_STATIC_CONFIGS(X) \
-    X(11, 10, 32, 1) X(20, 10, 80, 1) X(20, 16, 144, 1) X(29, 16, 224, 1) \
-    X(11, 10, 32, 2) X(20, 10, 80, 2) X(20, 16, 144, 2) X(29, 16, 224, 2)
+#include "rw_static_configs.h"
 
 typedef void (*rw_kernel_fn)(const RwParams, const int32_t *, float *, float *, uint8_t *, const uint8_t *);
 
@@ -303,6 +303,11 @@ static rw_kernel_fn kernel_for_mode(RwMode mode) {
 
 static rw_kernel_fn select_kernel(RwMode mode, const RwParams &p, bool force_dynamic) {
     if (!force_dynamic && p.msg_bits == 0) {
+#define X(H_, W_, S_, R_, N_, RQ_) \
+    if (p.H == H_ && p.W == W_ && p.S == S_ && p.r == R_ && p.n == N_ && p.R == RQ_) \
+        return kernel_for_mode<RwStatic<H_, W_, S_, R_, 0, N_, RQ_>>(mode);
+        RW_FULL_STATIC_CONFIGS(X)
+#undef X
 #define X(H_, W_, S_, R_) \
     if (p.H == H_ && p.W == W_ && p.S == S_ && p.r == R_) return kernel_for_mode<RwStatic<H_, W_, S_, R_, 0>>(mode);
         RW_STATIC_CONFIGS(X)

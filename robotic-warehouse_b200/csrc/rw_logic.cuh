@@ -100,51 +100,53 @@ RW_HD int rw_ffs32(uint32_t b) {
 // id of the shelf the reference's grid shows on `cell`: the highest id standing there (ref:751-752), 0 if none
 template <class C>
 RW_HD int rw_shelf_at(const RwParams &p, const RwLane &l, uint32_t cell) {
+    const RwOff o = rw_off<C>(p);
     const int S = C::S(p);
     // fast path: without overlaps a cell holds at most one shelf, and almost always it is the one whose home it is
     int id = l.home_id[cell];
-    if (id && (uint32_t)rw_shelf_cell(p, l, id - 1) == cell && !((uint32_t)l.tile[p.w_inact * RW_TILE] & RW_OVERLAP_BIT))
+    if (id && (uint32_t)rw_shelf_cell(o, l, id - 1) == cell && !((uint32_t)l.tile[o.w_inact * RW_TILE] & RW_OVERLAP_BIT))
         return id;
     id = 0;
 #pragma unroll 4
     for (int k2 = 0; k2 < (S >> 1); k2++) {
-        uint32_t w = (uint32_t)l.tile[(p.w_shelf + k2) * RW_TILE];
+        uint32_t w = (uint32_t)l.tile[(o.w_shelf + k2) * RW_TILE];
         if ((w & 0xffffu) == cell) id = 2 * k2 + 1;
         if ((w >> 16) == cell) id = 2 * k2 + 2;
     }
     if (S & 1) {
-        uint32_t w = (uint32_t)l.tile[(p.w_shelf + (S >> 1)) * RW_TILE];
+        uint32_t w = (uint32_t)l.tile[(o.w_shelf + (S >> 1)) * RW_TILE];
         if ((w & 0xffffu) == cell) id = S;
     }
     return id;
 }
 
-RW_HD bool rw_in_queue(const RwParams &p, const RwLane &l, int id) {
-    for (int q = 0; q < p.R; q++)
-        if (rw_queue(p, l, q) == id) return true;
+RW_HD bool rw_in_queue(const RwOff &o, const RwLane &l, int id) {
+    for (int q = 0; q < o.R; q++)
+        if (rw_queue(o, l, q) == id) return true;
     return false;
 }
 
 template <class C>
 RW_HD void rw_build_grid(const RwParams &p, const RwLane &l) {
+    const RwOff o = rw_off<C>(p);
     const int S = C::S(p);
 #pragma unroll 4
     for (int k2 = 0; k2 < (S >> 1); k2++) {  // two shelves per state word
-        uint32_t w = (uint32_t)l.tile[(p.w_shelf + k2) * RW_TILE];
+        uint32_t w = (uint32_t)l.tile[(o.w_shelf + k2) * RW_TILE];
         l.g[w & 0xffffu] = (uint8_t)RW_G_SHELF;
         l.g[w >> 16] = (uint8_t)RW_G_SHELF;
     }
-    if (S & 1) l.g[(uint32_t)l.tile[(p.w_shelf + (S >> 1)) * RW_TILE] & 0xffffu] = (uint8_t)RW_G_SHELF;
-    const bool overlap = ((uint32_t)l.tile[p.w_inact * RW_TILE] & RW_OVERLAP_BIT) != 0;
-    for (int q = 0; q < p.R; q++) {
-        int id = rw_queue(p, l, q);
+    if (S & 1) l.g[(uint32_t)l.tile[(o.w_shelf + (S >> 1)) * RW_TILE] & 0xffffu] = (uint8_t)RW_G_SHELF;
+    const bool overlap = ((uint32_t)l.tile[o.w_inact * RW_TILE] & RW_OVERLAP_BIT) != 0;
+    for (int q = 0; q < o.R; q++) {
+        int id = rw_queue(o, l, q);
         if (!id) continue;
-        uint32_t c = (uint32_t)rw_shelf_cell(p, l, id - 1);
+        uint32_t c = (uint32_t)rw_shelf_cell(o, l, id - 1);
         // with overlapping shelves the reference's grid shows the highest id on the cell; only that one counts
         if (!overlap || rw_shelf_at<C>(p, l, c) == id) l.g[c] |= (uint8_t)RW_G_REQ;
     }
-    for (int i = 0; i < p.n; i++) {
-        uint32_t aw = rw_agent(p, l, i);
+    for (int i = 0; i < o.n; i++) {
+        uint32_t aw = rw_agent(l, i);
         uint32_t c = (uint32_t)(rw_ay(aw) * C::W(p) + rw_ax(aw));
         l.g[c] = (uint8_t)((l.g[c] & (RW_G_SHELF | RW_G_REQ)) | (uint32_t)(i + 1));
     }
@@ -153,15 +155,16 @@ RW_HD void rw_build_grid(const RwParams &p, const RwLane &l) {
 // literal _recalc_grid for worlds flagged with overlapping shelves; also refreshes the flag (O(S^2), cold)
 template <class C>
 RW_HD_NOINLINE void rw_rebuild_grid_slow(const RwParams &p, const RwLane &l) {
+    const RwOff o = rw_off<C>(p);
     uint32_t *gz = reinterpret_cast<uint32_t *>(l.g);
     for (int i = 0; i < (p.grid_env_stride >> 2); i++) gz[i] = 0;
     bool overlap = false;
     for (int k = 0; k < C::S(p) && !overlap; k++) {
-        int c = rw_shelf_cell(p, l, k);
-        for (int j = 0; j < k; j++) overlap |= (rw_shelf_cell(p, l, j) == c);
+        int c = rw_shelf_cell(o, l, k);
+        for (int j = 0; j < k; j++) overlap |= (rw_shelf_cell(o, l, j) == c);
     }
-    uint32_t w = (uint32_t)l.tile[p.w_inact * RW_TILE];
-    l.tile[p.w_inact * RW_TILE] = (int32_t)((w & ~RW_OVERLAP_BIT) | (overlap ? RW_OVERLAP_BIT : 0u));
+    uint32_t w = (uint32_t)l.tile[o.w_inact * RW_TILE];
+    l.tile[o.w_inact * RW_TILE] = (int32_t)((w & ~RW_OVERLAP_BIT) | (overlap ? RW_OVERLAP_BIT : 0u));
     rw_build_grid<C>(p, l);
 }
 
@@ -236,7 +239,8 @@ RW_HD void rw_pyset_add(RwPySet &s, int key, HashOf hash_of) {
 // (NX/classes/coreviews.py:293-300, 342-349; NX/algorithms/components/weakly_connected.py:61-66, 169-196).
 template <class C>
 RW_HD_NOINLINE int rw_tie_first(const RwParams &p, const RwLane &l, uint32_t ties) {
-    const int n = p.n, m = 2 * n;
+    const RwOff o = rw_off<C>(p);
+    const int n = o.n, m = 2 * n;
     // node id of a cell := index of its first appearance in the sequence s_0, t_0, s_1, t_1, ... (DiGraph.add_edge
     // inserts the start node, then the target node, ref:825-846)
     uint8_t first[2 * RW_MAX_AGENTS];
@@ -345,12 +349,13 @@ RW_HD int rw_pick(const RwParams &p, const RwLane &l, uint32_t cand) {
 // new = np_random.choice(candidates), replaces the delivered shelf in place.
 template <class C>
 RW_HD_NOINLINE void rw_resample(const RwParams &p, const RwLane &l, int delivered_id, int64_t env) {
+    const RwOff o = rw_off<C>(p);
     const int S = C::S(p);
     int distinct = 0;
-    for (int q = 0; q < p.R; q++) {
-        int id = rw_queue(p, l, q);
+    for (int q = 0; q < o.R; q++) {
+        int id = rw_queue(o, l, q);
         bool dup = false;
-        for (int j = 0; j < q; j++) dup |= (rw_queue(p, l, j) == id);
+        for (int j = 0; j < q; j++) dup |= (rw_queue(o, l, j) == id);
         distinct += !dup;
     }
     int n_cand = S - distinct;
@@ -361,20 +366,20 @@ RW_HD_NOINLINE void rw_resample(const RwParams &p, const RwLane &l, int delivere
         int pick = (int)rw_bounded(g, (uint32_t)(n_cand - 1));
         rw_pcg_store(g, p.rng, p.E_pad, env);
         for (int s = 1; s <= S; s++) {
-            if (rw_in_queue(p, l, s)) continue;
+            if (rw_in_queue(o, l, s)) continue;
             if (pick-- == 0) { new_id = s; break; }
         }
     }
-    for (int q = 0; q < p.R; q++)
-        if (rw_queue(p, l, q) == delivered_id) { rw_set_queue(p, l, q, new_id); break; }
-    if ((uint32_t)l.tile[p.w_inact * RW_TILE] & RW_OVERLAP_BIT) {
+    for (int q = 0; q < o.R; q++)
+        if (rw_queue(o, l, q) == delivered_id) { rw_set_queue(o, l, q, new_id); break; }
+    if ((uint32_t)l.tile[o.w_inact * RW_TILE] & RW_OVERLAP_BIT) {
         rw_rebuild_grid_slow<C>(p, l);
         return;
     }
     // request bits of the two shelves involved
-    uint32_t cd = (uint32_t)rw_shelf_cell(p, l, delivered_id - 1);
-    if (!rw_in_queue(p, l, delivered_id)) l.g[cd] &= (uint8_t)~RW_G_REQ;
-    l.g[rw_shelf_cell(p, l, new_id - 1)] |= (uint8_t)RW_G_REQ;
+    uint32_t cd = (uint32_t)rw_shelf_cell(o, l, delivered_id - 1);
+    if (!rw_in_queue(o, l, delivered_id)) l.g[cd] &= (uint8_t)~RW_G_REQ;
+    l.g[rw_shelf_cell(o, l, new_id - 1)] |= (uint8_t)RW_G_REQ;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -382,11 +387,12 @@ RW_HD_NOINLINE void rw_resample(const RwParams &p, const RwLane &l, int delivere
 // the occupancy grid (the caller rebuilds it).
 template <class C>
 RW_HD_NOINLINE void rw_reset_lane(const RwParams &p, const RwLane &l, int64_t env) {
+    const RwOff o = rw_off<C>(p);
     RwPcg g;
     rw_pcg_load(g, p.rng, p.E_pad, env);
     const int S = C::S(p), W = C::W(p);
-    for (int k = 0; k < S; k++) rw_set_shelf_cell(p, l, k, p.home_cell[k]);  // ref:771-778
-    const int n = p.n;
+    for (int k = 0; k < S; k++) rw_set_shelf_cell(o, l, k, p.home_cell[k]);  // ref:771-778
+    const int n = o.n;
     // ref:781-785 np_random.choice(arange(H*W), size=n, replace=False): Floyd's algorithm then a shuffle
     const int cells = C::H(p) * W;
     for (int k = 0; k < n; k++) {
@@ -406,25 +412,25 @@ RW_HD_NOINLINE void rw_reset_lane(const RwParams &p, const RwLane &l, int64_t en
         uint32_t loc = l.sc[i * RW_TILE];
         uint32_t y = C::div_w(p, loc);
         uint32_t dir = rw_bounded(g, 3);
-        rw_set_agent(p, l, i, rw_apack((int)(loc - y * (uint32_t)W), (int)y, (int)dir, 0, 0));
-        if (C::mb(p)) l.tile[(p.w_msg + i) * RW_TILE] = 0;
+        rw_set_agent(l, i, rw_apack((int)(loc - y * (uint32_t)W), (int)y, (int)dir, 0, 0));
+        if (C::mb(p)) l.tile[(o.w_msg + i) * RW_TILE] = 0;
     }
     // ref:796-800 np_random.choice(self.shelfs, size=R, replace=False)
-    for (int k = 0; k < p.R; k++) {
-        uint32_t j = (uint32_t)(S - p.R + k);
+    for (int k = 0; k < o.R; k++) {
+        uint32_t j = (uint32_t)(S - o.R + k);
         uint32_t val = rw_bounded(g, j);
         bool found = false;
-        for (int q = 0; q < k; q++) found |= ((uint32_t)rw_queue(p, l, q) == val + 1);
-        rw_set_queue(p, l, k, (int)((found ? j : val) + 1));
+        for (int q = 0; q < k; q++) found |= ((uint32_t)rw_queue(o, l, q) == val + 1);
+        rw_set_queue(o, l, k, (int)((found ? j : val) + 1));
     }
-    for (int i = p.R - 1; i >= 1; i--) {
+    for (int i = o.R - 1; i >= 1; i--) {
         int j = (int)rw_bounded(g, (uint32_t)i);
-        int t = rw_queue(p, l, i);
-        rw_set_queue(p, l, i, rw_queue(p, l, j));
-        rw_set_queue(p, l, j, t);
+        int t = rw_queue(o, l, i);
+        rw_set_queue(o, l, i, rw_queue(o, l, j));
+        rw_set_queue(o, l, j, t);
     }
-    l.tile[p.w_steps * RW_TILE] = 0;  // ref:764-765
-    l.tile[p.w_inact * RW_TILE] = 0;  // (also clears the overlap flag: every shelf is back on its own home cell)
+    l.tile[o.w_steps * RW_TILE] = 0;  // ref:764-765
+    l.tile[o.w_inact * RW_TILE] = 0;  // (also clears the overlap flag: every shelf is back on its own home cell)
     rw_pcg_store(g, p.rng, p.E_pad, env);
 }
 
@@ -437,7 +443,8 @@ RW_HD_NOINLINE void rw_reset_lane(const RwParams &p, const RwLane &l, int64_t en
 // the state tile is still in flight: scratch entry 2i+1 <- action | message bits << 8.  Invalid values become NOOP.
 template <class C>
 RW_HD void rw_load_actions(const RwParams &p, const RwLane &l, const int32_t *act) {
-    const int n = p.n, mb = C::mb(p), A = 1 + mb;
+    const RwOff o = rw_off<C>(p);
+    const int n = o.n, mb = C::mb(p), A = 1 + mb;
     uint32_t bad = 0;
     for (int i = 0; i < n; i++) {
         int a = act[i * A];
@@ -457,14 +464,15 @@ RW_HD void rw_load_actions(const RwParams &p, const RwLane &l, const int32_t *ac
 
 template <class C>
 RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, float *reward, int64_t env) {
-    const int n = p.n, W = C::W(p), H = C::H(p), mb = C::mb(p);
+    const RwOff o = rw_off<C>(p);
+    const int n = o.n, W = C::W(p), H = C::H(p), mb = C::mb(p);
     uint32_t commit = 0, dag = 0;
     // ---- proposals (ref:825-846); actions were decoded into the scratch by rw_load_actions
     for (int i = 0; i < n; i++) {
-        uint32_t aw = rw_agent(p, l, i);
+        uint32_t aw = rw_agent(l, i);
         uint32_t pre = rw_meta(l, i);
         int a = (int)(pre & 7u);
-        if (mb) l.tile[(p.w_msg + i) * RW_TILE] = (int32_t)(pre >> 8);
+        if (mb) l.tile[(o.w_msg + i) * RW_TILE] = (int32_t)(pre >> 8);
         int x = rw_ax(aw), y = rw_ay(aw), tx = x, ty = y;
         if (a == RW_ACT_FORWARD) {  // Agent.req_location ref:102-116, clamped at the walls
             int d = rw_adir(aw);
@@ -480,7 +488,7 @@ RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, float *reward, int64
             uint32_t gt = l.g[t];
             uint32_t o = gt & RW_G_AGENT;
             // ref:829-844 a carrier may not enter a cell holding a shelf unless an agent there carries it
-            if (rw_acarry(aw) && (gt & RW_G_SHELF) && !(o && rw_acarry(rw_agent(p, l, (int)o - 1)))) {
+            if (rw_acarry(aw) && (gt & RW_G_SHELF) && !(o && rw_acarry(rw_agent(l, (int)o - 1)))) {
                 a = RW_ACT_NOOP; t = s; nxt = RW_NXT_SELF; commit |= 1u << i;
             } else {
                 nxt = o ? o - 1 : RW_NXT_SINK;
@@ -551,7 +559,7 @@ RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, float *reward, int64
         }
     }
     // ---- apply (ref:878-899).  Failed agents become NOOP (ref:871-876).
-    const bool overlap = ((uint32_t)l.tile[p.w_inact * RW_TILE] & RW_OVERLAP_BIT) != 0;
+    const bool overlap = ((uint32_t)l.tile[o.w_inact * RW_TILE] & RW_OVERLAP_BIT) != 0;
     uint64_t rew_lo = 0, rew_hi = 0;  // per-agent reward in half units, 4 bits each
     int rew_global = 0;
     uint32_t moved = 0;
@@ -559,7 +567,7 @@ RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, float *reward, int64
         uint32_t m = rw_meta(l, i);
         uint32_t a = rw_m_act(m);
         if (a == RW_ACT_NOOP) continue;
-        uint32_t aw = rw_agent(p, l, i);
+        uint32_t aw = rw_agent(l, i);
         uint32_t st = rw_st(l, i);
         uint32_t s = st & 0xffffu, t = st >> 16;
         if (a == RW_ACT_FORWARD) {
@@ -575,28 +583,28 @@ RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, float *reward, int64
         } else if (a == RW_ACT_LEFT || a == RW_ACT_RIGHT) {  // Agent.req_direction ref:118-125
             uint32_t d = (uint32_t)rw_adir(aw);
             uint32_t nd = ((a == RW_ACT_RIGHT ? 0x4Bu : 0x1Eu) >> (2 * d)) & 3u;
-            rw_set_agent(p, l, i, (aw & ~(3u << 16)) | (nd << 16));
+            rw_set_agent(l, i, (aw & ~(3u << 16)) | (nd << 16));
         } else {  // TOGGLE_LOAD ref:889-899
             if (!rw_acarry(aw)) {
-                if (l.g[s] & RW_G_SHELF) rw_set_agent(p, l, i, aw | ((uint32_t)rw_shelf_at<C>(p, l, s) << 19));
+                if (l.g[s] & RW_G_SHELF) rw_set_agent(l, i, aw | ((uint32_t)rw_shelf_at<C>(p, l, s) << 19));
             } else if (!l.highway[s]) {
                 if (rw_adeliv(aw) && p.reward_type == 2) {
                     if (i < 16) rew_lo += 1ULL << (4 * i); else rew_hi += 1ULL << (4 * (i - 16));
                 }
-                rw_set_agent(p, l, i, aw & 0x3ffffu & ~(1u << 18));
+                rw_set_agent(l, i, aw & 0x3ffffu & ~(1u << 18));
             }
         }
     }
     for (uint32_t b = moved; b; b &= b - 1) {
         int i = rw_ffs32(b);
-        uint32_t aw = rw_agent(p, l, i);
+        uint32_t aw = rw_agent(l, i);
         uint32_t t = rw_st(l, i) >> 16;
         uint32_t ty = C::div_w(p, t), tx = t - ty * (uint32_t)W;
-        rw_set_agent(p, l, i, (aw & ~0xffffu) | tx | (ty << 8));
+        rw_set_agent(l, i, (aw & ~0xffffu) | tx | (ty << 8));
         int carry = rw_acarry(aw);
         if (carry) {
             l.g[t] = (uint8_t)((uint32_t)(i + 1) | (rw_meta(l, i) >> 16));
-            rw_set_shelf_cell(p, l, carry - 1, (int)t);
+            rw_set_shelf_cell(o, l, carry - 1, (int)t);
         } else {
             l.g[t] = (uint8_t)((l.g[t] & (RW_G_SHELF | RW_G_REQ)) | (uint32_t)(i + 1));
         }
@@ -616,7 +624,7 @@ RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, float *reward, int64
         else {
             uint64_t add = (p.reward_type == 1) ? 2ULL : 1ULL;
             if (ai < 16) rew_lo += add << (4 * ai); else rew_hi += add << (4 * (ai - 16));
-            if (p.reward_type == 2) rw_set_agent(p, l, ai, rw_agent(p, l, ai) | (1u << 18));
+            if (p.reward_type == 2) rw_set_agent(l, ai, rw_agent(l, ai) | (1u << 18));
         }
     }
     for (int i = 0; i < n; i++) {
@@ -624,11 +632,11 @@ RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, float *reward, int64
         reward[i] = 0.5f * (float)half;
     }
     // ---- counters / termination (ref:929-941)
-    uint32_t wi = (uint32_t)l.tile[p.w_inact * RW_TILE];
+    uint32_t wi = (uint32_t)l.tile[o.w_inact * RW_TILE];
     int inact = delivered ? 0 : (int)(wi & ~RW_OVERLAP_BIT) + 1;
-    int steps = l.tile[p.w_steps * RW_TILE] + 1;
-    l.tile[p.w_inact * RW_TILE] = (int32_t)((uint32_t)inact | (wi & RW_OVERLAP_BIT));
-    l.tile[p.w_steps * RW_TILE] = steps;
+    int steps = l.tile[o.w_steps * RW_TILE] + 1;
+    l.tile[o.w_inact * RW_TILE] = (int32_t)((uint32_t)inact | (wi & RW_OVERLAP_BIT));
+    l.tile[o.w_steps * RW_TILE] = steps;
     return (p.max_inact && inact >= p.max_inact) || (p.max_steps && steps >= p.max_steps);
 }
 
@@ -636,7 +644,8 @@ RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, float *reward, int64
 // Flattened observation of agent i of the world in `l` (ref:598-674; layout SURVEY.md App. C) -> out[L].
 template <class C>
 RW_HD void rw_obs_agent(const RwParams &p, const RwLane &l, int i, float *out) {
-    uint32_t aw = rw_agent(p, l, i);
+    const RwOff o = rw_off<C>(p);
+    uint32_t aw = rw_agent(l, i);
     const int x = rw_ax(aw), y = rw_ay(aw), d = rw_adir(aw);
     const int W = C::W(p), H = C::H(p);
     out[0] = p.norm_coords ? p.normx[x] : (float)x;  // ref:636-643
@@ -647,7 +656,7 @@ RW_HD void rw_obs_agent(const RwParams &p, const RwLane &l, int i, float *out) {
     out[5] = d == 2 ? 1.0f : 0.0f;
     out[6] = d == 3 ? 1.0f : 0.0f;
     out[7] = l.highway[y * W + x] ? 1.0f : 0.0f;      // ref:647
-    float *o = out + 8;
+    float *oc = out + 8;
     const int r = C::r(p), mb = C::mb(p);
     const uint8_t *gc = l.g + (y * W + x);
 #pragma unroll
@@ -660,18 +669,18 @@ RW_HD void rw_obs_agent(const RwParams &p, const RwLane &l, int i, float *out) {
             const uint32_t ida = gb & RW_G_AGENT;
             uint32_t od = 0, bits = 0;
             if (ida) {
-                od = (uint32_t)rw_adir(rw_agent(p, l, (int)ida - 1));
-                if (mb) bits = (uint32_t)l.tile[(p.w_msg + (int)ida - 1) * RW_TILE];
+                od = (uint32_t)rw_adir(rw_agent(l, (int)ida - 1));
+                if (mb) bits = (uint32_t)l.tile[(o.w_msg + (int)ida - 1) * RW_TILE];
             }
-            o[0] = ida ? 1.0f : 0.0f;                  // ref:656-667: an empty cell reads as direction one-hot [1,0,0,0]
-            o[1] = od == 0 ? 1.0f : 0.0f;
-            o[2] = od == 1 ? 1.0f : 0.0f;
-            o[3] = od == 2 ? 1.0f : 0.0f;
-            o[4] = od == 3 ? 1.0f : 0.0f;
-            for (int b = 0; b < mb; b++) o[5 + b] = (float)((bits >> b) & 1u);
-            o[5 + mb] = (gb & RW_G_SHELF) ? 1.0f : 0.0f;  // ref:668-673
-            o[6 + mb] = (gb & RW_G_REQ) ? 1.0f : 0.0f;
-            o += 7 + mb;
+            oc[0] = ida ? 1.0f : 0.0f;                  // ref:656-667: an empty cell reads as direction one-hot [1,0,0,0]
+            oc[1] = od == 0 ? 1.0f : 0.0f;
+            oc[2] = od == 1 ? 1.0f : 0.0f;
+            oc[3] = od == 2 ? 1.0f : 0.0f;
+            oc[4] = od == 3 ? 1.0f : 0.0f;
+            for (int b = 0; b < mb; b++) oc[5 + b] = (float)((bits >> b) & 1u);
+            oc[5 + mb] = (gb & RW_G_SHELF) ? 1.0f : 0.0f;  // ref:668-673
+            oc[6 + mb] = (gb & RW_G_REQ) ? 1.0f : 0.0f;
+            oc += 7 + mb;
         }
     }
 }

@@ -20,7 +20,7 @@ def _load():
     if _lib is None:
         src = os.path.join(_HERE, "hostsim.cpp")
         csrc = os.path.join(os.path.dirname(os.path.dirname(_HERE)), "robotic-warehouse_b200", "csrc")
-        deps = [src] + [os.path.join(csrc, f) for f in ("rw_logic.cuh", "rw_common.h", "rw_host_layout.h")]
+        deps = [src] + [os.path.join(csrc, f) for f in ("rw_logic.cuh", "rw_common.h", "rw_host_layout.h", "rw_static_configs.h")]
         if not os.path.exists(_LIB) or os.path.getmtime(_LIB) < max(os.path.getmtime(d) for d in deps):
             os.makedirs(os.path.dirname(_LIB), exist_ok=True)
             subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", _LIB, src], check=True)
@@ -36,6 +36,7 @@ def _load():
         L.sim_error_count.restype = ctypes.c_longlong
         L.sim_seed.argtypes = [vp, vp, vp]
         L.sim_run.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp]
+        L.sim_force_dynamic.argtypes = [ctypes.c_int]
         L.sim_get_state.argtypes = [vp, ctypes.POINTER(RwStateView)]
         L.sim_set_state.argtypes = [vp, ctypes.POINTER(RwStateView)]
         _lib = L

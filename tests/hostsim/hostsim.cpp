@@ -122,9 +122,7 @@ static void sim_run_t(Sim *s, int mode, const int32_t *actions, float *obs, floa
     }
 }
 
-#define RW_STATIC_CONFIGS(X) \
-    X(11, 10, 32, 1) X(20, 10, 80, 1) X(20, 16, 144, 1) X(29, 16, 224, 1) \
-    X(11, 10, 32, 2) X(20, 10, 80, 2) X(20, 16, 144, 2) X(29, 16, 224, 2)
+#include "../../robotic-warehouse_b200/csrc/rw_static_configs.h"
 
 extern "C" {
 
@@ -135,6 +133,11 @@ void sim_force_dynamic(int on) { g_force_dynamic = on; }
 void sim_run(Sim *s, int mode, const int32_t *actions, float *obs, float *reward, uint8_t *done, const uint8_t *mask) {
     const RwParams &p = s->p;
     if (!g_force_dynamic && p.msg_bits == 0) {
+#define X(H_, W_, S_, R_, N_, RQ_) \
+    if (p.H == H_ && p.W == W_ && p.S == S_ && p.r == R_ && p.n == N_ && p.R == RQ_) \
+        return sim_run_t<RwStatic<H_, W_, S_, R_, 0, N_, RQ_>>(s, mode, actions, obs, reward, done, mask);
+        RW_FULL_STATIC_CONFIGS(X)
+#undef X
 #define X(H_, W_, S_, R_) \
     if (p.H == H_ && p.W == W_ && p.S == S_ && p.r == R_) return sim_run_t<RwStatic<H_, W_, S_, R_, 0>>(s, mode, actions, obs, reward, done, mask);
         RW_STATIC_CONFIGS(X)
@@ -149,8 +152,9 @@ void sim_get_state(Sim *s, const rw_state_view *v) {
     for (int64_t env = 0; env < p.E; env++) {
         int32_t *t = p.state + (size_t)(env >> 5) * p.nw * RW_TILE + (env & 31);
         RwLane l{t, nullptr, nullptr, nullptr, nullptr};
+        const RwOff o = rw_off<RwDynamic>(p);
         for (int i = 0; i < p.n; i++) {
-            uint32_t aw = rw_agent(p, l, i);
+            uint32_t aw = rw_agent(l, i);
             if (v->agent_x) v->agent_x[env * p.n + i] = rw_ax(aw);
             if (v->agent_y) v->agent_y[env * p.n + i] = rw_ay(aw);
             if (v->agent_dir) v->agent_dir[env * p.n + i] = rw_adir(aw);
@@ -161,12 +165,12 @@ void sim_get_state(Sim *s, const rw_state_view *v) {
                     v->agent_msg[(env * p.n + i) * p.msg_bits + b] = ((uint32_t)t[(p.w_msg + i) * RW_TILE] >> b) & 1u;
         }
         for (int k = 0; k < p.S; k++) {
-            int c = rw_shelf_cell(p, l, k);
+            int c = rw_shelf_cell(o, l, k);
             if (v->shelf_x) v->shelf_x[env * p.S + k] = c % p.W;
             if (v->shelf_y) v->shelf_y[env * p.S + k] = c / p.W;
         }
         if (v->queue)
-            for (int q = 0; q < p.R; q++) v->queue[env * p.R + q] = rw_queue(p, l, q);
+            for (int q = 0; q < p.R; q++) v->queue[env * p.R + q] = rw_queue(o, l, q);
         if (v->cur_steps) v->cur_steps[env] = t[p.w_steps * RW_TILE];
         if (v->cur_inactive) v->cur_inactive[env] = (int32_t)((uint32_t)t[p.w_inact * RW_TILE] & ~RW_OVERLAP_BIT);
         if (v->rng)
@@ -179,14 +183,15 @@ void sim_set_state(Sim *s, const rw_state_view *v) {
     for (int64_t env = 0; env < p.E; env++) {
         int32_t *t = p.state + (size_t)(env >> 5) * p.nw * RW_TILE + (env & 31);
         RwLane l{t, nullptr, nullptr, nullptr, nullptr};
+        const RwOff o = rw_off<RwDynamic>(p);
         for (int i = 0; i < p.n; i++) {
-            uint32_t aw = rw_agent(p, l, i);
+            uint32_t aw = rw_agent(l, i);
             int x = v->agent_x ? v->agent_x[env * p.n + i] : rw_ax(aw);
             int y = v->agent_y ? v->agent_y[env * p.n + i] : rw_ay(aw);
             int d = v->agent_dir ? v->agent_dir[env * p.n + i] : rw_adir(aw);
             int c = v->agent_carry ? v->agent_carry[env * p.n + i] : rw_acarry(aw);
             int hd = v->agent_has_delivered ? (v->agent_has_delivered[env * p.n + i] != 0) : rw_adeliv(aw);
-            rw_set_agent(p, l, i, rw_apack(x & 0xff, y & 0xff, d & 3, hd, c & 0x1fff));
+            rw_set_agent(l, i, rw_apack(x & 0xff, y & 0xff, d & 3, hd, c & 0x1fff));
             if (v->agent_msg && p.msg_bits) {
                 uint32_t bits = 0;
                 for (int b = 0; b < p.msg_bits; b++) bits |= (uint32_t)(v->agent_msg[(env * p.n + i) * p.msg_bits + b] & 1) << b;
@@ -194,15 +199,15 @@ void sim_set_state(Sim *s, const rw_state_view *v) {
             }
         }
         if (v->shelf_x && v->shelf_y)
-            for (int k = 0; k < p.S; k++) rw_set_shelf_cell(p, l, k, v->shelf_y[env * p.S + k] * p.W + v->shelf_x[env * p.S + k]);
+            for (int k = 0; k < p.S; k++) rw_set_shelf_cell(o, l, k, v->shelf_y[env * p.S + k] * p.W + v->shelf_x[env * p.S + k]);
         if (v->queue)
-            for (int q = 0; q < p.R; q++) rw_set_queue(p, l, q, v->queue[env * p.R + q]);
+            for (int q = 0; q < p.R; q++) rw_set_queue(o, l, q, v->queue[env * p.R + q]);
         if (v->cur_steps) t[p.w_steps * RW_TILE] = v->cur_steps[env];
         if (v->cur_inactive) t[p.w_inact * RW_TILE] = v->cur_inactive[env] & 0x7fffffff;
         bool overlap = false;
         for (int k = 1; k < p.S && !overlap; k++) {
-            int c = rw_shelf_cell(p, l, k);
-            for (int j = 0; j < k; j++) overlap |= (rw_shelf_cell(p, l, j) == c);
+            int c = rw_shelf_cell(o, l, k);
+            for (int j = 0; j < k; j++) overlap |= (rw_shelf_cell(o, l, j) == c);
         }
         uint32_t wi = (uint32_t)t[p.w_inact * RW_TILE] & ~RW_OVERLAP_BIT;
         t[p.w_inact * RW_TILE] = (int32_t)(wi | (overlap ? RW_OVERLAP_BIT : 0u));

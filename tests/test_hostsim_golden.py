@@ -13,3 +13,24 @@ def test_replays_reference_trajectory(name, backend):
     # 37 worlds: two tiles, the second one ragged; every world must produce the reference trajectory
     drv = replay.VecDriver(fx, backend_factory(backend), num_envs=37)
     assert replay.replay(drv, fx) == len(fx["actions"])
+
+
+@pytest.mark.parametrize("backend", backend_params())
+@pytest.mark.parametrize("name", ["tiny4_indiv", "large16_r2"])
+def test_dynamic_instantiation_matches_too(name, backend, monkeypatch):
+    """The registered geometries normally run static specialisations; force the fully dynamic kernel as well."""
+    fx = replay.load_fixture(name)
+    if backend == "hostsim":
+        from hostsim import backend as hs
+        hs._load().sim_force_dynamic(1)
+    else:
+        monkeypatch.setenv("RWARE_B200_FORCE_DYNAMIC", "1")
+    try:
+        drv = replay.VecDriver(fx, backend_factory(backend), num_envs=33)
+        assert replay.replay(drv, fx, max_steps=400) == 400
+    finally:
+        if backend == "hostsim":
+            hs._load().sim_force_dynamic(0)
+        else:
+            monkeypatch.setenv("RWARE_B200_FORCE_DYNAMIC", "0")
+            replay.VecDriver(fx, backend_factory(backend), num_envs=1)  # resets the library-wide switch
