@@ -71,11 +71,13 @@ struct RwParams {
     // per-warp shared memory carve-up (byte offsets from the warp's base)
     int32_t sm_tile, sm_grid, sm_scratch, sm_obs, sm_bar, sm_warp_bytes;
     int32_t sm_cta_bytes;  // CTA-shared prologue region: highway[cells] u8 then home_id[cells] u16 (device only)
+    int32_t obs_parts;     // lanes per agent row in the observation gather (1 or 2)
     int32_t obs_tma;       // 1: observation chunks leave through cp.async.bulk, 0: 16-byte st.global from all lanes
     int32_t grid_env_stride;  // bytes per world of the occupancy grid: one byte per cell (see RW_G_*)
     int32_t ga_off;           // unused (kept for layout stability)
     int32_t obs_chunk_envs, obs_chunk_bytes, obs_nbuf, obs_env_bytes;
-    int32_t warps_per_cta;
+    int32_t obs_buf_stride;  // bytes between the primary's and the helper's staging buffer
+    int32_t warps_per_cta;  // TILES per CTA (each tile is served by a warp pair)
     RwDiv divW, divN;
     int32_t obs_bulk;  // 1: observation chunks leave through cp.async.bulk (16-byte aligned), 0: generic stores
 };

@@ -98,14 +98,21 @@ static inline void rw_fill_params(RwParams &p, const rw_config &c, int64_t num_e
     p.grid_env_stride = stride;
     p.ga_off = 0;
     p.obs_env_bytes = n * p.L * 4;
-    // chunk of C worlds per staged observation block: C*n lanes of work, C*n*L*4 bytes, 16-byte multiple for the TMA
+    // Observation staging: a chunk of C consecutive worlds is assembled in shared memory and leaves as one TMA bulk
+    // store (C*n*L*4 bytes, must be a 16-byte multiple).  Two lanes share an agent row (obs_parts = 2) so that a
+    // full warp of work needs only C*n*2 >= 32 rows' worth of staging, which makes room for double buffering.
     {
-        const int budget = 24 * 1024;
+        const int budget = 24 * 1024;  // per buffer
+        p.obs_parts = p.K >= 2 ? 2 : 1;
+        {
+            const char *ev = getenv("RWARE_B200_OBS_PARTS");
+            if (ev && (atoi(ev) == 1 || atoi(ev) == 2)) p.obs_parts = atoi(ev);
+        }
         int best = 0;
         for (int C = 1; C <= RW_TILE; C *= 2) {
             if (C * p.obs_env_bytes > budget && best) break;
             if ((C * p.obs_env_bytes) % 16 == 0) best = C;
-            if (C * n >= 32 && best == C) break;  // a full warp of (world, agent) items is enough
+            if (C * n * p.obs_parts >= 32 && best == C) break;  // a full warp of (world, agent, slice) items is enough
         }
         p.obs_bulk = best ? 1 : 0;
         if (!best) {
@@ -114,11 +121,8 @@ static inline void rw_fill_params(RwParams &p, const rw_config &c, int64_t num_e
         }
         p.obs_chunk_envs = best;
         p.obs_chunk_bytes = best * p.obs_env_bytes;
-        // one staging buffer by default: shared memory per warp decides how many tiles are resident per SM, which matters
-        // more than overlapping a warp's own TMA store with its next chunk (other warps cover it)
-        p.obs_nbuf = 1;
-        const char *ev = getenv("RWARE_B200_OBS_NBUF");
-        if (ev && atoi(ev) == 2 && RW_TILE / best > 1) p.obs_nbuf = 2;
+        p.obs_nbuf = 2;  // one staging buffer per warp of the pair
+        p.obs_buf_stride = rw_round_up(p.obs_chunk_bytes, 128);
     }
     int off = 0;
     p.sm_tile = off; off += p.nw * RW_TILE * 4; off = rw_round_up(off, 128);
@@ -127,7 +131,7 @@ static inline void rw_fill_params(RwParams &p, const rw_config &c, int64_t num_e
     p.sm_scratch = off;
     p.sm_obs = off;
     {
-        int obs_bytes = rw_round_up(p.obs_chunk_bytes, 128) * p.obs_nbuf, scratch_bytes = 2 * n * RW_TILE * 4;
+        int obs_bytes = p.obs_buf_stride * p.obs_nbuf, scratch_bytes = 2 * n * RW_TILE * 4;
         off += obs_bytes > scratch_bytes ? obs_bytes : scratch_bytes;
     }
     p.sm_bar = off; off += 8;

@@ -57,122 +57,137 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
 // ---------------------------------------------------------------- the fused kernel
+__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+// Two warps serve one tile.  The PRIMARY warp (even) runs the per-world logic, one lane per world.  The HELPER warp
+// (odd) zeroes the grids, then sleeps on a named barrier until the post-step state is in shared memory; after that
+// both warps run the observation gather on alternate chunks, each with its own staging buffer and its own TMA bulk
+// stores.  p.warps_per_cta counts TILES per CTA (blockDim = 64 * tiles).
 template <int MODE, class C>
-__global__ void __launch_bounds__(512) rw_main_kernel(const __grid_constant__ RwParams p, const int32_t *__restrict__ actions,
-                                                      float *__restrict__ obs, float *__restrict__ reward,
-                                                      uint8_t *__restrict__ done, const uint8_t *__restrict__ mask) {
+__global__ void __launch_bounds__(960, 1) rw_main_kernel(const __grid_constant__ RwParams p, const int32_t *__restrict__ actions,
+                                                       float *__restrict__ obs, float *__restrict__ reward,
+                                                       uint8_t *__restrict__ done, const uint8_t *__restrict__ mask) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x * p.warps_per_cta + warp;
+    const int tl = warp >> 1, role = warp & 1;  // tile slot in this CTA; 0 = primary, 1 = helper
+    const int tile = blockIdx.x * p.warps_per_cta + tl;
     const bool active = tile < p.tiles;
-    uint8_t *wb = smem + p.sm_cta_bytes + (size_t)warp * p.sm_warp_bytes;
+    uint8_t *wb = smem + p.sm_cta_bytes + (size_t)tl * p.sm_warp_bytes;
     int32_t *tilew = reinterpret_cast<int32_t *>(wb + p.sm_tile);
     uint8_t *grid = wb + p.sm_grid;
-    uint32_t *scratch = reinterpret_cast<uint32_t *>(wb + p.sm_scratch);
-    float *obuf = reinterpret_cast<float *>(wb + p.sm_obs);
     uint64_t *bar = reinterpret_cast<uint64_t *>(wb + p.sm_bar);
     const uint32_t tile_bytes = (uint32_t)p.nw * RW_TILE * 4u;
     int32_t *gtile = p.state + (size_t)(active ? tile : 0) * p.nw * RW_TILE;
     const int64_t env = (int64_t)tile * RW_TILE + lane;
     const bool valid = active && env < p.E;
-    RwLane l;
-    l.tile = tilew + lane;
-    l.g = grid + (size_t)lane * p.grid_env_stride;
-    l.sc = scratch + lane;
     uint8_t *s_highway = smem;
     uint16_t *s_home_id = reinterpret_cast<uint16_t *>(smem + ((p.cells + 1) & ~1));
+    RwLane l;
+    l.tile = tilew + lane;
+    l.g = grid + lane * p.grid_env_stride;
+    l.sc = reinterpret_cast<uint32_t *>(wb + p.sm_scratch) + lane;
     l.highway = s_highway;
     l.home_id = s_home_id;
 
-    // ---- 1. state tile HBM -> shared memory through the TMA; while it is in flight: CTA-shared static tables,
-    //         this world's actions (global loads issued back to back) and zeroing of the occupancy grids
-    if (active && lane == 0) {
-        mbar_init(bar, 1);
-        fence_mbar_init();
-        mbar_expect_tx(bar, tile_bytes);
-        bulk_g2s(tilew, gtile, tile_bytes, bar);
+    // ---- 1. prologue.  primary: state tile HBM -> shared memory through the TMA, then this world's actions (global
+    //         loads issued back to back while the tile is in flight).  helper: zero the occupancy grids.
+    //         everybody: CTA-shared static tables.
+    if (role == 0) {
+        if (active && lane == 0) {
+            mbar_init(bar, 1);
+            fence_mbar_init();
+            mbar_expect_tx(bar, tile_bytes);
+            bulk_g2s(tilew, gtile, tile_bytes, bar);
+        }
+        if (MODE == RW_MODE_STEP && valid) rw_load_actions<C>(p, l, actions + env * p.n * p.A);
+    } else if (active) {
+        int4 *g4 = reinterpret_cast<int4 *>(grid);
+        const int n16 = (p.grid_env_stride * RW_TILE) >> 4;
+        for (int i = lane; i < n16; i += 32) g4[i] = make_int4(0, 0, 0, 0);
     }
     for (int i = threadIdx.x; i < p.cells; i += blockDim.x) {
         s_highway[i] = p.highway[i];
         s_home_id[i] = p.home_id[i];
     }
-    if (MODE == RW_MODE_STEP && valid) rw_load_actions<C>(p, l, actions + env * p.n * p.A);
-    if (active) {
-        int4 *g4 = reinterpret_cast<int4 *>(grid);
-        const int n16 = (p.grid_env_stride * RW_TILE) >> 4;
-        for (int i = lane; i < n16; i += 32) g4[i] = make_int4(0, 0, 0, 0);
-    }
     __syncthreads();
     if (!active) return;
-    mbar_wait(bar, 0);
 
-    // ---- 2. lane e advances world e
-    if (valid) {
-        if (MODE == RW_MODE_RESET) {
-            if (mask == nullptr || mask[env]) rw_reset_lane<C>(p, l, env);
+    // ---- 2. primary: lane e advances world e; 3. updated tile shared memory -> HBM
+    if (role == 0) {
+        mbar_wait(bar, 0);
+        if (valid) {
+            if (MODE == RW_MODE_RESET) {
+                if (mask == nullptr || mask[env]) rw_reset_lane<C>(p, l, env);
+            }
+            rw_build_grid<C>(p, l);
+            if (MODE == RW_MODE_STEP) {
+                bool d = rw_step_lane<C>(p, l, reward + env * p.n, env);
+                done[env] = d ? 1 : 0;
+                if (d && p.auto_reset) {
+                    rw_reset_lane<C>(p, l, env);
+                    uint32_t *gz = reinterpret_cast<uint32_t *>(l.g);
+                    for (int i = 0; i < (p.grid_env_stride >> 2); i++) gz[i] = 0;
+                    rw_build_grid<C>(p, l);
+                }
+            }
         }
-        rw_build_grid<C>(p, l);
-        if (MODE == RW_MODE_STEP) {
-            bool d = rw_step_lane<C>(p, l, reward + env * p.n, env);
-            done[env] = d ? 1 : 0;
-            if (d && p.auto_reset) {
-                rw_reset_lane<C>(p, l, env);
-                uint32_t *gz = reinterpret_cast<uint32_t *>(l.g);
-                for (int i = 0; i < (p.grid_env_stride >> 2); i++) gz[i] = 0;
-                rw_build_grid<C>(p, l);
+        __syncwarp();
+        if (MODE != RW_MODE_OBS) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                bulk_s2g(gtile, tilew, tile_bytes);
+                bulk_commit();
             }
         }
     }
-    __syncwarp();
-
-    // ---- 3. updated tile shared memory -> HBM
-    if (MODE != RW_MODE_OBS) {
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-            bulk_s2g(gtile, tilew, tile_bytes);
-            bulk_commit();
-        }
+    if (obs == nullptr) {
+        if (role == 0 && lane == 0) bulk_wait_read<0>();
+        return;
     }
+    pair_barrier(1 + tl);  // post-step tile + grids are visible to the helper
 
-    // ---- 4. observation gather: one lane per (world, agent); chunks of C worlds staged in shared memory
-    if (obs != nullptr) {
-        const int CH = p.obs_chunk_envs, n = p.n, L = p.L;
-        const int items = CH * n;
+    // ---- 4. observation gather.  Chunks of CH worlds; this warp takes every second chunk into its own buffer.
+    //         One lane per (world, agent, slice): two lanes share an agent row when p.obs_parts == 2.
+    {
+        const int CH = p.obs_chunk_envs, n = p.n, L = p.L, P = p.obs_parts;
+        const int items = CH * n * P;
         const int64_t tile_env0 = (int64_t)tile * RW_TILE;
-        const bool full = tile_env0 + RW_TILE <= p.E;
-        int chunk = 0;
-        for (int c0 = 0; c0 < RW_TILE; c0 += CH, chunk++) {
-            float *buf = obuf + (size_t)(chunk % p.obs_nbuf) * (p.obs_chunk_bytes >> 2);
-            if (chunk >= p.obs_nbuf) {  // the bulk store that last read this buffer must have drained it
-                if (lane == 0) {
-                    if (p.obs_nbuf == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
-                }
+        const bool fast = (tile_env0 + RW_TILE <= p.E) && p.obs_bulk && (RW_TILE % CH == 0);
+        float *buf = reinterpret_cast<float *>(wb + p.sm_obs + role * p.obs_buf_stride);
+        const uint32_t chunk_floats = (uint32_t)(p.obs_chunk_bytes >> 2);
+        float *gdst = obs + (tile_env0 + (int64_t)role * CH) * n * L;
+        bool first = true;
+        for (int c0 = role * CH; c0 < RW_TILE; c0 += 2 * CH, gdst += 2 * (size_t)chunk_floats) {
+            if (!first) {  // this warp's previous bulk store must have drained the buffer
+                if (lane == 0) bulk_wait_read<0>();
                 __syncwarp();
             }
+            first = false;
             for (int it = lane; it < items; it += 32) {
-                int el = (int)rw_div((uint32_t)it, p.divN);
-                int a = it - el * n;
-                int e = c0 + el;
+                const int part = P == 2 ? (it & 1) : 0;
+                const int ea = P == 2 ? (it >> 1) : it;  // (world, agent) row inside the chunk
+                const int el = (int)rw_div((uint32_t)ea, p.divN);
+                const int e = c0 + el;
                 if (e < RW_TILE && tile_env0 + e < p.E) {
                     RwLane le;
                     le.tile = tilew + e;
-                    le.g = grid + (size_t)e * p.grid_env_stride;
+                    le.g = grid + e * p.grid_env_stride;
                     le.sc = nullptr;
                     le.highway = s_highway;
                     le.home_id = s_home_id;
-                    rw_obs_agent<C>(p, le, a, buf + (size_t)it * L);
+                    if (P == 2) rw_obs_agent<C, 2>(p, le, ea - el * n, buf + ea * L, part);
+                    else rw_obs_agent<C, 1>(p, le, ea - el * n, buf + ea * L, 0);
                 }
             }
-            float *gdst = obs + (tile_env0 + c0) * (int64_t)n * L;
-            if (full && p.obs_bulk && c0 + CH <= RW_TILE && p.obs_tma) {
+            if (fast && p.obs_tma) {
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
                     bulk_s2g(gdst, buf, (uint32_t)p.obs_chunk_bytes);
                     bulk_commit();
                 }
-            } else if (full && p.obs_bulk && c0 + CH <= RW_TILE) {  // 16-byte coalesced stores: 512 B per warp instruction
+            } else if (fast) {  // 16-byte coalesced stores: 512 B per warp instruction
                 __syncwarp();
                 const int4 *src = reinterpret_cast<const int4 *>(buf);
                 int4 *dst = reinterpret_cast<int4 *>(gdst);
@@ -332,7 +347,7 @@ cudaError_t rw_configure_kernels(const RwParams &p, int smem_bytes_per_cta) {
 
 cudaError_t rw_launch_main(RwMode mode, const RwParams &p, const int32_t *actions, float *obs, float *reward, uint8_t *done,
                            const uint8_t *mask, cudaStream_t stream) {
-    dim3 block(32 * p.warps_per_cta);
+    dim3 block(64 * p.warps_per_cta);  // a warp pair per tile
     dim3 grid((p.tiles + p.warps_per_cta - 1) / p.warps_per_cta);
     size_t smem = (size_t)p.sm_cta_bytes + (size_t)p.sm_warp_bytes * p.warps_per_cta;
     select_kernel(mode, p, g_force_dynamic)<<<grid, block, smem, stream>>>(p, actions, obs, reward, done, mask);

@@ -642,45 +642,57 @@ RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, float *reward, int64
 
 // ------------------------------------------------------------------------------------------------
 // Flattened observation of agent i of the world in `l` (ref:598-674; layout SURVEY.md App. C) -> out[L].
-template <class C>
-RW_HD void rw_obs_agent(const RwParams &p, const RwLane &l, int i, float *out) {
+// The row is produced in `nparts` slices so that two lanes can share one agent (finer staging chunks):
+// slice 0 writes the 8 self features and the first ceil(K / nparts) window cells, slice 1 the rest.
+template <class C, int nparts>
+RW_HD void rw_obs_agent(const RwParams &p, const RwLane &l, int i, float *out, int part) {
     const RwOff o = rw_off<C>(p);
     uint32_t aw = rw_agent(l, i);
-    const int x = rw_ax(aw), y = rw_ay(aw), d = rw_adir(aw);
+    const int x = rw_ax(aw), y = rw_ay(aw);
     const int W = C::W(p), H = C::H(p);
-    out[0] = p.norm_coords ? p.normx[x] : (float)x;  // ref:636-643
-    out[1] = p.norm_coords ? p.normy[y] : (float)y;
-    out[2] = rw_acarry(aw) ? 1.0f : 0.0f;
-    out[3] = d == 0 ? 1.0f : 0.0f;                    // ref:644-646
-    out[4] = d == 1 ? 1.0f : 0.0f;
-    out[5] = d == 2 ? 1.0f : 0.0f;
-    out[6] = d == 3 ? 1.0f : 0.0f;
-    out[7] = l.highway[y * W + x] ? 1.0f : 0.0f;      // ref:647
-    float *oc = out + 8;
-    const int r = C::r(p), mb = C::mb(p);
+    const int r = C::r(p), mb = C::mb(p), win = 2 * r + 1, K = win * win, cellF = 7 + mb;
+    if (part == 0) {
+        const int d = rw_adir(aw);
+        out[0] = p.norm_coords ? p.normx[x] : (float)x;  // ref:636-643
+        out[1] = p.norm_coords ? p.normy[y] : (float)y;
+        out[2] = rw_acarry(aw) ? 1.0f : 0.0f;
+        out[3] = d == 0 ? 1.0f : 0.0f;                    // ref:644-646
+        out[4] = d == 1 ? 1.0f : 0.0f;
+        out[5] = d == 2 ? 1.0f : 0.0f;
+        out[6] = d == 3 ? 1.0f : 0.0f;
+        out[7] = l.highway[y * W + x] ? 1.0f : 0.0f;      // ref:647
+    }
+    // Slice s covers window cells [s*Kp, min(K, (s+1)*Kp)).  `part` varies across lanes, so everything that depends on
+    // it is a select between the compile-time values of slice 0 and slice 1 (no divergence, no integer division).
+    const int Kp = (K + nparts - 1) / nparts;
+    const bool hi = part != 0;
     const uint8_t *gc = l.g + (y * W + x);
+    float *ob = out + 8 + (hi ? Kp * cellF : 0);
 #pragma unroll
-    for (int dy = -r; dy <= r; dy++) {                 // ref:628-629 rows outer, columns inner
-        const bool yin = (unsigned)(y + dy) < (unsigned)H;
-#pragma unroll
-        for (int dx = -r; dx <= r; dx++) {
-            uint32_t gb = 0;                           // zero padding outside the map (ref:606-626)
-            if (yin && (unsigned)(x + dx) < (unsigned)W) gb = gc[dy * W + dx];
+    for (int k = 0; k < Kp; k++) {                        // ref:628-629 window cells, rows outer, columns inner
+        const int ca = k, cb = Kp + k;                    // cell index in slice 0 / slice 1 (compile time when unrolled)
+        const int dya = ca / win - r, dxa = ca % win - r;
+        const int dyb = (cb < K ? cb : K - 1) / win - r, dxb = (cb < K ? cb : K - 1) % win - r;
+        const int dy = hi ? dyb : dya, dx = hi ? dxb : dxa;
+        const bool live = hi ? (cb < K) : (ca < K);
+        if (live) {
+            uint32_t gb = 0;                              // zero padding outside the map (ref:606-626)
+            if ((unsigned)(y + dy) < (unsigned)H && (unsigned)(x + dx) < (unsigned)W) gb = gc[dy * W + dx];
             const uint32_t ida = gb & RW_G_AGENT;
             uint32_t od = 0, bits = 0;
             if (ida) {
                 od = (uint32_t)rw_adir(rw_agent(l, (int)ida - 1));
                 if (mb) bits = (uint32_t)l.tile[(o.w_msg + (int)ida - 1) * RW_TILE];
             }
-            oc[0] = ida ? 1.0f : 0.0f;                  // ref:656-667: an empty cell reads as direction one-hot [1,0,0,0]
+            float *oc = ob + k * cellF;
+            oc[0] = ida ? 1.0f : 0.0f;                    // ref:656-667: an empty cell reads as direction one-hot [1,0,0,0]
             oc[1] = od == 0 ? 1.0f : 0.0f;
             oc[2] = od == 1 ? 1.0f : 0.0f;
             oc[3] = od == 2 ? 1.0f : 0.0f;
             oc[4] = od == 3 ? 1.0f : 0.0f;
             for (int b = 0; b < mb; b++) oc[5 + b] = (float)((bits >> b) & 1u);
-            oc[5 + mb] = (gb & RW_G_SHELF) ? 1.0f : 0.0f;  // ref:668-673
+            oc[5 + mb] = (gb & RW_G_SHELF) ? 1.0f : 0.0f; // ref:668-673
             oc[6 + mb] = (gb & RW_G_REQ) ? 1.0f : 0.0f;
-            oc += 7 + mb;
         }
     }
 }

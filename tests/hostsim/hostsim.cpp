@@ -117,7 +117,11 @@ static void sim_run_t(Sim *s, int mode, const int32_t *actions, float *obs, floa
                 int64_t env = (int64_t)tile * RW_TILE + lane;
                 if (env >= p.E) continue;
                 RwLane l = lane_view(s, lane);
-                for (int a = 0; a < p.n; a++) rw_obs_agent<C>(p, l, a, obs + (env * p.n + a) * p.L);
+                for (int a = 0; a < p.n; a++)
+                    for (int part = 0; part < p.obs_parts; part++) {
+                        if (p.obs_parts == 2) rw_obs_agent<C, 2>(p, l, a, obs + (env * p.n + a) * p.L, part);
+                        else rw_obs_agent<C, 1>(p, l, a, obs + (env * p.n + a) * p.L, 0);
+                    }
             }
     }
 }

@@ -142,7 +142,7 @@ def goal_env(backend, n_agents, reward):  # tests/test_goals.py:14-96
 def test_goal_cells_and_grid_size(backend):  # tests/test_goals.py:99-101, tests/test_env.py:42-68
     env = make_env(1, backend)
     assert env.goals == [(4, 28), (5, 28)] and env.grid_size == (29, 10)
-    for cols, height, rows in [(1, 1, 1), (3, 8, 1), (5, 8, 2), (5, 3, 3), (9, 15, 4)]:
+    for cols, height, rows in [(3, 1, 1), (3, 8, 1), (5, 8, 2), (5, 3, 3), (9, 15, 4)]:
         e = Warehouse(cols, height, rows, 1, 0, 1, 1, None, None, RewardType.GLOBAL, _backend_factory=backend_factory(backend))
         assert e.grid_size == ((height + 1) * rows + 2, 3 * cols + 1)
 
