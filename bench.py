@@ -197,9 +197,11 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        for i in range(2000):  # ~70 ms of load before the timed region so that the clock samples are taken under load
-            one_step(i)
-        torch.cuda.synchronize()
+    for i in range(2000):  # ~70 ms of load before the timed region (every rank: the gather is a collective) so that
+        one_step(i)        # the nvidia-smi clock samples are taken under load
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     torch.cuda.synchronize()

@@ -1,8 +1,6 @@
 set -x
 cd $GRAFT_REPO_ROOT
-nproc
-timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -3
-python bench.py --impl reference --steps 1 --warmup 0 2>&1 | tail -1 > gpurun_out/bench_ref_r1.json; cat gpurun_out/bench_ref_r1.json | cut -c1-400
-python bench.py 2>&1 | tail -1 > gpurun_out/bench_r1.json; cat gpurun_out/bench_r1.json
-ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 60 --csv --log-file gpurun_out/launches_r1.csv python bench.py --steps 10 --warmup 5 --no-cpu-baseline --e2e-steps 2 > gpurun_out/bench_under_ncu.log 2>&1
-tail -5 gpurun_out/launches_r1.csv
+nvidia-smi -L
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 100 --warmup 10 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_2gpu.json; cut -c1-700 gpurun_out/bench_2gpu.json
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 100 --warmup 10 --no-cpu-baseline --gather 2>&1 | tail -1 > gpurun_out/bench_2gpu_gather.json; cut -c1-700 gpurun_out/bench_2gpu_gather.json
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --impl reference --gpus 2 --steps 1 --warmup 0 --ref-seconds 3 2>&1 | tail -1 | cut -c1-300
