@@ -10,9 +10,11 @@ A "step" is ONE launch of the fused kernel (rw_step) over the whole batch of wor
 proposals, collision resolution, apply, deliveries/resample, counters, in-kernel auto-reset and the observation gather.
 Workload (N=1): BASELINE.json configs[1] = rware-tiny-4ag-v1 x 65 536 worlds, actions iid uniform over {0..4}
 (generated on the device beforehand, resident in HBM), episodes of 500 steps with auto-reset.
-Timing: every timed step is bracketed by its own pair of CUDA events on the launching stream; between timed steps the
-L2 is flushed by writing a 512 MiB buffer (the per-step working set, ~83 MB, is smaller than the 126 MB L2).  `value`
-= worlds * steps / sum(step times), max over ranks.  `e2e` goes through the host-buffer C-ABI call (rw_step_host):
+Timing (default `--l2 rotate`): the launches rotate over 16 independent sets of worlds (16 x 83 MB of state and
+observation buffers = 1.3 GB >> the 126 MB L2, so every launch finds its inputs in HBM and its 74 MB of observations
+evict the previous set's), K launches back to back inside ONE pair of CUDA events on the launching stream.
+`--l2 flush` instead brackets every launch with its own event pair and writes 512 MiB between launches.  `value`
+= worlds * steps / time, max over ranks.  `e2e` goes through the host-buffer C-ABI call (rw_step_host):
 pinned host actions -> device, kernel, observations/rewards/done -> pinned host, inside the timed region.
 """
 import argparse
@@ -143,7 +145,10 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", action="store_true", help="all-gather obs/reward/done across ranks every step (NCCL)")
-    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps (diagnostic)")
+    ap.add_argument("--l2", default="rotate", choices=["rotate", "flush", "none"],
+                    help="cold-L2 protocol: rotate over 16 world sets (default), flush 512 MiB between launches, or none")
+    ap.add_argument("--flush-with", default="library", choices=["library", "torch"],
+                    help="L2 flush kernel: the library's (same shared-memory carve-out as the step kernel) or torch fill_")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -165,10 +170,13 @@ def main():
 
     env_id, overrides, E = WORKLOADS[args.workload]
     E = args.envs or E
-    vec = rware_b200.make_vec(env_id, E, auto_reset=True, device=dev, **overrides)
+    NSETS = 16 if args.l2 == "rotate" else 1
+    sets = [rware_b200.make_vec(env_id, E, auto_reset=True, device=dev, **overrides) for _ in range(NSETS)]
+    vec = sets[0]
     n, L, A = vec.n_agents, vec.obs_len, 1 + vec.msg_bits
     info = vec.info
-    vec.reset(seed=rank * E)  # world e of rank r is seeded with r*E + e: results do not depend on the sharding
+    for k, v in enumerate(sets):  # world e of set k on rank r is seeded with (k*world + r)*E + e
+        v.reset(seed=(k * world + rank) * E)
 
     # synthetic input: a ring of pre-generated uniform action tensors, resident in HBM
     RING = 16
@@ -176,6 +184,12 @@ def main():
     for i, a in enumerate(actions):
         vec.backend.random_actions(a, 12345 + rank, i)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    def do_flush(i):
+        if args.flush_with == "torch":
+            flush.fill_(i & 0xff)
+        else:
+            vec.backend.flush_l2(flush, i & 0xff)
+
     gathered = None
     if args.gather and world > 1:
         gathered = (torch.empty((world * E, n, L), dtype=torch.float32, device=dev),
@@ -183,7 +197,7 @@ def main():
                     torch.empty((world * E,), dtype=torch.uint8, device=dev))
 
     def one_step(i):
-        obs, rew, done = vec.step(actions[i % RING])
+        obs, rew, done = sets[i % NSETS].step(actions[i % RING])
         if gathered is not None:
             dist.all_gather_into_tensor(gathered[0], obs)
             dist.all_gather_into_tensor(gathered[1], rew)
@@ -202,46 +216,63 @@ def main():
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     torch.cuda.synchronize()
     t_wall0 = time.perf_counter()
-    for i in range(args.steps):
-        if not args.no_flush:
-            flush.fill_(i & 0xff)
-        starts[i].record()
-        one_step(args.warmup + i)
-        stops[i].record()
-    torch.cuda.synchronize()
+    if args.l2 == "flush":
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        for i in range(args.steps):
+            do_flush(i)
+            starts[i].record()
+            one_step(args.warmup + i)
+            stops[i].record()
+        torch.cuda.synchronize()
+        total_ms = float(sum(s.elapsed_time(e) for s, e in zip(starts, stops)))
+    else:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(args.steps):
+            one_step(args.warmup + i)
+        ev1.record()
+        torch.cuda.synchronize()
+        total_ms = float(ev0.elapsed_time(ev1))
     if dist:
         dist.barrier()
     t_wall = time.perf_counter() - t_wall0
-    step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
-    total_ms = float(sum(step_ms))
 
-    # back-to-back (warm L2, no flush) for reference, one event pair around K launches
+    # one world set stepped back to back (its 83 MB working set stays in the 126 MB L2): upper bound, for reference
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0.record()
     for i in range(args.steps):
-        one_step(i)
+        vec.step(actions[i % RING])
     s1.record()
     torch.cuda.synchronize()
     warm_ms = s0.elapsed_time(s1)
     clocks = sampler.stop() if rank == 0 else None
 
     # the observation gather alone (rw_obs: state read + obs write), same flush + per-launch event protocol
-    obs_ms = []
-    for i in range(min(args.steps, 50)):
-        if not args.no_flush:
-            flush.fill_(i & 0xff)
+    n_obs = min(args.steps, 64)
+    if args.l2 == "flush":
+        pairs = []
+        for i in range(n_obs):
+            do_flush(i)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            vec.observations()
+            b.record()
+            pairs.append((a, b))
+        torch.cuda.synchronize()
+        obs_kernel_ms = sum(a.elapsed_time(b) for a, b in pairs) / n_obs
+    else:
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(NSETS):
+            sets[i].observations()
         a.record()
-        vec.observations()
+        for i in range(n_obs):
+            sets[i % NSETS].observations()
         b.record()
-        obs_ms.append((a, b))
-    torch.cuda.synchronize()
-    obs_ms = [a.elapsed_time(b) for a, b in obs_ms]
-    obs_kernel_ms = sum(obs_ms) / len(obs_ms)
+        torch.cuda.synchronize()
+        obs_kernel_ms = a.elapsed_time(b) / n_obs
 
     # end to end through the host-buffer C-ABI entry point
     e2e_steps = args.e2e_steps
@@ -291,10 +322,15 @@ def main():
         "config": {"workload": f"{env_id} {overrides or ''}".strip() + f", {E} worlds per GPU, random-action rollout, auto-reset",
                    "worlds_per_gpu": E, "n_agents": n, "obs_len": L, "parallelism": f"dp{world} (independent worlds, no exchange"
                    + (", obs/reward/done all-gathered" if gathered is not None else "") + ")",
-                   "l2": "flushed between timed steps (512 MiB write)" if not args.no_flush else "not flushed",
-                   "timing": "per-step CUDA event pairs on the launch stream, summed; max over ranks"},
+                   "l2": {"rotate": f"inputs larger than L2: launches rotate over {NSETS} independent world sets "
+                                    f"({NSETS} x {(int(info['packed_bytes_step']) * E) >> 20} MiB touched per launch)",
+                          "flush": f"flushed between timed launches (512 MiB write, {args.flush_with} kernel)",
+                          "none": "not flushed"}[args.l2],
+                   "timing": {"rotate": "one CUDA event pair around the K back-to-back launches; max over ranks",
+                              "flush": "per-launch CUDA event pairs, summed; max over ranks",
+                              "none": "one CUDA event pair around the K back-to-back launches; max over ranks"}[args.l2]},
         "agent_steps_per_s": world * E * n * args.steps / (total_ms * 1e-3),
-        "value_warm_l2": world * E * args.steps / (warm_ms * 1e-3),
+        "value_single_set_l2_resident": world * E * args.steps / (warm_ms * 1e-3),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "kernel": "rw_main_kernel<STEP>",
                      "algorithmic_bytes_per_env_step": b_step, "layout_bytes_per_env_step": b_packed,

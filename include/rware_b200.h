@@ -131,6 +131,15 @@ int rw_reset_host(rw_handle *h, const uint64_t *seeds_host, float *obs_host);
 int rw_host_alloc(void **out, int64_t bytes); /* cudaHostAlloc */
 int rw_host_free(void *p);
 
+/* Diagnostics: when dev_ptr != NULL every warp of every CTA writes phase timestamps (globaltimer, ns) to
+ * dev_ptr[(cta*32 + warp)*8 + k] (uint64).  NULL switches it off (default). */
+int rw_debug_set_clock_buffer(rw_handle *h, void *dev_ptr);
+
+/* Benchmark helper: write `bytes` (a multiple of 16, larger than the L2) to buf_dev with a kernel that uses the same
+ * shared-memory carve-out as the step kernel, so that an L2 flush between timed launches does not also force an SM
+ * shared-memory reconfiguration on the next launch. */
+int rw_flush_l2(rw_handle *h, void *buf_dev, int64_t bytes, int value, void *stream);
+
 /* Synthetic-rollout helper for benchmarks: fills actions_dev [E][n][A] with iid uniform actions over {0..4}
  * (message bits uniform over {0,1}) from a counter-based generator keyed by (seed, step). */
 int rw_random_actions(rw_handle *h, int32_t *actions_dev, uint64_t seed, uint64_t step, void *stream);

@@ -86,9 +86,11 @@ def load_library():
     L.rw_host_alloc.argtypes = [ctypes.POINTER(vp), i64]
     L.rw_host_free.argtypes = [vp]
     L.rw_random_actions.argtypes = [vp, vp, u64, u64, vp]
+    L.rw_debug_set_clock_buffer.argtypes = [vp, vp]
+    L.rw_flush_l2.argtypes = [vp, vp, i64, ci, vp]
     for name in ("rw_create", "rw_destroy", "rw_get_info", "rw_seed", "rw_reset", "rw_step", "rw_obs", "rw_set_auto_reset",
                  "rw_get_state", "rw_set_state", "rw_error_count", "rw_step_host", "rw_reset_host", "rw_host_alloc",
-                 "rw_host_free", "rw_random_actions"):
+                 "rw_host_free", "rw_random_actions", "rw_debug_set_clock_buffer", "rw_flush_l2"):
         getattr(L, name).restype = ci
     _lib = L
     return L
@@ -199,6 +201,12 @@ class CudaBackend:
         out = ctypes.c_int64()
         self._check(self.lib.rw_error_count(self._h, ctypes.byref(out), self._stream()))
         return out.value
+
+    def flush_l2(self, buf, value=0):
+        self._check(self.lib.rw_flush_l2(self._h, _ptr(buf), buf.numel() * buf.element_size(), int(value), self._stream()))
+
+    def set_clock_buffer(self, tensor):
+        self._check(self.lib.rw_debug_set_clock_buffer(self._h, _ptr(tensor)))
 
     def random_actions(self, actions, seed, step):
         self._check(self.lib.rw_random_actions(self._h, _ptr(actions), int(seed), int(step), self._stream()))

@@ -21,7 +21,7 @@ struct rw_handle {
     int device;
     bool ready;  // worlds hold a valid state (after rw_reset / rw_set_state)
     std::string err;
-    void *d_highway = nullptr, *d_home = nullptr, *d_home_id = nullptr, *d_normx = nullptr, *d_normy = nullptr;
+    void *d_highway = nullptr, *d_home = nullptr, *d_home_id = nullptr, *d_cta_tables = nullptr, *d_normx = nullptr, *d_normy = nullptr;
     void *d_state = nullptr, *d_rng = nullptr, *d_err = nullptr;
     // staging for the *_host entry points
     int32_t *d_actions = nullptr;
@@ -140,6 +140,14 @@ static int create_impl(rw_handle *h, const rw_config *cfg, int64_t num_envs, int
         CK(cudaMalloc(&h->d_home_id, sizeof(uint16_t) * cells));
         CK(cudaMemcpy(h->d_home_id, home_id.data(), sizeof(uint16_t) * cells, cudaMemcpyHostToDevice));
     }
+    {   // image of the CTA-shared table region: highway bytes, then (2-byte aligned) home ids
+        std::vector<uint8_t> img((size_t)p.sm_cta_bytes, 0);
+        memcpy(img.data(), cfg->highways, cells);
+        uint16_t *hid = reinterpret_cast<uint16_t *>(img.data() + ((cells + 1) & ~1));
+        for (int k = 0; k < S; k++) hid[home[k]] = (uint16_t)(k + 1);
+        CK(cudaMalloc(&h->d_cta_tables, img.size()));
+        CK(cudaMemcpy(h->d_cta_tables, img.data(), img.size(), cudaMemcpyHostToDevice));
+    }
     CK(cudaMalloc(&h->d_normx, sizeof(float) * W));
     CK(cudaMalloc(&h->d_normy, sizeof(float) * H));
     CK(cudaMemcpy(h->d_normx, nx.data(), sizeof(float) * W, cudaMemcpyHostToDevice));
@@ -154,6 +162,7 @@ static int create_impl(rw_handle *h, const rw_config *cfg, int64_t num_envs, int
     p.highway = (const uint8_t *)h->d_highway;
     p.home_cell = (const uint16_t *)h->d_home;
     p.home_id = (const uint16_t *)h->d_home_id;
+    p.cta_tables = (const uint8_t *)h->d_cta_tables;
     p.normx = (const float *)h->d_normx;
     p.normy = (const float *)h->d_normy;
     p.state = (int32_t *)h->d_state;
@@ -180,7 +189,7 @@ extern "C" {
 int rw_destroy(rw_handle *h) {
     if (!h) return RW_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->d_highway); cudaFree(h->d_home); cudaFree(h->d_home_id); cudaFree(h->d_normx); cudaFree(h->d_normy);
+    cudaFree(h->d_highway); cudaFree(h->d_home); cudaFree(h->d_home_id); cudaFree(h->d_cta_tables); cudaFree(h->d_normx); cudaFree(h->d_normy);
     cudaFree(h->d_state); cudaFree(h->d_rng); cudaFree(h->d_err);
     cudaFree(h->d_actions); cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_done);
     if (h->host_stream) cudaStreamDestroy(h->host_stream);
@@ -191,6 +200,12 @@ int rw_destroy(rw_handle *h) {
 int rw_get_info(const rw_handle *h, rw_info *out) {
     if (!h || !out) return RW_EINVAL;
     *out = h->info;
+    return RW_OK;
+}
+
+int rw_debug_set_clock_buffer(rw_handle *h, void *dev_ptr) {  // diagnostics: [CTA][32][8] uint64 phase timestamps
+    if (!h) return RW_EINVAL;
+    h->p.dbg_clock = (unsigned long long *)dev_ptr;
     return RW_OK;
 }
 
@@ -278,6 +293,13 @@ int rw_error_count(rw_handle *h, int64_t *out, void *stream) {
     CK(cudaMemcpyAsync(&v, h->d_err, 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CK(cudaStreamSynchronize((cudaStream_t)stream));
     *out = (int64_t)v;
+    return RW_OK;
+}
+
+int rw_flush_l2(rw_handle *h, void *buf_dev, int64_t bytes, int value, void *stream) {
+    if (!h || !buf_dev || bytes < 16) return RW_EINVAL;
+    CK(cudaSetDevice(h->device));
+    CK(rw_launch_flush_l2(buf_dev, (size_t)bytes, value, h->p.sm_cta_bytes + h->p.sm_warp_bytes * h->p.warps_per_cta, (cudaStream_t)stream));
     return RW_OK;
 }
 

@@ -61,16 +61,20 @@ struct RwParams {
     const uint8_t *highway;     // [cells]
     const uint16_t *home_cell;  // [S]
     const uint16_t *home_id;    // [cells]: inverse of home_cell (0 = highway)
+    const uint8_t *cta_tables;  // device only: image of the CTA-shared table region (highway bytes, then home_id), sm_cta_bytes long
     const float *normx, *normy; // [W], [H]: float32(x / (W-1)), float32(y / (H-1))
     // world state
     int32_t *state;  // [tiles][nw][32]
     uint32_t *rng;   // [RW_RNG_WORDS][E_pad]
     unsigned long long *err_count;
+    unsigned long long *dbg_clock;  // optional [CTA][warp][8] phase timestamps (globaltimer ns), NULL = off
     int64_t E, E_pad;
     int32_t tiles;
     // per-warp shared memory carve-up (byte offsets from the warp's base)
-    int32_t sm_tile, sm_grid, sm_scratch, sm_obs, sm_bar, sm_warp_bytes;
+    int32_t sm_tile, sm_grid, sm_scratch, sm_obs, sm_bar, sm_tie, sm_warp_bytes;
+    int32_t sm_cta_tx;     // bytes of the table image moved by the TMA (multiple of 16, < sm_cta_bytes - 8: the CTA mbarrier sits at the end)
     int32_t sm_cta_bytes;  // CTA-shared prologue region: highway[cells] u8 then home_id[cells] u16 (device only)
+    int32_t coop, gshift;  // cooperative step: a group of 1 << gshift lanes per world (rw_coop.cuh); 0 = one lane per world
     int32_t obs_parts;     // lanes per agent row in the observation gather (1 or 2)
     int32_t obs_tma;       // 1: observation chunks leave through cp.async.bulk, 0: 16-byte st.global from all lanes
     int32_t grid_env_stride;  // bytes per world of the occupancy grid: one byte per cell (see RW_G_*)
@@ -105,7 +109,10 @@ RW_HD uint32_t rw_apack(int x, int y, int dir, int deliv, int carry) {
 struct RwLane {
     int32_t *tile;   // word w at tile[w * RW_TILE]
     uint8_t *g;      // occupancy grid of this world, one byte per cell (RW_G_*)
-    uint32_t *sc;    // scratch, entry k at sc[k * RW_TILE]; 2*n entries
+    uint32_t *sc;    // resolver scratch.  One-lane-per-world step: [2n][32] words interleaved over the tile's lanes
+                     // (sc_step = 32: start|target of agent i at sc[i*64], meta at sc[i*64+32]).  Cooperative step: a
+                     // private n-word buffer per group (sc_step = 1: start|target of agent i at sc[i], no meta words).
+    int sc_step;
     const uint8_t *highway;   // [cells] 1 = highway (CTA-shared copy in shared memory on the device)
     const uint16_t *home_id;  // [cells] id of the shelf whose home is this cell, 0 for highways (CTA-shared copy)
 };
@@ -115,6 +122,7 @@ struct RwLane {
 struct RwDynamic {
     static constexpr bool is_static = false;
     static constexpr bool full_static = false;
+    static constexpr int static_n = 0;
     RW_HD static int n(const RwParams &p) { return p.n; }
     RW_HD static int R(const RwParams &p) { return p.R; }
     RW_HD static int H(const RwParams &p) { return p.H; }
@@ -129,6 +137,7 @@ template <int H_, int W_, int S_, int R_, int MB_, int N_ = 0, int RQ_ = -1>
 struct RwStatic {
     static constexpr bool is_static = true;
     static constexpr bool full_static = (N_ > 0 && RQ_ >= 0);
+    static constexpr int static_n = N_;
     RW_HD static int n(const RwParams &p) { return N_ > 0 ? N_ : p.n; }
     RW_HD static int R(const RwParams &p) { return RQ_ >= 0 ? RQ_ : p.R; }
     RW_HD static int H(const RwParams &) { return H_; }

@@ -135,8 +135,17 @@ static inline void rw_fill_params(RwParams &p, const rw_config &c, int64_t num_e
         off += obs_bytes > scratch_bytes ? obs_bytes : scratch_bytes;
     }
     p.sm_bar = off; off += 8;
+    off = rw_round_up(off, 128);
+    p.sm_tie = off; off += 2 * 32 * 4;  // 32 words per warp of the pair (rw_coop.cuh)
     p.sm_warp_bytes = rw_round_up(off, 128);
-    p.sm_cta_bytes = rw_round_up(3 * cells + 2, 128);
+    p.sm_cta_tx = rw_round_up(((cells + 1) & ~1) + 2 * cells, 16);
+    p.sm_cta_bytes = rw_round_up(p.sm_cta_tx + 8, 128);
+    p.gshift = 0;
+    while ((1 << p.gshift) < n) p.gshift++;
+    {
+        const char *ev = getenv("RWARE_B200_COOP");
+        p.coop = ev ? atoi(ev) : 0;  // measured (profiles/phase_timeline.py): one lane per world is ~2.5 us faster per launch
+    }
     {
         const char *ev = getenv("RWARE_B200_OBS_TMA");
         p.obs_tma = ev ? atoi(ev) : 1;  // measured: TMA bulk stores beat st.global.v4 copy-out (30 vs 38 us under ncu)

@@ -13,8 +13,11 @@
 //        worlds is contiguous in the caller's [E][n][L] tensor).
 //   Rewards/done are tiny and written directly (coalesced).  HBM-bound integer work: no tensor cores.
 // MODE: 0 = step, 1 = observation gather only (state read + obs write), 2 = reset (+ obs).
+#include <cstdlib>
+
 #include "rw_launch.h"
 #include "rw_logic.cuh"
+#include "rw_coop.cuh"
 #include "../../include/rware_b200.h"
 
 // ---------------------------------------------------------------- PTX helpers (TMA bulk copies + mbarrier)
@@ -57,6 +60,16 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
 // ---------------------------------------------------------------- the fused kernel
+__device__ __forceinline__ unsigned long long rw_gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define RW_STAMP(k)                                                                                     \
+    do {                                                                                                \
+        if (p.dbg_clock && lane == 0) p.dbg_clock[((size_t)blockIdx.x * 32 + warp) * 8 + (k)] = rw_gtime(); \
+    } while (0)
+
 __device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
 // Two warps serve one tile.  The PRIMARY warp (even) runs the per-world logic, one lane per world.  The HELPER warp
@@ -86,12 +99,31 @@ __global__ void __launch_bounds__(960, 1) rw_main_kernel(const __grid_constant__
     l.tile = tilew + lane;
     l.g = grid + lane * p.grid_env_stride;
     l.sc = reinterpret_cast<uint32_t *>(wb + p.sm_scratch) + lane;
+    l.sc_step = RW_TILE;
     l.highway = s_highway;
     l.home_id = s_home_id;
 
-    // ---- 1. prologue.  primary: state tile HBM -> shared memory through the TMA, then this world's actions (global
-    //         loads issued back to back while the tile is in flight).  helper: zero the occupancy grids.
-    //         everybody: CTA-shared static tables.
+    // Programmatic dependent launch: this grid may have been scheduled while the previous grid on the stream was still
+    // draining; nothing it wrote may be read before this point.  Dependents of this grid may start launching right away
+    // (they wait at the same instruction).  Both are no-ops for an ordinary launch.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    RW_STAMP(0);
+    // ---- 1. prologue.  Thread 0: the CTA-shared static tables (highway bytes + home ids) arrive through one TMA bulk
+    //         copy on a CTA-level mbarrier.  Primary lane 0: this tile's packed state through another TMA bulk copy on
+    //         the tile's mbarrier.  While they are in flight: helper zeroes the occupancy grids, primary issues its
+    //         action loads.
+    // the fully static specialisations carry only the one-lane-per-world step (select_kernel routes p.coop elsewhere)
+    const bool coop = !C::full_static && (MODE == RW_MODE_STEP) && p.coop;
+    uint64_t *cta_bar = reinterpret_cast<uint64_t *>(smem + p.sm_cta_bytes - 8);
+    if (threadIdx.x == 0) {
+        mbar_init(cta_bar, 1);
+        fence_mbar_init();
+        mbar_expect_tx(cta_bar, (uint32_t)p.sm_cta_tx);
+        bulk_g2s(smem, p.cta_tables, (uint32_t)p.sm_cta_tx, cta_bar);
+    }
+    RwActRegs<C> areg;
+    const bool pre = rw_can_prefetch_actions<C>(p);
     if (role == 0) {
         if (active && lane == 0) {
             mbar_init(bar, 1);
@@ -99,22 +131,116 @@ __global__ void __launch_bounds__(960, 1) rw_main_kernel(const __grid_constant__
             mbar_expect_tx(bar, tile_bytes);
             bulk_g2s(tilew, gtile, tile_bytes, bar);
         }
-        if (MODE == RW_MODE_STEP && valid) rw_load_actions<C>(p, l, actions + env * p.n * p.A);
+        if (MODE == RW_MODE_STEP && !coop && valid) {
+            if (pre) rw_prefetch_actions<C>(p, actions + env * p.n * p.A, areg);  // loads in flight, consumed below
+            else rw_load_actions<C>(p, l, actions + env * p.n * p.A);
+        }
     } else if (active) {
         int4 *g4 = reinterpret_cast<int4 *>(grid);
         const int n16 = (p.grid_env_stride * RW_TILE) >> 4;
         for (int i = lane; i < n16; i += 32) g4[i] = make_int4(0, 0, 0, 0);
     }
-    for (int i = threadIdx.x; i < p.cells; i += blockDim.x) {
-        s_highway[i] = p.highway[i];
-        s_home_id[i] = p.home_id[i];
-    }
-    __syncthreads();
+    __syncthreads();  // mbarrier inits and the zeroed grids are visible CTA-wide
     if (!active) return;
+    mbar_wait(cta_bar, 0);  // static tables landed
+    if (role == 0 && MODE == RW_MODE_STEP && !coop && valid && pre) rw_commit_actions<C>(p, l, areg);
+    RW_STAMP(1);
 
-    // ---- 2. primary: lane e advances world e; 3. updated tile shared memory -> HBM
-    if (role == 0) {
+    // Observation staging of this warp: chunk of CH worlds starting at world c0 of the tile -> its slice of the caller's
+    // [E][n][L] tensor.  One lane per (world, agent, half row); the chunk leaves as one TMA bulk store.
+    const int CH = p.obs_chunk_envs;
+    const int64_t tile_env0 = (int64_t)tile * RW_TILE;
+    const bool fast = (tile_env0 + RW_TILE <= p.E) && p.obs_bulk && (RW_TILE % CH == 0);
+    float *buf = reinterpret_cast<float *>(wb + p.sm_obs + role * p.obs_buf_stride);
+    bool buf_busy = false;
+    auto emit_chunk = [&](int c0) {
+        const int n = p.n, L = p.L, P = p.obs_parts;
+        const int items = CH * n * P;
+        if (buf_busy) {  // this warp's previous bulk store must have drained the buffer
+            if (lane == 0) bulk_wait_read<0>();
+            __syncwarp();
+        }
+        for (int it = lane; it < items; it += 32) {
+            const int part = P == 2 ? (it & 1) : 0;
+            const int ea = P == 2 ? (it >> 1) : it;  // (world, agent) row inside the chunk
+            const int el = (int)rw_div((uint32_t)ea, p.divN);
+            const int e = c0 + el;
+            if (e < RW_TILE && tile_env0 + e < p.E) {
+                RwLane le;
+                le.tile = tilew + e;
+                le.g = grid + e * p.grid_env_stride;
+                le.sc = nullptr;
+                le.sc_step = 0;
+                le.highway = s_highway;
+                le.home_id = s_home_id;
+                if (P == 2) rw_obs_agent<C, 2>(p, le, ea - el * n, buf + ea * L, part);
+                else rw_obs_agent<C, 1>(p, le, ea - el * n, buf + ea * L, 0);
+            }
+        }
+        float *gdst = obs + (tile_env0 + c0) * n * L;
+        if (fast && p.obs_tma) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                bulk_s2g(gdst, buf, (uint32_t)p.obs_chunk_bytes);
+                bulk_commit();
+            }
+            buf_busy = true;
+        } else if (fast) {  // 16-byte coalesced stores: 512 B per warp instruction
+            __syncwarp();
+            const int4 *src = reinterpret_cast<const int4 *>(buf);
+            int4 *dst = reinterpret_cast<int4 *>(gdst);
+            const int n16 = p.obs_chunk_bytes >> 4;
+#pragma unroll 4
+            for (int i = lane; i < n16; i += 32) __stcs(dst + i, src[i]);
+            __syncwarp();
+        } else {  // ragged tail / unaligned geometry: plain coalesced stores
+            __syncwarp();
+            int64_t envs_here = p.E - (tile_env0 + c0);
+            if (envs_here > CH) envs_here = CH;
+            if (envs_here > RW_TILE - c0) envs_here = RW_TILE - c0;
+            const int nf = (int)(envs_here > 0 ? envs_here : 0) * n * L;
+            for (int i = lane; i < nf; i += 32) gdst[i] = buf[i];
+            __syncwarp();
+        }
+    };
+
+    // ---- 2. the step
+    const int passes = 1 << p.gshift;
+    const bool interleave = coop && p.coop == 2 && passes >= 2 && CH <= RW_TILE / 2;  // measured slower: opt-in (RWARE_B200_COOP=2)
+    if (coop) {
+        // a group of 2^gshift lanes per world (rw_coop.cuh).  Each warp of the pair owns half of the tile's worlds and
+        // emits the observations of a chunk as soon as its worlds are stepped, so that the TMA stores of one pass drain
+        // while the next pass computes.
         mbar_wait(bar, 0);
+        RW_STAMP(2);
+        RwCoopCtx cx;
+        cx.tilew = tilew; cx.grid = grid;
+        cx.tiebuf = reinterpret_cast<uint32_t *>(wb + p.sm_tie) + 32 * role;
+        cx.highway = s_highway; cx.home_id = s_home_id;
+        cx.tile_env0 = tile_env0;
+        cx.actions = actions + tile_env0 * p.n * p.A;
+        cx.reward = reward + tile_env0 * p.n;
+        cx.done = done + tile_env0;
+        if (interleave) {
+            const int half = passes >> 1, epp = RW_TILE >> p.gshift;
+            int ready = role * (RW_TILE / 2), emitted = ready;
+            for (int pass = role * half; pass < (role + 1) * half; pass++) {
+                rw_step_coop_pass<C>(p, cx, pass, p.gshift);
+                ready += epp;
+                if (obs != nullptr)
+                    for (; ready - emitted >= CH; emitted += CH) emit_chunk(emitted);
+            }
+        } else {
+            for (int pass = role; pass < passes; pass += 2) rw_step_coop_pass<C>(p, cx, pass, p.gshift);
+        }
+        RW_STAMP(3);
+        pair_barrier(1 + tl);  // every world of the tile is in its post-step state
+        RW_STAMP(4);
+    } else if (role == 0) {
+        // primary: lane e advances world e
+        mbar_wait(bar, 0);
+        RW_STAMP(2);
         if (valid) {
             if (MODE == RW_MODE_RESET) {
                 if (mask == nullptr || mask[env]) rw_reset_lane<C>(p, l, env);
@@ -132,82 +258,29 @@ __global__ void __launch_bounds__(960, 1) rw_main_kernel(const __grid_constant__
             }
         }
         __syncwarp();
-        if (MODE != RW_MODE_OBS) {
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-                bulk_s2g(gtile, tilew, tile_bytes);
-                bulk_commit();
-            }
+        RW_STAMP(3);
+    }
+    // ---- 3. updated tile shared memory -> HBM
+    if (role == 0 && MODE != RW_MODE_OBS) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            bulk_s2g(gtile, tilew, tile_bytes);
+            bulk_commit();
         }
     }
-    if (obs == nullptr) {
-        if (role == 0 && lane == 0) bulk_wait_read<0>();
-        return;
-    }
-    pair_barrier(1 + tl);  // post-step tile + grids are visible to the helper
-
-    // ---- 4. observation gather.  Chunks of CH worlds; this warp takes every second chunk into its own buffer.
-    //         One lane per (world, agent, slice): two lanes share an agent row when p.obs_parts == 2.
-    {
-        const int CH = p.obs_chunk_envs, n = p.n, L = p.L, P = p.obs_parts;
-        const int items = CH * n * P;
-        const int64_t tile_env0 = (int64_t)tile * RW_TILE;
-        const bool fast = (tile_env0 + RW_TILE <= p.E) && p.obs_bulk && (RW_TILE % CH == 0);
-        float *buf = reinterpret_cast<float *>(wb + p.sm_obs + role * p.obs_buf_stride);
-        const uint32_t chunk_floats = (uint32_t)(p.obs_chunk_bytes >> 2);
-        float *gdst = obs + (tile_env0 + (int64_t)role * CH) * n * L;
-        bool first = true;
-        for (int c0 = role * CH; c0 < RW_TILE; c0 += 2 * CH, gdst += 2 * (size_t)chunk_floats) {
-            if (!first) {  // this warp's previous bulk store must have drained the buffer
-                if (lane == 0) bulk_wait_read<0>();
-                __syncwarp();
-            }
-            first = false;
-            for (int it = lane; it < items; it += 32) {
-                const int part = P == 2 ? (it & 1) : 0;
-                const int ea = P == 2 ? (it >> 1) : it;  // (world, agent) row inside the chunk
-                const int el = (int)rw_div((uint32_t)ea, p.divN);
-                const int e = c0 + el;
-                if (e < RW_TILE && tile_env0 + e < p.E) {
-                    RwLane le;
-                    le.tile = tilew + e;
-                    le.g = grid + e * p.grid_env_stride;
-                    le.sc = nullptr;
-                    le.highway = s_highway;
-                    le.home_id = s_home_id;
-                    if (P == 2) rw_obs_agent<C, 2>(p, le, ea - el * n, buf + ea * L, part);
-                    else rw_obs_agent<C, 1>(p, le, ea - el * n, buf + ea * L, 0);
-                }
-            }
-            if (fast && p.obs_tma) {
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) {
-                    bulk_s2g(gdst, buf, (uint32_t)p.obs_chunk_bytes);
-                    bulk_commit();
-                }
-            } else if (fast) {  // 16-byte coalesced stores: 512 B per warp instruction
-                __syncwarp();
-                const int4 *src = reinterpret_cast<const int4 *>(buf);
-                int4 *dst = reinterpret_cast<int4 *>(gdst);
-                const int n16 = p.obs_chunk_bytes >> 4;
-#pragma unroll 4
-                for (int i = lane; i < n16; i += 32) __stcs(dst + i, src[i]);
-                __syncwarp();
-            } else {  // ragged tail / unaligned geometry: plain coalesced stores
-                __syncwarp();
-                int64_t envs_here = p.E - (tile_env0 + c0);
-                if (envs_here > CH) envs_here = CH;
-                if (envs_here > RW_TILE - c0) envs_here = RW_TILE - c0;
-                const int nf = (int)(envs_here > 0 ? envs_here : 0) * n * L;
-                for (int i = lane; i < nf; i += 32) gdst[i] = buf[i];
-                __syncwarp();
-            }
+    if (obs != nullptr && !interleave) {
+        if (!coop) {
+            pair_barrier(1 + tl);  // post-step tile + grids are visible to the helper
+            RW_STAMP(4);
         }
+        // ---- 4. observation gather after the fact: this warp takes every second chunk
+        for (int c0 = role * CH; c0 < RW_TILE; c0 += 2 * CH) emit_chunk(c0);
     }
+    RW_STAMP(5);
     if (lane == 0) bulk_wait_read<0>();  // shared memory must stay valid until the TMA has read it
     __syncwarp();
+    RW_STAMP(6);
 }
 
 // ---------------------------------------------------------------- cold-path kernels (state views, seeding, synthetic actions)
@@ -215,7 +288,7 @@ __global__ void rw_get_state_kernel(const RwParams p, const rw_state_view v) {
     int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= p.E) return;
     int32_t *t = p.state + (size_t)(env >> 5) * p.nw * RW_TILE + (env & 31);
-    RwLane l{t, nullptr, nullptr, nullptr, nullptr};
+    RwLane l{t, nullptr, nullptr, 0, nullptr, nullptr};
     const RwOff o = rw_off<RwDynamic>(p);
     for (int i = 0; i < p.n; i++) {
         uint32_t aw = rw_agent(l, i);
@@ -247,7 +320,7 @@ __global__ void rw_set_state_kernel(const RwParams p, const rw_state_view v) {
     int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= p.E) return;
     int32_t *t = p.state + (size_t)(env >> 5) * p.nw * RW_TILE + (env & 31);
-    RwLane l{t, nullptr, nullptr, nullptr, nullptr};
+    RwLane l{t, nullptr, nullptr, 0, nullptr, nullptr};
     const RwOff o = rw_off<RwDynamic>(p);
     for (int i = 0; i < p.n; i++) {
         uint32_t aw = rw_agent(l, i);
@@ -300,6 +373,26 @@ __global__ void rw_random_actions_kernel(const RwParams p, int32_t *__restrict__
     for (int b = 0; b < p.msg_bits; b++) actions[idx * p.A + 1 + b] = (int32_t)((z >> b) & 1ULL);
 }
 
+// L2 flush for benchmarks: streams `bytes` of writes through the L2 with the SAME shared-memory carve-out as the step
+// kernel (a flush kernel with a different carve-out makes the next launch pay an SM reconfiguration).
+__global__ void rw_flush_l2_kernel(int4 *buf, size_t n16, int value) {
+    extern __shared__ uint8_t flush_smem[];
+    if (threadIdx.x == 0 && n16 == 0) flush_smem[0] = 0;
+    const int4 v = make_int4(value, value, value, value);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) buf[i] = v;
+}
+
+cudaError_t rw_launch_flush_l2(void *buf, size_t bytes, int value, int smem_bytes, cudaStream_t stream) {
+    static int configured = -1;
+    if (configured != smem_bytes) {
+        cudaError_t e = cudaFuncSetAttribute(rw_flush_l2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e != cudaSuccess) return e;
+        configured = smem_bytes;
+    }
+    rw_flush_l2_kernel<<<148, 512, smem_bytes, stream>>>((int4 *)buf, bytes / 16, value);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------- launch wrappers
 // Static specialisations: the four registered warehouse sizes (rware/__init__.py:7-12 with column_height 8) at
 // sensor range 1 and 2 without message bits; every other geometry runs the RwDynamic instantiation.
@@ -319,7 +412,7 @@ static rw_kernel_fn kernel_for_mode(RwMode mode) {
 static rw_kernel_fn select_kernel(RwMode mode, const RwParams &p, bool force_dynamic) {
     if (!force_dynamic && p.msg_bits == 0) {
 #define X(H_, W_, S_, R_, N_, RQ_) \
-    if (p.H == H_ && p.W == W_ && p.S == S_ && p.r == R_ && p.n == N_ && p.R == RQ_) \
+    if (!p.coop && p.H == H_ && p.W == W_ && p.S == S_ && p.r == R_ && p.n == N_ && p.R == RQ_) \
         return kernel_for_mode<RwStatic<H_, W_, S_, R_, 0, N_, RQ_>>(mode);
         RW_FULL_STATIC_CONFIGS(X)
 #undef X
@@ -350,8 +443,22 @@ cudaError_t rw_launch_main(RwMode mode, const RwParams &p, const int32_t *action
     dim3 block(64 * p.warps_per_cta);  // a warp pair per tile
     dim3 grid((p.tiles + p.warps_per_cta - 1) / p.warps_per_cta);
     size_t smem = (size_t)p.sm_cta_bytes + (size_t)p.sm_warp_bytes * p.warps_per_cta;
-    select_kernel(mode, p, g_force_dynamic)<<<grid, block, smem, stream>>>(p, actions, obs, reward, done, mask);
-    return cudaGetLastError();
+    static int pdl = -1;
+    if (pdl < 0) {
+        const char *ev = getenv("RWARE_B200_PDL");
+        pdl = ev ? atoi(ev) : 1;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, select_kernel(mode, p, g_force_dynamic), p, actions, obs, reward, done, mask);
 }
 
 static inline dim3 per_env_grid(int64_t n) { return dim3((unsigned)((n + 255) / 256)); }

@@ -16,3 +16,4 @@ cudaError_t rw_launch_seed_scatter(const RwParams &p, const uint32_t *staging /*
                                    cudaStream_t stream);
 cudaError_t rw_launch_random_actions(const RwParams &p, int32_t *actions, uint64_t seed, uint64_t step,
                                      cudaStream_t stream);
+cudaError_t rw_launch_flush_l2(void *buf, size_t bytes, int value, int smem_bytes, cudaStream_t stream);

@@ -130,11 +130,23 @@ template <class C>
 RW_HD void rw_build_grid(const RwParams &p, const RwLane &l) {
     const RwOff o = rw_off<C>(p);
     const int S = C::S(p);
-#pragma unroll 4
-    for (int k2 = 0; k2 < (S >> 1); k2++) {  // two shelves per state word
-        uint32_t w = (uint32_t)l.tile[(o.w_shelf + k2) * RW_TILE];
-        l.g[w & 0xffffu] = (uint8_t)RW_G_SHELF;
-        l.g[w >> 16] = (uint8_t)RW_G_SHELF;
+    {   // two shelves per state word; batches of 8 words: all loads first, then the scattered byte stores
+        int k2 = 0;
+        for (; k2 + 8 <= (S >> 1); k2 += 8) {
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) w[j] = (uint32_t)l.tile[(o.w_shelf + k2 + j) * RW_TILE];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                l.g[w[j] & 0xffffu] = (uint8_t)RW_G_SHELF;
+                l.g[w[j] >> 16] = (uint8_t)RW_G_SHELF;
+            }
+        }
+        for (; k2 < (S >> 1); k2++) {
+            uint32_t w = (uint32_t)l.tile[(o.w_shelf + k2) * RW_TILE];
+            l.g[w & 0xffffu] = (uint8_t)RW_G_SHELF;
+            l.g[w >> 16] = (uint8_t)RW_G_SHELF;
+        }
     }
     if (S & 1) l.g[(uint32_t)l.tile[(o.w_shelf + (S >> 1)) * RW_TILE] & 0xffffu] = (uint8_t)RW_G_SHELF;
     const bool overlap = ((uint32_t)l.tile[o.w_inact * RW_TILE] & RW_OVERLAP_BIT) != 0;
@@ -169,8 +181,8 @@ RW_HD_NOINLINE void rw_rebuild_grid_slow(const RwParams &p, const RwLane &l) {
 }
 
 // scratch accessors: entry 2i = start | target<<16, entry 2i+1 = meta
-RW_HD uint32_t &rw_st(const RwLane &l, int i) { return l.sc[(2 * i) * RW_TILE]; }
-RW_HD uint32_t &rw_meta(const RwLane &l, int i) { return l.sc[(2 * i + 1) * RW_TILE]; }
+RW_HD uint32_t &rw_st(const RwLane &l, int i) { return l.sc[i * (l.sc_step == 1 ? 1 : 2 * RW_TILE)]; }
+RW_HD uint32_t &rw_meta(const RwLane &l, int i) { return l.sc[(2 * i + 1) * RW_TILE]; }  // one-lane-per-world step only
 // meta: act[0:3) nxt[3:9) h[9:15) sh[16:32)
 RW_HD uint32_t rw_m_act(uint32_t m) { return m & 7u; }
 RW_HD uint32_t rw_m_nxt(uint32_t m) { return (m >> 3) & 63u; }
@@ -399,17 +411,17 @@ RW_HD_NOINLINE void rw_reset_lane(const RwParams &p, const RwLane &l, int64_t en
         uint32_t j = (uint32_t)(cells - n + k);
         uint32_t val = rw_bounded(g, j);
         bool found = false;
-        for (int q = 0; q < k; q++) found |= (l.sc[q * RW_TILE] == val);
-        l.sc[k * RW_TILE] = found ? j : val;
+        for (int q = 0; q < k; q++) found |= (l.sc[q * l.sc_step] == val);
+        l.sc[k * l.sc_step] = found ? j : val;
     }
     for (int i = n - 1; i >= 1; i--) {
         uint32_t j = rw_bounded(g, (uint32_t)i);
-        uint32_t t = l.sc[i * RW_TILE];
-        l.sc[i * RW_TILE] = l.sc[j * RW_TILE];
-        l.sc[j * RW_TILE] = t;
+        uint32_t t = l.sc[i * l.sc_step];
+        l.sc[i * l.sc_step] = l.sc[j * l.sc_step];
+        l.sc[j * l.sc_step] = t;
     }
     for (int i = 0; i < n; i++) {  // ref:786-792: unravel_index -> (y, x); dirs from choice(Direction, size=n)
-        uint32_t loc = l.sc[i * RW_TILE];
+        uint32_t loc = l.sc[i * l.sc_step];
         uint32_t y = C::div_w(p, loc);
         uint32_t dir = rw_bounded(g, 3);
         rw_set_agent(l, i, rw_apack((int)(loc - y * (uint32_t)W), (int)y, (int)dir, 0, 0));
@@ -439,6 +451,37 @@ RW_HD_NOINLINE void rw_reset_lane(const RwParams &p, const RwLane &l, int64_t en
 // act: this world's actions [n][A]; reward: this world's [n] floats.  Returns done.
 // Precondition: grid built from the current state.  Postcondition: tile words and grid hold the
 // post-step state (post-move agents/shelves, post-resample request bits).
+// Deliveries, rewards, request-queue resample, counters and termination of one world (ref:903-941), run after the
+// moves have been applied to the tile words and the grid.  Rewards accumulate in half units: 4 bits per agent in
+// rew_lo (agents 0-15) / rew_hi (16-31), plus rew_global whole units for every agent.  Returns done.
+template <class C>
+RW_HD bool rw_finish_lane(const RwParams &p, const RwLane &l, int64_t env, uint64_t &rew_lo, uint64_t &rew_hi, int &rew_global) {
+    const RwOff o = rw_off<C>(p);
+    bool delivered = false;
+    for (int gi = 0; gi < p.n_goals; gi++) {
+        uint32_t c = (uint32_t)p.goal_cell[gi];
+        uint32_t gb = l.g[c];
+        if ((gb & (RW_G_SHELF | RW_G_REQ)) != (RW_G_SHELF | RW_G_REQ)) continue;
+        delivered = true;
+        rw_resample<C>(p, l, rw_shelf_at<C>(p, l, c), env);
+        int occ = (int)(gb & RW_G_AGENT);
+        int ai = occ ? occ - 1 : o.n - 1;  // python's rewards[-1] when nobody stands on the goal
+        if (p.reward_type == 0) rew_global++;
+        else {
+            uint64_t add = (p.reward_type == 1) ? 2ULL : 1ULL;
+            if (ai < 16) rew_lo += add << (4 * ai); else rew_hi += add << (4 * (ai - 16));
+            if (p.reward_type == 2) rw_set_agent(l, ai, rw_agent(l, ai) | (1u << 18));
+        }
+    }
+    // counters / termination (ref:929-941)
+    uint32_t wi = (uint32_t)l.tile[o.w_inact * RW_TILE];
+    int inact = delivered ? 0 : (int)(wi & ~RW_OVERLAP_BIT) + 1;
+    int steps = l.tile[o.w_steps * RW_TILE] + 1;
+    l.tile[o.w_inact * RW_TILE] = (int32_t)((uint32_t)inact | (wi & RW_OVERLAP_BIT));
+    l.tile[o.w_steps * RW_TILE] = steps;
+    return (p.max_inact && inact >= p.max_inact) || (p.max_steps && steps >= p.max_steps);
+}
+
 // Action decode (ref:809-814), hoisted out of the step so that the global loads are issued back to back while
 // the state tile is still in flight: scratch entry 2i+1 <- action | message bits << 8.  Invalid values become NOOP.
 template <class C>
@@ -462,41 +505,49 @@ RW_HD void rw_load_actions(const RwParams &p, const RwLane &l, const int32_t *ac
     }
 }
 
+// Register prefetch of the actions for fully static configurations without message bits: the loads are issued at the
+// very top of the kernel and only consumed (rw_commit_actions) after the shared-memory barriers, so their DRAM latency
+// overlaps the TMA transfers instead of serialising in front of them.
 template <class C>
-RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, float *reward, int64_t env) {
-    const RwOff o = rw_off<C>(p);
-    const int n = o.n, W = C::W(p), H = C::H(p), mb = C::mb(p);
-    uint32_t commit = 0, dag = 0;
-    // ---- proposals (ref:825-846); actions were decoded into the scratch by rw_load_actions
-    for (int i = 0; i < n; i++) {
-        uint32_t aw = rw_agent(l, i);
-        uint32_t pre = rw_meta(l, i);
-        int a = (int)(pre & 7u);
-        if (mb) l.tile[(o.w_msg + i) * RW_TILE] = (int32_t)(pre >> 8);
-        int x = rw_ax(aw), y = rw_ay(aw), tx = x, ty = y;
-        if (a == RW_ACT_FORWARD) {  // Agent.req_location ref:102-116, clamped at the walls
-            int d = rw_adir(aw);
-            if (d == 0) ty = y > 0 ? y - 1 : 0;
-            else if (d == 1) ty = y < H - 1 ? y + 1 : H - 1;
-            else if (d == 2) tx = x > 0 ? x - 1 : 0;
-            else tx = x < W - 1 ? x + 1 : W - 1;
+struct RwActRegs {
+    static constexpr int N = C::full_static ? 8 : 1;
+    int32_t v[N];
+};
+template <class C>
+RW_HD bool rw_can_prefetch_actions(const RwParams &p) { return C::full_static && C::mb(p) == 0 && C::n(p) <= 8; }
+template <class C>
+RW_HD void rw_prefetch_actions(const RwParams &p, const int32_t *act, RwActRegs<C> &r) {
+#pragma unroll
+    for (int i = 0; i < RwActRegs<C>::N; i++)
+        if (i < C::n(p)) r.v[i] = act[i];
+}
+template <class C>
+RW_HD void rw_commit_actions(const RwParams &p, const RwLane &l, const RwActRegs<C> &r) {
+    uint32_t bad = 0;
+#pragma unroll
+    for (int i = 0; i < RwActRegs<C>::N; i++)
+        if (i < C::n(p)) {
+            int a = r.v[i];
+            if ((unsigned)a > 4u) { a = RW_ACT_NOOP; bad++; }
+            rw_meta(l, i) = (uint32_t)a;
         }
-        uint32_t s = (uint32_t)(y * W + x), t = (uint32_t)(ty * W + tx);
-        uint32_t nxt;
-        if (t == s) { nxt = RW_NXT_SELF; commit |= 1u << i; }
-        else {
-            uint32_t gt = l.g[t];
-            uint32_t o = gt & RW_G_AGENT;
-            // ref:829-844 a carrier may not enter a cell holding a shelf unless an agent there carries it
-            if (rw_acarry(aw) && (gt & RW_G_SHELF) && !(o && rw_acarry(rw_agent(l, (int)o - 1)))) {
-                a = RW_ACT_NOOP; t = s; nxt = RW_NXT_SELF; commit |= 1u << i;
-            } else {
-                nxt = o ? o - 1 : RW_NXT_SINK;
-            }
-        }
-        rw_st(l, i) = s | (t << 16);
-        rw_meta(l, i) = (uint32_t)a | (nxt << 3);
+    if (bad) {
+#if defined(__CUDA_ARCH__)
+        atomicAdd(p.err_count, (unsigned long long)bad);
+#else
+        *p.err_count += bad;
+#endif
     }
+}
+
+// Collision resolution for one world (ref:848-876 restated agent-centrically).  Input: the scratch
+// holds start|target and action|successor of every agent, `commit` the agents that stay put.  Returns the final
+// commit mask (bit i: agent i's proposed move, if any, is carried out).
+template <class C>
+RW_HD uint32_t rw_resolve_lane(const RwParams &p, const RwLane &l, uint32_t commit) {
+    const RwOff o = rw_off<C>(p);
+    const int n = o.n;
+    uint32_t dag = 0;
     // ---- resolve (ref:848-876 restated agent-centrically)
     uint32_t movers = ~commit & (n == 32 ? 0xffffffffu : ((1u << n) - 1u));
     if (movers) {
@@ -558,11 +609,141 @@ RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, float *reward, int64
             }
         }
     }
-    // ---- apply (ref:878-899).  Failed agents become NOOP (ref:871-876).
+    return commit;
+}
+
+template <class C>
+RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, float *reward, int64_t env) {
+    const RwOff o = rw_off<C>(p);
+    const int n = o.n, W = C::W(p), H = C::H(p), mb = C::mb(p);
+    uint32_t commit = 0;
     const bool overlap = ((uint32_t)l.tile[o.w_inact * RW_TILE] & RW_OVERLAP_BIT) != 0;
     uint64_t rew_lo = 0, rew_hi = 0;  // per-agent reward in half units, 4 bits each
     int rew_global = 0;
     uint32_t moved = 0;
+    if constexpr (C::full_static && C::static_n >= 1 && C::static_n <= 8) {
+        // ---- fully static agent count: everything per agent lives in registers and every phase is written as explicit
+        // batches (all loads, then arithmetic, then the dependent loads, stores last) so that the shared-memory
+        // latencies of the agents overlap instead of adding up.  Same semantics as the generic branch below.
+        // proposals (ref:825-846); actions were decoded into the scratch beforehand
+        constexpr int N = C::static_n;
+        uint32_t awv[N], av[N], sv[N], tv[N], gtv[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            awv[i] = rw_agent(l, i);
+            av[i] = rw_meta(l, i);
+        }
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            if (mb) l.tile[(o.w_msg + i) * RW_TILE] = (int32_t)(av[i] >> 8);
+            av[i] &= 7u;
+            int x = rw_ax(awv[i]), y = rw_ay(awv[i]), tx = x, ty = y;
+            if (av[i] == RW_ACT_FORWARD) {  // Agent.req_location ref:102-116, clamped at the walls
+                int d = rw_adir(awv[i]);
+                if (d == 0) ty = y > 0 ? y - 1 : 0;
+                else if (d == 1) ty = y < H - 1 ? y + 1 : H - 1;
+                else if (d == 2) tx = x > 0 ? x - 1 : 0;
+                else tx = x < W - 1 ? x + 1 : W - 1;
+            }
+            sv[i] = (uint32_t)(y * W + x);
+            tv[i] = (uint32_t)(ty * W + tx);
+        }
+#pragma unroll
+        for (int i = 0; i < N; i++) gtv[i] = l.g[tv[i]];
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            uint32_t nxt;
+            if (tv[i] == sv[i]) { nxt = RW_NXT_SELF; commit |= 1u << i; }
+            else {
+                uint32_t occ = gtv[i] & RW_G_AGENT;
+                // ref:829-844 a carrier may not enter a cell holding a shelf unless an agent there carries it
+                if (rw_acarry(awv[i]) && (gtv[i] & RW_G_SHELF) && !(occ && rw_acarry(rw_agent(l, (int)occ - 1)))) {
+                    av[i] = RW_ACT_NOOP; tv[i] = sv[i]; nxt = RW_NXT_SELF; commit |= 1u << i;
+                } else {
+                    nxt = occ ? occ - 1 : RW_NXT_SINK;
+                }
+            }
+            rw_st(l, i) = sv[i] | (tv[i] << 16);
+            rw_meta(l, i) = av[i] | (nxt << 3);
+        }
+        commit = rw_resolve_lane<C>(p, l, commit);
+        // apply (ref:878-899); failed agents become NOOP (ref:871-876)
+        uint32_t gsv[N], lift[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) gsv[i] = l.g[sv[i]];
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            lift[i] = 0;
+            const uint32_t a = av[i];
+            if (a == RW_ACT_FORWARD) {
+                if (((commit >> i) & 1u) && tv[i] != sv[i]) {
+                    moved |= 1u << i;
+                    if (rw_acarry(awv[i])) { lift[i] = gsv[i] & (RW_G_SHELF | RW_G_REQ); l.g[sv[i]] = 0; }
+                    else l.g[sv[i]] = (uint8_t)(gsv[i] & (RW_G_SHELF | RW_G_REQ));
+                }
+            } else if (a == RW_ACT_LEFT || a == RW_ACT_RIGHT) {  // Agent.req_direction ref:118-125
+                uint32_t d = (uint32_t)rw_adir(awv[i]);
+                uint32_t nd = ((a == RW_ACT_RIGHT ? 0x4Bu : 0x1Eu) >> (2 * d)) & 3u;
+                awv[i] = (awv[i] & ~(3u << 16)) | (nd << 16);
+                rw_set_agent(l, i, awv[i]);
+            } else if (a == RW_ACT_TOGGLE) {  // ref:889-899
+                if (!rw_acarry(awv[i])) {
+                    if (gsv[i] & RW_G_SHELF) rw_set_agent(l, i, awv[i] | ((uint32_t)rw_shelf_at<C>(p, l, sv[i]) << 19));
+                } else if (!l.highway[sv[i]]) {
+                    if (rw_adeliv(awv[i]) && p.reward_type == 2) rew_lo += 1ULL << (4 * i);
+                    rw_set_agent(l, i, awv[i] & 0x3ffffu & ~(1u << 18));
+                }
+            }
+        }
+        if (moved) {
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                if (!((moved >> i) & 1u)) continue;
+                const uint32_t t = tv[i];
+                uint32_t ty = C::div_w(p, t), tx = t - ty * (uint32_t)W;
+                rw_set_agent(l, i, (awv[i] & ~0xffffu) | tx | (ty << 8));
+                int carry = rw_acarry(awv[i]);
+                if (carry) {
+                    l.g[t] = (uint8_t)((uint32_t)(i + 1) | lift[i]);
+                    rw_set_shelf_cell(o, l, carry - 1, (int)t);
+                } else {
+                    l.g[t] = (uint8_t)((l.g[t] & (RW_G_SHELF | RW_G_REQ)) | (uint32_t)(i + 1));
+                }
+            }
+        }
+    } else {
+    // ---- proposals (ref:825-846); actions were decoded into the scratch by rw_load_actions
+    for (int i = 0; i < n; i++) {
+        uint32_t aw = rw_agent(l, i);
+        uint32_t pre = rw_meta(l, i);
+        int a = (int)(pre & 7u);
+        if (mb) l.tile[(o.w_msg + i) * RW_TILE] = (int32_t)(pre >> 8);
+        int x = rw_ax(aw), y = rw_ay(aw), tx = x, ty = y;
+        if (a == RW_ACT_FORWARD) {  // Agent.req_location ref:102-116, clamped at the walls
+            int d = rw_adir(aw);
+            if (d == 0) ty = y > 0 ? y - 1 : 0;
+            else if (d == 1) ty = y < H - 1 ? y + 1 : H - 1;
+            else if (d == 2) tx = x > 0 ? x - 1 : 0;
+            else tx = x < W - 1 ? x + 1 : W - 1;
+        }
+        uint32_t s = (uint32_t)(y * W + x), t = (uint32_t)(ty * W + tx);
+        uint32_t nxt;
+        if (t == s) { nxt = RW_NXT_SELF; commit |= 1u << i; }
+        else {
+            uint32_t gt = l.g[t];
+            uint32_t o = gt & RW_G_AGENT;
+            // ref:829-844 a carrier may not enter a cell holding a shelf unless an agent there carries it
+            if (rw_acarry(aw) && (gt & RW_G_SHELF) && !(o && rw_acarry(rw_agent(l, (int)o - 1)))) {
+                a = RW_ACT_NOOP; t = s; nxt = RW_NXT_SELF; commit |= 1u << i;
+            } else {
+                nxt = o ? o - 1 : RW_NXT_SINK;
+            }
+        }
+        rw_st(l, i) = s | (t << 16);
+        rw_meta(l, i) = (uint32_t)a | (nxt << 3);
+    }
+    commit = rw_resolve_lane<C>(p, l, commit);
+    // ---- apply (ref:878-899).  Failed agents become NOOP (ref:871-876).
     for (int i = 0; i < n; i++) {
         uint32_t m = rw_meta(l, i);
         uint32_t a = rw_m_act(m);
@@ -609,35 +790,14 @@ RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, float *reward, int64
             l.g[t] = (uint8_t)((l.g[t] & (RW_G_SHELF | RW_G_REQ)) | (uint32_t)(i + 1));
         }
     }
-    if (overlap && moved) rw_rebuild_grid_slow<C>(p, l);  // degenerate injected state: redo ref:901 literally
-    // ---- deliveries (ref:903-927)
-    bool delivered = false;
-    for (int gi = 0; gi < p.n_goals; gi++) {
-        uint32_t c = (uint32_t)p.goal_cell[gi];
-        uint32_t gb = l.g[c];
-        if ((gb & (RW_G_SHELF | RW_G_REQ)) != (RW_G_SHELF | RW_G_REQ)) continue;
-        delivered = true;
-        rw_resample<C>(p, l, rw_shelf_at<C>(p, l, c), env);
-        int o = (int)(gb & RW_G_AGENT);
-        int ai = o ? o - 1 : n - 1;  // python's rewards[-1] when nobody stands on the goal
-        if (p.reward_type == 0) rew_global++;
-        else {
-            uint64_t add = (p.reward_type == 1) ? 2ULL : 1ULL;
-            if (ai < 16) rew_lo += add << (4 * ai); else rew_hi += add << (4 * (ai - 16));
-            if (p.reward_type == 2) rw_set_agent(l, ai, rw_agent(l, ai) | (1u << 18));
-        }
     }
+    if (overlap && moved) rw_rebuild_grid_slow<C>(p, l);  // degenerate injected state: redo ref:901 literally
+    const bool done = rw_finish_lane<C>(p, l, env, rew_lo, rew_hi, rew_global);
     for (int i = 0; i < n; i++) {
         uint32_t half = (uint32_t)(((i < 16 ? rew_lo >> (4 * i) : rew_hi >> (4 * (i - 16))) & 15ULL)) + 2u * (uint32_t)rew_global;
         reward[i] = 0.5f * (float)half;
     }
-    // ---- counters / termination (ref:929-941)
-    uint32_t wi = (uint32_t)l.tile[o.w_inact * RW_TILE];
-    int inact = delivered ? 0 : (int)(wi & ~RW_OVERLAP_BIT) + 1;
-    int steps = l.tile[o.w_steps * RW_TILE] + 1;
-    l.tile[o.w_inact * RW_TILE] = (int32_t)((uint32_t)inact | (wi & RW_OVERLAP_BIT));
-    l.tile[o.w_steps * RW_TILE] = steps;
-    return (p.max_inact && inact >= p.max_inact) || (p.max_steps && steps >= p.max_steps);
+    return done;
 }
 
 // ------------------------------------------------------------------------------------------------

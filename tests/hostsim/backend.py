@@ -37,6 +37,7 @@ def _load():
         L.sim_seed.argtypes = [vp, vp, vp]
         L.sim_run.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp]
         L.sim_force_dynamic.argtypes = [ctypes.c_int]
+        L.sim_set_coop.argtypes = [vp, ctypes.c_int]
         L.sim_get_state.argtypes = [vp, ctypes.POINTER(RwStateView)]
         L.sim_set_state.argtypes = [vp, ctypes.POINTER(RwStateView)]
         _lib = L
@@ -58,6 +59,8 @@ class HostSimBackend:
         self.info = dict(num_envs=self.num_envs, n_agents=cfg.n_agents, n_shelves=self.lib.sim_n_shelves(self._h),
                          obs_len=self.lib.sim_obs_len(self._h))
         self._ready = False
+        if os.environ.get("RWARE_B200_COOP") is not None:
+            self.lib.sim_set_coop(self._h, int(os.environ["RWARE_B200_COOP"]))
 
     def close(self):
         if self._h:

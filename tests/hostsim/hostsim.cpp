@@ -12,6 +12,7 @@
 
 #include "../../robotic-warehouse_b200/csrc/rw_host_layout.h"
 #include "../../robotic-warehouse_b200/csrc/rw_logic.cuh"
+#include "../../robotic-warehouse_b200/csrc/rw_coop.cuh"
 
 struct Sim {
     RwParams p;
@@ -32,6 +33,7 @@ static RwLane lane_view(Sim *s, int lane) {
     l.tile = reinterpret_cast<int32_t *>(wb + p.sm_tile) + lane;
     l.g = wb + p.sm_grid + (size_t)lane * p.grid_env_stride;
     l.sc = reinterpret_cast<uint32_t *>(wb + p.sm_scratch) + lane;
+    l.sc_step = RW_TILE;
     l.highway = s->highway.data();
     l.home_id = s->home_id.data();
     return l;
@@ -71,6 +73,7 @@ void sim_destroy(Sim *s) { delete s; }
 int sim_obs_len(Sim *s) { return s->p.L; }
 int sim_n_shelves(Sim *s) { return s->p.S; }
 void sim_set_auto_reset(Sim *s, int on) { s->p.auto_reset = on; }
+void sim_set_coop(Sim *s, int on) { s->p.coop = on; }
 long long sim_error_count(Sim *s) { return (long long)s->err; }
 
 void sim_seed(Sim *s, const uint64_t *seeds, const uint8_t *mask) {
@@ -94,7 +97,17 @@ static void sim_run_t(Sim *s, int mode, const int32_t *actions, float *obs, floa
         int32_t *gtile = p.state + (size_t)tile * p.nw * RW_TILE;
         memcpy(tilew, gtile, (size_t)p.nw * RW_TILE * 4);
         memset(wb + p.sm_grid, 0, (size_t)p.grid_env_stride * RW_TILE);
-        for (int lane = 0; lane < RW_TILE; lane++) {
+        if (mode == 0 && p.coop) {  // warp-cooperative step: the host runs the passes one after the other
+            RwCoopCtx cx;
+            cx.tilew = tilew; cx.grid = wb + p.sm_grid; cx.tiebuf = reinterpret_cast<uint32_t *>(wb + p.sm_tie);
+            cx.highway = s->highway.data(); cx.home_id = s->home_id.data();
+            cx.tile_env0 = (int64_t)tile * RW_TILE;
+            cx.actions = actions + cx.tile_env0 * p.n * p.A;
+            cx.reward = reward + cx.tile_env0 * p.n;
+            cx.done = done + cx.tile_env0;
+            for (int pass = 0; pass < (1 << p.gshift); pass++) rw_step_coop_pass<C>(p, cx, pass, p.gshift);
+        }
+        for (int lane = 0; lane < RW_TILE && !(mode == 0 && p.coop); lane++) {
             int64_t env = (int64_t)tile * RW_TILE + lane;
             if (env >= p.E) continue;
             RwLane l = lane_view(s, lane);
@@ -155,7 +168,7 @@ void sim_get_state(Sim *s, const rw_state_view *v) {
     const RwParams &p = s->p;
     for (int64_t env = 0; env < p.E; env++) {
         int32_t *t = p.state + (size_t)(env >> 5) * p.nw * RW_TILE + (env & 31);
-        RwLane l{t, nullptr, nullptr, nullptr, nullptr};
+        RwLane l{t, nullptr, nullptr, 0, nullptr, nullptr};
         const RwOff o = rw_off<RwDynamic>(p);
         for (int i = 0; i < p.n; i++) {
             uint32_t aw = rw_agent(l, i);
@@ -186,7 +199,7 @@ void sim_set_state(Sim *s, const rw_state_view *v) {
     const RwParams &p = s->p;
     for (int64_t env = 0; env < p.E; env++) {
         int32_t *t = p.state + (size_t)(env >> 5) * p.nw * RW_TILE + (env & 31);
-        RwLane l{t, nullptr, nullptr, nullptr, nullptr};
+        RwLane l{t, nullptr, nullptr, 0, nullptr, nullptr};
         const RwOff o = rw_off<RwDynamic>(p);
         for (int i = 0; i < p.n; i++) {
             uint32_t aw = rw_agent(l, i);

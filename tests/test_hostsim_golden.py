@@ -34,3 +34,15 @@ def test_dynamic_instantiation_matches_too(name, backend, monkeypatch):
         else:
             monkeypatch.setenv("RWARE_B200_FORCE_DYNAMIC", "0")
             replay.VecDriver(fx, backend_factory(backend), num_envs=1)  # resets the library-wide switch
+
+
+@pytest.mark.parametrize("backend", backend_params())
+@pytest.mark.parametrize("name", ["tiny4_indiv", "tiny19_twostage", "custom_layout", "medium8_hard_twostage"])
+@pytest.mark.parametrize("coop", ["1", "2"])
+def test_warp_cooperative_step_matches_too(name, backend, coop, monkeypatch):
+    """The default step advances one world per lane (rw_step_lane); the warp-cooperative form (rw_coop.cuh: a group of
+    lanes per world, shfl/ballot/match_any resolver; "2" = with interleaved observation emission) must agree."""
+    monkeypatch.setenv("RWARE_B200_COOP", coop)
+    fx = replay.load_fixture(name)
+    drv = replay.VecDriver(fx, backend_factory(backend), num_envs=35)
+    assert replay.replay(drv, fx, max_steps=500) == 500

@@ -28,8 +28,10 @@ def _mk_oracles(vec, kw, E):
 
 
 @pytest.mark.parametrize("backend", backend_params())
+@pytest.mark.parametrize("coop", ["0", "1"], ids=["lane-per-world", "group-per-world"])
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
-def test_random_rollout_matches_oracle(case, backend):
+def test_random_rollout_matches_oracle(case, backend, coop, monkeypatch):
+    monkeypatch.setenv("RWARE_B200_COOP", coop)
     name, kw, E, steps, pf = case
     vec = rware_b200.VecWarehouse(E, auto_reset=True, _backend_factory=backend_factory(backend), **kw)
     orcs = _mk_oracles(vec, kw, E)
