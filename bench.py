@@ -59,7 +59,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -211,8 +211,13 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    for i in range(2000):  # ~70 ms of load before the timed region (every rank: the gather is a collective) so that
-        one_step(i)        # the nvidia-smi clock samples are taken under load
+    t_load = time.perf_counter()
+    i_load = 0
+    while time.perf_counter() - t_load < 0.6:  # ~0.6 s of the same load before the timed region (every rank: the gather is
+        for _ in range(500):                    # a collective) so that the nvidia-smi clock samples are taken under load
+            one_step(i_load)
+            i_load += 1
+        torch.cuda.synchronize()
     torch.cuda.synchronize()
     if dist:
         dist.barrier()

@@ -1,0 +1,91 @@
+"""End-to-end known answers of the UNMODIFIED reference (tests/golden/known_answers.json = SURVEY.md App. E): registered
+ids, `reset(seed=0)`, 500 steps of `default_rng(12345)` actions, SHA-256 over every float32 observation, float64 reward
+and done flag.  No oracle involved: the product path alone has to reproduce the reference's hashes, which covers the
+numpy-compatible reset sampler, the step, and the observation gather in one go.  Also: full-size batches (65 536 worlds)
+checked through size-independent properties and against the oracle on a sample of worlds."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import rware_b200
+from conftest import backend_factory, backend_params
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+with open(os.path.join(HERE, "golden", "known_answers.json")) as f:
+    KNOWN = json.load(f)
+
+
+@pytest.mark.parametrize("backend", backend_params())
+@pytest.mark.parametrize("key", sorted(KNOWN))
+def test_reference_sha256_through_the_product_path(key, backend):
+    rec = KNOWN[key]
+    kw = rware_b200.env_kwargs(key.split("+")[0], **rec["extra"])
+    E = 3  # three identical worlds: they must stay identical and all match the reference
+    vec = rware_b200.VecWarehouse(E, _backend_factory=backend_factory(backend), **kw)
+    vec.seed(np.zeros(E, np.uint64))
+    obs = vec.reset().cpu().numpy()
+    hs = [hashlib.sha256(obs[e].tobytes()) for e in range(E)]
+    acts = np.random.default_rng(12345).integers(0, 5, size=(500, kw["n_agents"]))
+    total = 0.0
+    for t in range(500):
+        a = torch.from_numpy(np.broadcast_to(acts[t].astype(np.int32), (E, kw["n_agents"])).copy())
+        obs, rew, done = vec.step(a)
+        obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy().astype(np.float64), done.cpu().numpy()
+        total += rew[0].sum()
+        for e in range(E):
+            hs[e].update(obs[e].tobytes() + rew[e].tobytes() + bytes([int(done[e])]))
+    assert [h.hexdigest() for h in hs] == [rec["sha256"]] * E
+    assert total == rec["reward_sum"]
+    st = vec.get_state()
+    final = [[int(st["agent_x"][0, i]), int(st["agent_y"][0, i]), int(st["agent_dir"][0, i]), int(st["agent_carry"][0, i])]
+             for i in range(kw["n_agents"])]
+    assert final == rec["final_agents"]
+
+
+@pytest.mark.gpu
+def test_full_size_batch_properties_and_sampled_oracle_parity():
+    """BASELINE.json configs[1]: rware-tiny-4ag x 65 536 worlds on one GPU."""
+    import oracle_py
+    E, T = 65536, 40
+    kw = rware_b200.env_kwargs("rware-tiny-4ag-v1")
+    vec = rware_b200.make_vec("rware-tiny-4ag-v1", E, auto_reset=True)
+    obs0 = vec.reset(seed=0).clone()
+    sample = np.r_[0:48, 32000:32016, E - 48:E]  # first tile(s), middle, last tile
+    orcs = {int(e): oracle_py.OracleEnv(vec.highways, vec.goals, 4, 0, 1, 4, None, 500, 1) for e in sample}
+    for e, o in orcs.items():
+        assert np.array_equal(o.reset(e), obs0[e].cpu().numpy())
+    g = torch.Generator(device="cuda").manual_seed(5)
+    ref = rware_b200.make_vec("rware-tiny-4ag-v1", E, auto_reset=True)  # second instance: determinism
+    ref.reset(seed=0)
+    for t in range(T):
+        a = torch.randint(0, 5, (E, 4), generator=g, device="cuda", dtype=torch.int32)
+        obs, rew, done = vec.step(a)
+        obs2, rew2, done2 = ref.step(a)
+        assert torch.equal(obs, obs2) and torch.equal(rew, rew2) and torch.equal(done, done2)
+        # structural invariants of every observation row (App. C): one-hot direction blocks, 0/1 flags
+        o = obs.view(E * 4, -1)
+        assert bool(((o[:, 3:7].sum(1) == 1) & (o[:, 2] <= 1) & (o[:, 7] <= 1)).all())
+        cells = o[:, 8:].view(E * 4, 9, 7)
+        assert bool((cells[:, :, 1:5].sum(2) == 1).all()) and bool((cells[:, 4, 0] == 1).all())
+        assert bool(((cells == 0) | (cells == 1)).all())
+        assert bool((cells[:, :, 6] <= cells[:, :, 5]).all())  # requested implies shelf
+        ah = a.cpu().numpy()
+        oh, rh, dh = obs[sample].cpu().numpy(), rew[sample].cpu().numpy(), done[sample].cpu().numpy()
+        for k, e in enumerate(sample):
+            oo, orw, od = orcs[int(e)].step(ah[e])
+            if od:
+                oo = orcs[int(e)].reset()
+            assert np.array_equal(oo, oh[k]) and np.array_equal(orw.astype(np.float32), rh[k]) and od == bool(dh[k])
+    st = vec.get_state()
+    # no two agents of a world share a cell; carried shelves sit under their carriers
+    cell = st["agent_y"] * vec.grid_size[1] + st["agent_x"]
+    assert bool((torch.sort(cell, dim=1).values.diff(dim=1) != 0).all())
+    carry = st["agent_carry"].long()
+    has = carry > 0
+    sx = torch.gather(st["shelf_x"], 1, (carry - 1).clamp(min=0))
+    sy = torch.gather(st["shelf_y"], 1, (carry - 1).clamp(min=0))
+    assert bool(((sx == st["agent_x"]) | ~has).all()) and bool(((sy == st["agent_y"]) | ~has).all())
