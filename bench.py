@@ -144,7 +144,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--ref-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather", action="store_true", help="all-gather obs/reward/done across ranks every step (NCCL)")
+    ap.add_argument("--gather", nargs="?", const="nccl", default=None, choices=["nccl", "fused"],
+                    help="all-gather obs/reward/done across ranks every step: NCCL all_gather_into_tensor, or the fused "
+                         "push (the step kernel's TMA stores write into every rank's gathered tensor over NVLink)")
     ap.add_argument("--l2", default="rotate", choices=["rotate", "flush", "none"],
                     help="cold-L2 protocol: rotate over 16 world sets (default), flush 512 MiB between launches, or none")
     ap.add_argument("--flush-with", default="library", choices=["library", "torch"],
@@ -191,12 +193,27 @@ def main():
             vec.backend.flush_l2(flush, i & 0xff)
 
     gathered = None
-    if args.gather and world > 1:
+    fused = None
+    if args.gather == "nccl" and world > 1:
         gathered = (torch.empty((world * E, n, L), dtype=torch.float32, device=dev),
                     torch.empty((world * E, n), dtype=torch.float32, device=dev),
                     torch.empty((world * E,), dtype=torch.uint8, device=dev))
+    if args.gather == "fused" and world > 1:
+        fused = []
+        for v in sets:  # every world set gets its own peer-mapped gathered buffers
+            tensors, handle = v.backend.gather_create(world, rank)
+            handles = [None] * world
+            dist.all_gather_object(handles, handle)
+            v.backend.gather_open(b"".join(handles))
+            fused.append(tensors)
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        dist.barrier()
 
     def one_step(i):
+        if fused is not None:
+            sets[i % NSETS].backend.step_gather(actions[i % RING])
+            dist.all_reduce(flag)  # the barrier: all ranks' pushes have landed
+            return
         obs, rew, done = sets[i % NSETS].step(actions[i % RING])
         if gathered is not None:
             dist.all_gather_into_tensor(gathered[0], obs)
@@ -326,7 +343,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": f"{env_id} {overrides or ''}".strip() + f", {E} worlds per GPU, random-action rollout, auto-reset",
                    "worlds_per_gpu": E, "n_agents": n, "obs_len": L, "parallelism": f"dp{world} (independent worlds, no exchange"
-                   + (", obs/reward/done all-gathered" if gathered is not None else "") + ")",
+                   + (f", obs/reward/done all-gathered ({args.gather})" if args.gather and world > 1 else "") + ")",
                    "l2": {"rotate": f"inputs larger than L2: launches rotate over {NSETS} independent world sets "
                                     f"({NSETS} x {(int(info['packed_bytes_step']) * E) >> 20} MiB touched per launch)",
                           "flush": f"flushed between timed launches (512 MiB write, {args.flush_with} kernel)",

@@ -131,6 +131,20 @@ int rw_reset_host(rw_handle *h, const uint64_t *seeds_host, float *obs_host);
 int rw_host_alloc(void **out, int64_t bytes); /* cudaHostAlloc */
 int rw_host_free(void *p);
 
+/* ---- Fused push all-gather (one process per GPU, NVLink / NVSwitch peers).  SURVEY.md section 8(e): the single optional
+ * exchange of the path is an all-gather of obs / reward / done.  Instead of a separate collective, the step kernel's TMA
+ * bulk stores write every observation chunk straight into this rank's slot of EVERY rank's gathered tensor.
+ *   rw_gather_create    allocates this rank's gathered buffers (one cudaMalloc: obs [W*E][n][L] f32, reward [W*E][n] f32,
+ *                       done [W*E] u8 for W = world_size ranks of E worlds each) and returns their device pointers plus
+ *                       a 64-byte CUDA IPC handle to hand to the other ranks (any transport: torch.distributed, MPI...)
+ *   rw_gather_open      maps the peers' buffers from their IPC handles ([W][64] bytes, own slot ignored)
+ *   rw_step_gather      rw_step whose outputs land in all gathered tensors; the caller then runs ONE barrier-like
+ *                       collective on the same stream (e.g. a 4-byte all-reduce) before reading its gathered tensors */
+int rw_gather_create(rw_handle *h, int world_size, int rank, float **obs_all, float **reward_all, uint8_t **done_all,
+                     void *ipc_handle_out /* 64 bytes */);
+int rw_gather_open(rw_handle *h, const void *ipc_handles /* [world_size][64] */);
+int rw_step_gather(rw_handle *h, const int32_t *actions_dev, void *stream);
+
 /* Diagnostics: when dev_ptr != NULL every warp of every CTA writes phase timestamps (globaltimer, ns) to
  * dev_ptr[(cta*32 + warp)*8 + k] (uint64).  NULL switches it off (default). */
 int rw_debug_set_clock_buffer(rw_handle *h, void *dev_ptr);

@@ -88,9 +88,12 @@ def load_library():
     L.rw_random_actions.argtypes = [vp, vp, u64, u64, vp]
     L.rw_debug_set_clock_buffer.argtypes = [vp, vp]
     L.rw_flush_l2.argtypes = [vp, vp, i64, ci, vp]
+    L.rw_gather_create.argtypes = [vp, ci, ci, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp), vp]
+    L.rw_gather_open.argtypes = [vp, vp]
+    L.rw_step_gather.argtypes = [vp, vp, vp]
     for name in ("rw_create", "rw_destroy", "rw_get_info", "rw_seed", "rw_reset", "rw_step", "rw_obs", "rw_set_auto_reset",
                  "rw_get_state", "rw_set_state", "rw_error_count", "rw_step_host", "rw_reset_host", "rw_host_alloc",
-                 "rw_host_free", "rw_random_actions", "rw_debug_set_clock_buffer", "rw_flush_l2"):
+                 "rw_host_free", "rw_random_actions", "rw_debug_set_clock_buffer", "rw_flush_l2", "rw_gather_create", "rw_gather_open", "rw_step_gather"):
         getattr(L, name).restype = ci
     _lib = L
     return L
@@ -201,6 +204,30 @@ class CudaBackend:
         out = ctypes.c_int64()
         self._check(self.lib.rw_error_count(self._h, ctypes.byref(out), self._stream()))
         return out.value
+
+    # ---- fused push all-gather (multi-GPU)
+    def gather_create(self, world_size, rank):
+        """Allocates this rank's gathered obs/reward/done buffers; returns (tensors, 64-byte IPC handle)."""
+        po, pr, pd = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        self._check(self.lib.rw_gather_create(self._h, world_size, rank, ctypes.byref(po), ctypes.byref(pr),
+                                              ctypes.byref(pd), handle))
+        E, n, L = world_size * self.num_envs, self.cfg.n_agents, self.cfg.obs_len
+
+        def wrap(ptr, shape, typestr, dtype):
+            class _Raw:  # __cuda_array_interface__ view of library-owned memory
+                __cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
+            return torch.as_tensor(_Raw(), device=self.device).view(dtype).view(shape)
+        tensors = (wrap(po.value, (E, n, L), "<f4", torch.float32), wrap(pr.value, (E, n), "<f4", torch.float32),
+                   wrap(pd.value, (E,), "|u1", torch.uint8))
+        return tensors, handle.raw
+
+    def gather_open(self, handles: bytes):
+        buf = ctypes.create_string_buffer(handles, len(handles))
+        self._check(self.lib.rw_gather_open(self._h, buf))
+
+    def step_gather(self, actions):
+        self._check(self.lib.rw_step_gather(self._h, _ptr(actions), self._stream()))
 
     def flush_l2(self, buf, value=0):
         self._check(self.lib.rw_flush_l2(self._h, _ptr(buf), buf.numel() * buf.element_size(), int(value), self._stream()))

@@ -28,6 +28,12 @@ struct rw_handle {
     float *d_obs = nullptr, *d_reward = nullptr;
     uint8_t *d_done = nullptr;
     cudaStream_t host_stream = nullptr;
+    // fused push all-gather
+    void *d_gather = nullptr;
+    void *peer_base[RW_MAX_PEERS] = {};
+    int gather_world = 0, gather_rank = 0;
+    bool gather_open = false;
+    size_t gather_off_rew = 0, gather_off_done = 0;
     rw_info info;
 };
 
@@ -191,6 +197,9 @@ int rw_destroy(rw_handle *h) {
     cudaSetDevice(h->device);
     cudaFree(h->d_highway); cudaFree(h->d_home); cudaFree(h->d_home_id); cudaFree(h->d_cta_tables); cudaFree(h->d_normx); cudaFree(h->d_normy);
     cudaFree(h->d_state); cudaFree(h->d_rng); cudaFree(h->d_err);
+    for (int r = 0; r < h->gather_world; r++)
+        if (r != h->gather_rank && h->peer_base[r]) cudaIpcCloseMemHandle(h->peer_base[r]);
+    cudaFree(h->d_gather);
     cudaFree(h->d_actions); cudaFree(h->d_obs); cudaFree(h->d_reward); cudaFree(h->d_done);
     if (h->host_stream) cudaStreamDestroy(h->host_stream);
     delete h;
@@ -300,6 +309,72 @@ int rw_flush_l2(rw_handle *h, void *buf_dev, int64_t bytes, int value, void *str
     if (!h || !buf_dev || bytes < 16) return RW_EINVAL;
     CK(cudaSetDevice(h->device));
     CK(rw_launch_flush_l2(buf_dev, (size_t)bytes, value, h->p.sm_cta_bytes + h->p.sm_warp_bytes * h->p.warps_per_cta, (cudaStream_t)stream));
+    return RW_OK;
+}
+
+static void gather_set_peer(rw_handle *h, int r, void *base) {
+    h->peer_base[r] = base;
+    h->p.peer_obs[r] = (float *)base;
+    h->p.peer_rew[r] = (float *)((char *)base + h->gather_off_rew);
+    h->p.peer_done[r] = (uint8_t *)((char *)base + h->gather_off_done);
+}
+
+int rw_gather_create(rw_handle *h, int world_size, int rank, float **obs_all, float **reward_all, uint8_t **done_all,
+                     void *ipc_handle_out) {
+    if (!h || world_size < 1 || world_size > RW_MAX_PEERS || rank < 0 || rank >= world_size || !ipc_handle_out)
+        return fail(h, RW_EINVAL, "rw_gather_create: bad arguments (world_size 1..8)");
+    if (h->d_gather) return fail(h, RW_ESTATE, "rw_gather_create: already created");
+    CK(cudaSetDevice(h->device));
+    const RwParams &p = h->p;
+    const size_t W = (size_t)world_size, E = (size_t)p.E;
+    auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+    h->gather_off_rew = up(W * E * p.n * p.L * 4);
+    h->gather_off_done = h->gather_off_rew + up(W * E * p.n * 4);
+    const size_t total = h->gather_off_done + up(W * E);
+    CK(cudaMalloc(&h->d_gather, total));
+    CK(cudaMemset(h->d_gather, 0, total));
+    h->gather_world = world_size;
+    h->gather_rank = rank;
+    gather_set_peer(h, rank, h->d_gather);
+    cudaIpcMemHandle_t ipc;
+    CK(cudaIpcGetMemHandle(&ipc, h->d_gather));
+    static_assert(sizeof(ipc) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(ipc_handle_out, &ipc, 64);
+    if (obs_all) *obs_all = h->p.peer_obs[rank];
+    if (reward_all) *reward_all = h->p.peer_rew[rank];
+    if (done_all) *done_all = h->p.peer_done[rank];
+    return RW_OK;
+}
+
+int rw_gather_open(rw_handle *h, const void *ipc_handles) {
+    if (!h || !ipc_handles || !h->d_gather) return fail(h, RW_ESTATE, "rw_gather_open before rw_gather_create");
+    CK(cudaSetDevice(h->device));
+    for (int r = 0; r < h->gather_world; r++) {
+        if (r == h->gather_rank) continue;
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, (const char *)ipc_handles + 64 * (size_t)r, 64);
+        void *base = nullptr;
+        CK(cudaIpcOpenMemHandle(&base, ipc, cudaIpcMemLazyEnablePeerAccess));
+        gather_set_peer(h, r, base);
+    }
+    h->gather_open = true;
+    return RW_OK;
+}
+
+int rw_step_gather(rw_handle *h, const int32_t *actions_dev, void *stream) {
+    if (!h || !actions_dev) return RW_EINVAL;
+    if (!h->ready) return fail(h, RW_ESTATE, "rw_step_gather before rw_reset / rw_set_state");
+    if (!h->d_gather || (h->gather_world > 1 && !h->gather_open))
+        return fail(h, RW_ESTATE, "rw_step_gather before rw_gather_create / rw_gather_open");
+    CK(cudaSetDevice(h->device));
+    RwParams p = h->p;  // the plain entry points keep n_peers == 0
+    p.n_peers = h->gather_world;
+    p.my_rank = h->gather_rank;
+    p.gather_env0 = (int64_t)h->gather_rank * p.E;
+    float *obs = p.peer_obs[p.my_rank] + (size_t)p.gather_env0 * p.n * p.L;
+    float *rew = p.peer_rew[p.my_rank] + (size_t)p.gather_env0 * p.n;
+    uint8_t *done = p.peer_done[p.my_rank] + (size_t)p.gather_env0;
+    CK(rw_launch_main(RW_MODE_STEP, p, actions_dev, obs, rew, done, nullptr, (cudaStream_t)stream));
     return RW_OK;
 }
 

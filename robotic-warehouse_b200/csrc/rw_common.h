@@ -27,6 +27,7 @@
 #define RW_MAX_GOALS 16
 #define RW_MAX_MSG_BITS 16
 #define RW_RNG_WORDS 10
+#define RW_MAX_PEERS 8
 #define RW_MAX_SHELVES 8191
 // occupancy grid byte (shared memory, rebuilt every step): bits 0-5 id of the agent standing on the cell (0 = none),
 // bit 6 a shelf is on the cell (standing or carried), bit 7 that shelf is in the request queue
@@ -74,6 +75,13 @@ struct RwParams {
     int32_t sm_tile, sm_grid, sm_scratch, sm_obs, sm_bar, sm_tie, sm_warp_bytes;
     int32_t sm_cta_tx;     // bytes of the table image moved by the TMA (multiple of 16, < sm_cta_bytes - 8: the CTA mbarrier sits at the end)
     int32_t sm_cta_bytes;  // CTA-shared prologue region: highway[cells] u8 then home_id[cells] u16 (device only)
+    // fused push all-gather (multi-GPU, optional): every observation chunk is TMA-stored into the gathered buffer of
+    // every rank (peer-mapped over NVLink), rewards/done likewise with plain stores.  n_peers == 0: off.
+    int32_t n_peers, my_rank;
+    int64_t gather_env0;           // first world of this rank in the gathered tensors
+    float *peer_obs[RW_MAX_PEERS];
+    float *peer_rew[RW_MAX_PEERS];
+    uint8_t *peer_done[RW_MAX_PEERS];
     int32_t coop, gshift;  // cooperative step: a group of 1 << gshift lanes per world (rw_coop.cuh); 0 = one lane per world
     int32_t obs_parts;     // lanes per agent row in the observation gather (1 or 2)
     int32_t obs_tma;       // 1: observation chunks leave through cp.async.bulk, 0: 16-byte st.global from all lanes

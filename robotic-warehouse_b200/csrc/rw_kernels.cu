@@ -178,7 +178,20 @@ __global__ void __launch_bounds__(960, 1) rw_main_kernel(const __grid_constant__
             }
         }
         float *gdst = obs + (tile_env0 + c0) * n * L;
-        if (fast && p.obs_tma) {
+        if (fast && p.obs_tma && p.n_peers > 0) {
+            // fused push all-gather: the same staged chunk goes to this rank's slot of every rank's gathered tensor
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                const size_t off = (size_t)(p.gather_env0 + tile_env0 + c0) * n * L;
+                for (int d = 0; d < p.n_peers; d++) {
+                    const int dst = (p.my_rank + d) % p.n_peers;  // start with the local copy, then spread over the links
+                    bulk_s2g(p.peer_obs[dst] + off, buf, (uint32_t)p.obs_chunk_bytes);
+                }
+                bulk_commit();
+            }
+            buf_busy = true;
+        } else if (fast && p.obs_tma) {
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
@@ -276,6 +289,17 @@ __global__ void __launch_bounds__(960, 1) rw_main_kernel(const __grid_constant__
         }
         // ---- 4. observation gather after the fact: this warp takes every second chunk
         for (int c0 = role * CH; c0 < RW_TILE; c0 += 2 * CH) emit_chunk(c0);
+        if (MODE == RW_MODE_STEP && p.n_peers > 1 && role == 1) {
+            // rewards / done of this tile -> every peer's gathered tensors (the primary wrote the local copy)
+            const int n = p.n;
+            const size_t r0 = (size_t)(p.gather_env0 + tile_env0) * n, d0 = (size_t)(p.gather_env0 + tile_env0);
+            const int live = (int)((p.E - tile_env0) < RW_TILE ? (p.E - tile_env0) : RW_TILE);
+            for (int d = 1; d < p.n_peers; d++) {
+                const int dst = (p.my_rank + d) % p.n_peers;
+                for (int i = lane; i < live * n; i += 32) p.peer_rew[dst][r0 + i] = p.peer_rew[p.my_rank][r0 + i];
+                if (lane < live) p.peer_done[dst][d0 + lane] = p.peer_done[p.my_rank][d0 + lane];
+            }
+        }
     }
     RW_STAMP(5);
     if (lane == 0) bulk_wait_read<0>();  // shared memory must stay valid until the TMA has read it

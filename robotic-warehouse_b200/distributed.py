@@ -73,7 +73,28 @@ class ShardedVecWarehouse:
                         p.copy_(b[:sz])
         return g_obs, g_rew, g_done
 
+    def enable_fused_gather(self):
+        """Sets up the fused push all-gather (CUDA IPC peer mappings over NVLink): afterwards `step(..., gather=True)`
+        lets the step kernel's TMA stores write every observation chunk into all ranks' gathered tensors, and the only
+        collective left is a 4-byte all-reduce that acts as the barrier.  Needs uniform shards and one process per GPU."""
+        if not self.uniform:
+            raise ValueError("fused gather needs total_envs divisible by the number of ranks")
+        tensors, handle = self.local.backend.gather_create(self.world_size, self.rank)
+        handles = [None] * self.world_size
+        dist.all_gather_object(handles, handle, group=self.group)
+        self.local.backend.gather_open(b"".join(handles))
+        self._fused = tensors
+        self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        dist.barrier(group=self.group)
+
     def step(self, actions, gather=False):
+        if gather and getattr(self, "_fused", None) is not None:
+            a = actions
+            if not (isinstance(a, torch.Tensor) and a.dtype == torch.int32 and a.device == self.device and a.is_contiguous()):
+                a = torch.as_tensor(actions, device=self.device).to(torch.int32).contiguous()
+            self.local.backend.step_gather(a)
+            dist.all_reduce(self._flag, group=self.group)  # stream-ordered barrier: every rank's pushes have landed
+            return self._fused
         obs, rew, done = self.local.step(actions)
         if gather:
             return self.gather(obs, rew, done)
