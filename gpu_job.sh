@@ -1,3 +1,3 @@
 cd $GRAFT_REPO_ROOT
-timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -3
-python bench.py 2>&1 | tail -1 > gpurun_out/bench_r1.json; cat gpurun_out/bench_r1.json
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29521 tests/mgpu_check.py 2>&1 | tail -5
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus 2 --steps 100 --warmup 10 --no-cpu-baseline --e2e-steps 2 2>&1 | tail -1 | cut -c1-330
