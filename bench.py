@@ -35,6 +35,9 @@ WORKLOADS = {
     "small-4ag": ("rware-small-4ag-v1", {}, 32768),
     "medium-8ag-hard": ("rware-medium-8ag-hard-v1", {}, 32768),
     "large-16ag-r2": ("rware-large-16ag-v1", {"sensor_range": 2}, 16384),
+    # widened rows: image observations gathered on the device
+    "tiny-4ag-image": ("rware-tiny-4ag-v1", {"observation_type": 2}, 65536),
+    "tiny-4ag-imagedict": ("rware-tiny-4ag-v1", {"observation_type": 3}, 65536),
 }
 
 
@@ -90,7 +93,7 @@ def cpu_baseline(env_id, overrides, target_seconds=10.0, threads=None):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py
     import rware_b200
-    kw = rware_b200.env_kwargs(env_id, **overrides)
+    kw = rware_b200.env_kwargs(env_id, **{k: v for k, v in overrides.items() if k != "observation_type"})
     (H, W), highways, goals = rware_b200.layout_from_params(kw["shelf_columns"], kw["shelf_rows"], kw["column_height"])
     env = oracle_py.OracleEnv(highways, goals, kw["n_agents"], kw["msg_bits"], kw["sensor_range"], kw["request_queue_size"],
                               kw["max_inactivity_steps"], kw["max_steps"], kw["reward_type"].value)

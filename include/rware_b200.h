@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RW_ABI_VERSION 1
+#define RW_ABI_VERSION 2
 
 enum {
     RW_OK = 0,
@@ -38,6 +38,10 @@ enum {
 enum { RW_NOOP = 0, RW_FORWARD = 1, RW_LEFT = 2, RW_RIGHT = 3, RW_TOGGLE_LOAD = 4 };
 enum { RW_UP = 0, RW_DOWN = 1, RW_DIR_LEFT = 2, RW_DIR_RIGHT = 3 };
 enum { RW_REWARD_GLOBAL = 0, RW_REWARD_INDIVIDUAL = 1, RW_REWARD_TWO_STAGE = 2 };
+/* ObservationType (warehouse.py:52-56) and ImageLayer (warehouse.py:59-70) values */
+enum { RW_OBS_DICT = 0, RW_OBS_FLATTENED = 1, RW_OBS_IMAGE = 2, RW_OBS_IMAGE_DICT = 3 };
+enum { RW_LAYER_SHELVES = 0, RW_LAYER_REQUESTS = 1, RW_LAYER_AGENTS = 2, RW_LAYER_AGENT_DIRECTION = 3, RW_LAYER_AGENT_LOAD = 4,
+       RW_LAYER_GOALS = 5, RW_LAYER_ACCESSIBLE = 6 };
 
 /* Constructor kwargs of Warehouse.__init__ (warehouse.py:146-170) after layout construction
  * (warehouse.py:294-350, done by the host-side facade): all pointers are HOST pointers, copied by rw_create. */
@@ -53,6 +57,12 @@ typedef struct rw_config {
     int32_t reward_type;          /* RW_REWARD_* */
     int32_t normalised_coordinates;
     int32_t n_goals;              /* 1..16 */
+    int32_t observation_type;     /* RW_OBS_FLATTENED (default path; RW_OBS_DICT is served as FLATTENED and unflattened by the
+                                     host facade), RW_OBS_IMAGE or RW_OBS_IMAGE_DICT (warehouse.py:527-596, 726-742) */
+    int32_t image_directional;    /* image_observation_directional (warehouse.py:584-595) */
+    int32_t n_image_layers;       /* 0..7 */
+    int32_t image_layers[8];      /* RW_LAYER_*; AGENT_DIRECTION / AGENT_LOAD are rejected: the reference writes them with
+                                     transposed indices (warehouse.py:552, 558) and raises IndexError off the diagonal */
     const uint8_t *highways;      /* [grid_h*grid_w], row-major [y][x], 1 = highway (warehouse.py:308-326) */
     const int32_t *goals_xy;      /* [n_goals][2] = (x, y) in the reference's order (warehouse.py:303-306, 344-345) */
 } rw_config;
@@ -102,7 +112,8 @@ int rw_seed(rw_handle *h, const uint64_t *seeds_host, const uint8_t *mask_host, 
 int rw_reset(rw_handle *h, const uint8_t *mask_dev, float *obs_dev, void *stream);
 
 /* Warehouse.step(actions) (warehouse.py:804-946): one fused kernel.  actions_dev [E][n][A] int32;
- * obs_dev [E][n][L] float32 (may be NULL: skip the observation gather); reward_dev [E][n] float32;
+ * obs_dev [E][n][L] float32 (may be NULL: skip the observation gather; for the image types a row is the [C][K][K] image
+ * followed, for IMAGE_DICT, by the 6 feature floats, L = rw_info.obs_len); reward_dev [E][n] float32;
  * done_dev [E] uint8 (`terminated`; `truncated` is always False, warehouse.py:942). */
 int rw_step(rw_handle *h, const int32_t *actions_dev, float *obs_dev, float *reward_dev, uint8_t *done_dev,
             void *stream);

@@ -51,6 +51,8 @@ def lib():
         L.orc_get_state.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 11
         L.orc_set_state.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 11
         L.orc_get_grid.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_obs_image.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_obs_image.restype = ctypes.c_int
         L.orc_last_step_stats.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 3
         L.orc_py_tuple_hash.restype = ctypes.c_uint64
         L.orc_py_tuple_hash.argtypes = [ctypes.c_int64, ctypes.c_int64]
@@ -134,6 +136,19 @@ class OracleEnv:
         obs = np.zeros((self.n, self.L), np.float32)
         lib().orc_obs(self._h, _p(obs))
         return obs
+
+    def obs_image(self, layers=(0, 1, 2, 5, 6), directional=True, with_features=False):
+        """IMAGE observations [n, C, K, K] (and IMAGE_DICT features [n, 6]); IndexError where the reference raises."""
+        lay = np.ascontiguousarray(layers, np.int32)
+        K = 2 * self._cfg.sensor_range + 1
+        out = np.zeros((self.n, len(lay), K, K), np.float32)
+        feat = np.zeros((self.n, 6), np.float32)
+        rc = lib().orc_obs_image(self._h, _p(lay), len(lay), int(directional), _p(out), _p(feat))
+        if rc == -1:
+            raise IndexError("AGENT_DIRECTION / AGENT_LOAD layer: transposed index out of bounds (as in the reference)")
+        if rc:
+            raise ValueError(f"orc_obs_image failed: {rc}")
+        return (out, feat) if with_features else out
 
     def get_state(self):
         n, S, R, mb = self.n, self.S, self.R, self.msg_bits

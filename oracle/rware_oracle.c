@@ -152,6 +152,77 @@ void orc_obs(const orc_env *e, float *obs) {
     for (int a = 0; a < e->cfg.n_agents; a++) make_obs_agent(e, a, obs + (size_t)a * (size_t)e->L);
 }
 
+/* ---------------------------------------------------------------- image observations (warehouse.py:527-596, 726-742) */
+int orc_obs_image(const orc_env *e, const int32_t *layers, int n_layers, int directional, float *out, float *features) {
+    const orc_config *c = &e->cfg;
+    const int H = c->H, W = c->W, r = c->sensor_range, K = 2 * r + 1, n = c->n_agents;
+    const int PH = H + 2 * r, PW = W + 2 * r; /* np.pad(layer, sensor_range) 573 */
+    float *glob = (float *)calloc((size_t)n_layers * PH * PW, sizeof(float));
+    for (int li = 0; li < n_layers; li++) {
+        float *L = glob + (size_t)li * PH * PW;
+#define AT(row, col) L[((row) + r) * PW + (col) + r]
+        switch (layers[li]) {
+            case 0: /* SHELVES 533-536 */
+                for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) AT(y, x) = e->grid[H * W + y * W + x] > 0 ? 1.0f : 0.0f;
+                break;
+            case 1: /* REQUESTS 538-541 */
+                for (int q = 0; q < c->request_queue_size; q++) { int s = e->queue[q] - 1; AT(e->sy[s], e->sx[s]) = 1.0f; }
+                break;
+            case 2: /* AGENTS 543-546 */
+                for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) AT(y, x) = e->grid[y * W + x] > 0 ? 1.0f : 0.0f;
+                break;
+            case 3: /* AGENT_DIRECTION 548-552: layer[ag.x, ag.y] (sic) */
+                for (int a = 0; a < n; a++) {
+                    if (e->ax[a] >= H || e->ay[a] >= W) { free(glob); return -1; }
+                    AT(e->ax[a], e->ay[a]) = (float)(e->adir[a] + 1);
+                }
+                break;
+            case 4: /* AGENT_LOAD 554-558: layer[ag.x, ag.y] (sic) */
+                for (int a = 0; a < n; a++)
+                    if (e->acarry[a]) {
+                        if (e->ax[a] >= H || e->ay[a] >= W) { free(glob); return -1; }
+                        AT(e->ax[a], e->ay[a]) = 1.0f;
+                    }
+                break;
+            case 5: /* GOALS 560-563: goals are (x, y); layer[y, x] */
+                for (int g = 0; g < c->n_goals; g++) AT(e->goals_xy[2 * g + 1], e->goals_xy[2 * g]) = 1.0f;
+                break;
+            case 6: /* ACCESSIBLE 565-568 */
+                for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) AT(y, x) = 1.0f;
+                for (int a = 0; a < n; a++) AT(e->ay[a], e->ax[a]) = 0.0f;
+                break;
+            default: free(glob); return -2;
+        }
+#undef AT
+    }
+    for (int a = 0; a < n; a++) {
+        /* 578-582: rows agent.y .. agent.y+2r, columns agent.x .. agent.x+2r of the padded layers */
+        for (int li = 0; li < n_layers; li++) {
+            const float *L = glob + (size_t)li * PH * PW;
+            float *o = out + ((size_t)a * n_layers + li) * K * K;
+            int k = 0; /* np.rot90(obs, k, axes=(1, 2)), 584-595 */
+            if (directional) k = e->adir[a] == ORC_DOWN ? 2 : e->adir[a] == ORC_DIR_LEFT ? 3 : e->adir[a] == ORC_DIR_RIGHT ? 1 : 0;
+            for (int i = 0; i < K; i++)
+                for (int j = 0; j < K; j++) {
+                    int si, sj; /* R = rot90(A, k): k=1 R[i][j]=A[j][K-1-i]; k=2 A[K-1-i][K-1-j]; k=3 A[K-1-j][i] */
+                    if (k == 0) { si = i; sj = j; }
+                    else if (k == 1) { si = j; sj = K - 1 - i; }
+                    else if (k == 2) { si = K - 1 - i; sj = K - 1 - j; }
+                    else { si = K - 1 - j; sj = i; }
+                    o[i * K + j] = L[(e->ay[a] + si) * PW + e->ax[a] + sj];
+                }
+        }
+        if (features) { /* 727-738 */
+            float *f = features + (size_t)a * 6;
+            for (int d = 0; d < 4; d++) f[d] = e->adir[a] == d ? 1.0f : 0.0f;
+            f[4] = e->highways[e->ay[a] * W + e->ax[a]] ? 1.0f : 0.0f;
+            f[5] = e->acarry[a] ? 1.0f : 0.0f;
+        }
+    }
+    free(glob);
+    return 0;
+}
+
 /* ---------------------------------------------------------------- seeding / reset (warehouse.py:757-802, 962-964) */
 void orc_seed(orc_env *e, uint64_t seed) {
     np_seed(&e->rng, seed);

@@ -58,6 +58,14 @@ int orc_step(orc_env *e, const int32_t *actions, float *obs, double *reward, uin
 /* warehouse.py:722-744 -> 598-674 for every agent */
 void orc_obs(const orc_env *e, float *obs);
 
+/* warehouse.py:527-596 (_make_img_obs) for every agent: out [n][n_layers][K][K] float32, K = 2*sensor_range+1.
+ * layers: ImageLayer values (warehouse.py:59-70) 0 SHELVES 1 REQUESTS 2 AGENTS 3 AGENT_DIRECTION 4 AGENT_LOAD 5 GOALS
+ * 6 ACCESSIBLE.  Layers 3 and 4 are written with transposed indices in the reference (552, 558: layer[ag.x, ag.y]) and
+ * make it raise IndexError as soon as an agent stands at y >= W or x >= H; the oracle restates them literally and returns
+ * -1 in exactly that case.  directional: rot90 towards the agent's heading (584-595).
+ * features (IMAGE_DICT, warehouse.py:726-742): [n][6] = one-hot direction, on_highway, carrying; may be NULL. */
+int orc_obs_image(const orc_env *e, const int32_t *layers, int n_layers, int directional, float *out, float *features);
+
 /* plain-array state access (what the reference's tests poke through env.agents[i].x etc.).
  * agent arrays [n]; carry = shelf id (1-based) or 0; msg [n][msg_bits]; shelf arrays [S]; queue [R] ids;
  * counters[2] = {cur_steps, cur_inactive_steps}; rng[10] = np_export() words.  NULL pointers are skipped. */

@@ -13,15 +13,16 @@ import torch
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "lib", "librware_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_PKG_DIR), "include", "rware_b200.h")
-RW_ABI_VERSION = 1
+RW_ABI_VERSION = 2
 RNG_WORDS = 10
 
 
 class RwConfig(ctypes.Structure):
     _fields_ = [(k, ctypes.c_int32) for k in (
         "abi_version", "grid_h", "grid_w", "n_agents", "msg_bits", "sensor_range", "request_queue_size",
-        "max_inactivity_steps", "max_steps", "reward_type", "normalised_coordinates", "n_goals")] + [
-        ("highways", ctypes.c_void_p), ("goals_xy", ctypes.c_void_p)]
+        "max_inactivity_steps", "max_steps", "reward_type", "normalised_coordinates", "n_goals", "observation_type",
+        "image_directional", "n_image_layers")] + [("image_layers", ctypes.c_int32 * 8),
+                                                   ("highways", ctypes.c_void_p), ("goals_xy", ctypes.c_void_p)]
 
 
 class RwInfo(ctypes.Structure):
@@ -103,7 +104,8 @@ class EnvConfig:
     """Constructor kwargs of the reference's Warehouse (rware/warehouse.py:146-170) after layout construction."""
 
     def __init__(self, highways, goals, n_agents, msg_bits=0, sensor_range=1, request_queue_size=1,
-                 max_inactivity_steps=None, max_steps=None, reward_type=1, normalised_coordinates=False):
+                 max_inactivity_steps=None, max_steps=None, reward_type=1, normalised_coordinates=False,
+                 observation_type=1, image_layers=(0, 1, 2, 5, 6), image_directional=True):
         self.highways = np.ascontiguousarray(highways, dtype=np.uint8)
         self.grid_size = tuple(int(v) for v in self.highways.shape)
         self.goals = [(int(x), int(y)) for x, y in goals]
@@ -116,14 +118,23 @@ class EnvConfig:
         self.reward_type = int(getattr(reward_type, "value", reward_type))
         self.normalised_coordinates = bool(normalised_coordinates)
         self.n_shelves = int((self.highways == 0).sum())
-        self.obs_len = 8 + (2 * self.sensor_range + 1) ** 2 * (7 + self.msg_bits)  # rware/warehouse.py:432-443
+        self.observation_type = int(getattr(observation_type, "value", observation_type))
+        self.image_layers = [int(getattr(v, "value", v)) for v in image_layers]
+        self.image_directional = bool(image_directional)
+        K = 2 * self.sensor_range + 1
+        if self.observation_type >= 2:  # IMAGE / IMAGE_DICT rows: [C][K][K] image (+ 6 features)
+            self.obs_len = len(self.image_layers) * K * K + (6 if self.observation_type == 3 else 0)
+        else:
+            self.obs_len = 8 + K * K * (7 + self.msg_bits)  # rware/warehouse.py:432-443
 
     def to_struct(self):
         self._goals_arr = np.ascontiguousarray(np.asarray(self.goals, np.int32).reshape(-1, 2))
         H, W = self.grid_size
         return RwConfig(RW_ABI_VERSION, H, W, self.n_agents, self.msg_bits, self.sensor_range, self.request_queue_size,
                         int(self.max_inactivity_steps or 0), int(self.max_steps or 0), self.reward_type,
-                        int(self.normalised_coordinates), len(self.goals), self.highways.ctypes.data,
+                        int(self.normalised_coordinates), len(self.goals), self.observation_type,
+                        int(self.image_directional), len(self.image_layers) if self.observation_type >= 2 else 0,
+                        (ctypes.c_int32 * 8)(*(self.image_layers + [0] * 8)[:8]), self.highways.ctypes.data,
                         self._goals_arr.ctypes.data)
 
 

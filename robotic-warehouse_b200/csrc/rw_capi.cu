@@ -70,6 +70,17 @@ int rw_create(const rw_config *cfg, int64_t num_envs, int device, rw_handle **ou
     if (cfg->n_goals < 1 || cfg->n_goals > RW_MAX_GOALS) return fail(h, RW_EINVAL, "n_goals must be 1..16");
     if (!cfg->highways || !cfg->goals_xy) return fail(h, RW_EINVAL, "highways/goals_xy missing");
     if (cfg->reward_type < 0 || cfg->reward_type > 2) return fail(h, RW_EINVAL, "bad reward_type");
+    if (cfg->observation_type < 0 || cfg->observation_type > 3) return fail(h, RW_EINVAL, "bad observation_type");
+    if (cfg->observation_type >= RW_OBS_IMAGE) {
+        if (cfg->n_image_layers < 1 || cfg->n_image_layers > 7) return fail(h, RW_EINVAL, "n_image_layers must be 1..7");
+        for (int i = 0; i < cfg->n_image_layers; i++) {
+            int ly = cfg->image_layers[i];
+            if (ly < 0 || ly > 6) return fail(h, RW_EINVAL, "bad image layer");
+            if (ly == RW_LAYER_AGENT_DIRECTION || ly == RW_LAYER_AGENT_LOAD)
+                return fail(h, RW_EINVAL, "image layers AGENT_DIRECTION / AGENT_LOAD are not supported: the reference writes them with "
+                                          "transposed indices (warehouse.py:552, 558) and raises IndexError off the diagonal");
+        }
+    }
     const int H = cfg->grid_h, W = cfg->grid_w, cells = H * W, n = cfg->n_agents;
     if (n > cells) return fail(h, RW_EINVAL, "more agents than cells");
     std::vector<uint16_t> home;
@@ -148,7 +159,8 @@ static int create_impl(rw_handle *h, const rw_config *cfg, int64_t num_envs, int
     }
     {   // image of the CTA-shared table region: highway bytes, then (2-byte aligned) home ids
         std::vector<uint8_t> img((size_t)p.sm_cta_bytes, 0);
-        memcpy(img.data(), cfg->highways, cells);
+        for (int c = 0; c < cells; c++) img[c] = cfg->highways[c] ? 1 : 0;
+        for (int g = 0; g < cfg->n_goals; g++) img[cfg->goals_xy[2 * g + 1] * W + cfg->goals_xy[2 * g]] |= 2;  // bit 1: goal cell
         uint16_t *hid = reinterpret_cast<uint16_t *>(img.data() + ((cells + 1) & ~1));
         for (int k = 0; k < S; k++) hid[home[k]] = (uint16_t)(k + 1);
         CK(cudaMalloc(&h->d_cta_tables, img.size()));

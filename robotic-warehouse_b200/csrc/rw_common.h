@@ -56,6 +56,8 @@ struct RwParams {
     int32_t H, W, cells, n, msg_bits, A, r, win, K, cellF, L, R, S;
     int32_t reward_type, max_steps, max_inact, norm_coords, n_goals, auto_reset;
     int32_t goal_cell[RW_MAX_GOALS];
+    int32_t obs_kind;             // 0 flattened vector, 2 image, 3 image + features (ObservationType values)
+    int32_t img_directional, n_layers, img_layers[8];
     // tile layout
     int32_t nw, w_agent, w_msg, w_shelf, w_queue, w_steps, w_inact;
     // static device tables

@@ -73,6 +73,14 @@ static inline void rw_fill_params(RwParams &p, const rw_config &c, int64_t num_e
     p.H = H; p.W = W; p.cells = cells; p.n = n; p.msg_bits = cfg->msg_bits; p.A = 1 + cfg->msg_bits;
     p.r = cfg->sensor_range; p.win = 2 * p.r + 1; p.K = p.win * p.win; p.cellF = 7 + p.msg_bits;
     p.L = 8 + p.K * p.cellF;  // warehouse.py:432-443
+    p.obs_kind = 0;
+    if (cfg->observation_type == RW_OBS_IMAGE || cfg->observation_type == RW_OBS_IMAGE_DICT) {
+        p.obs_kind = cfg->observation_type;
+        p.img_directional = cfg->image_directional ? 1 : 0;
+        p.n_layers = cfg->n_image_layers;
+        for (int i = 0; i < 8; i++) p.img_layers[i] = cfg->image_layers[i];
+        p.L = p.n_layers * p.K + (p.obs_kind == RW_OBS_IMAGE_DICT ? 6 : 0);  // warehouse.py:365-388, 400-427
+    }
     p.R = cfg->request_queue_size; p.S = S;
     p.reward_type = cfg->reward_type; p.max_steps = cfg->max_steps; p.max_inact = cfg->max_inactivity_steps;
     p.norm_coords = cfg->normalised_coordinates ? 1 : 0; p.n_goals = cfg->n_goals; p.auto_reset = 0;

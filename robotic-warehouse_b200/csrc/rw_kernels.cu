@@ -173,8 +173,8 @@ __global__ void __launch_bounds__(960, 1) rw_main_kernel(const __grid_constant__
                 le.sc_step = 0;
                 le.highway = s_highway;
                 le.home_id = s_home_id;
-                if (P == 2) rw_obs_agent<C, 2>(p, le, ea - el * n, buf + ea * L, part);
-                else rw_obs_agent<C, 1>(p, le, ea - el * n, buf + ea * L, 0);
+                if (P == 2) rw_obs_row<C, 2>(p, le, ea - el * n, buf + ea * L, part);
+                else rw_obs_row<C, 1>(p, le, ea - el * n, buf + ea * L, 0);
             }
         }
         float *gdst = obs + (tile_env0 + c0) * n * L;

@@ -689,7 +689,7 @@ RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, float *reward, int64
             } else if (a == RW_ACT_TOGGLE) {  // ref:889-899
                 if (!rw_acarry(awv[i])) {
                     if (gsv[i] & RW_G_SHELF) rw_set_agent(l, i, awv[i] | ((uint32_t)rw_shelf_at<C>(p, l, sv[i]) << 19));
-                } else if (!l.highway[sv[i]]) {
+                } else if (!(l.highway[sv[i]] & 1)) {
                     if (rw_adeliv(awv[i]) && p.reward_type == 2) rew_lo += 1ULL << (4 * i);
                     rw_set_agent(l, i, awv[i] & 0x3ffffu & ~(1u << 18));
                 }
@@ -768,7 +768,7 @@ RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, float *reward, int64
         } else {  // TOGGLE_LOAD ref:889-899
             if (!rw_acarry(aw)) {
                 if (l.g[s] & RW_G_SHELF) rw_set_agent(l, i, aw | ((uint32_t)rw_shelf_at<C>(p, l, s) << 19));
-            } else if (!l.highway[s]) {
+            } else if (!(l.highway[s] & 1)) {
                 if (rw_adeliv(aw) && p.reward_type == 2) {
                     if (i < 16) rew_lo += 1ULL << (4 * i); else rew_hi += 1ULL << (4 * (i - 16));
                 }
@@ -820,7 +820,7 @@ RW_HD void rw_obs_agent(const RwParams &p, const RwLane &l, int i, float *out, i
         out[4] = d == 1 ? 1.0f : 0.0f;
         out[5] = d == 2 ? 1.0f : 0.0f;
         out[6] = d == 3 ? 1.0f : 0.0f;
-        out[7] = l.highway[y * W + x] ? 1.0f : 0.0f;      // ref:647
+        out[7] = (l.highway[y * W + x] & 1) ? 1.0f : 0.0f;  // ref:647
     }
     // Slice s covers window cells [s*Kp, min(K, (s+1)*Kp)).  `part` varies across lanes, so everything that depends on
     // it is a select between the compile-time values of slice 0 and slice 1 (no divergence, no integer division).
@@ -855,4 +855,63 @@ RW_HD void rw_obs_agent(const RwParams &p, const RwLane &l, int i, float *out, i
             oc[6 + mb] = (gb & RW_G_REQ) ? 1.0f : 0.0f;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Image observation of agent i (ref:527-596): out = [n_layers][K][K] float32, K = 2r+1, the window centred on the agent,
+// rotated towards its heading when `img_directional` (np.rot90, ref:584-595); IMAGE_DICT appends 6 feature floats
+// (one-hot direction, on_highway, carrying; ref:726-742).  Layers (ImageLayer values, ref:59-70): 0 SHELVES,
+// 1 REQUESTS, 2 AGENTS, 5 GOALS, 6 ACCESSIBLE (0 outside the map: the reference pads with zeros, ref:573).
+// Sliced over the window positions like rw_obs_agent.
+template <class C, int nparts>
+RW_HD void rw_obs_image_agent(const RwParams &p, const RwLane &l, int i, float *out, int part) {
+    const uint32_t aw = rw_agent(l, i);
+    const int x = rw_ax(aw), y = rw_ay(aw), d = rw_adir(aw);
+    const int W = C::W(p), H = C::H(p), r = C::r(p), K = 2 * r + 1, KK = K * K;
+    // k quarter turns counter-clockwise: DOWN 2, LEFT 3, RIGHT 1 (ref:586-594)
+    const int rot = p.img_directional ? (d == 1 ? 2 : d == 2 ? 3 : d == 3 ? 1 : 0) : 0;
+    const int Kp = (KK + nparts - 1) / nparts;
+    const int o0 = part * Kp;
+#pragma unroll
+    for (int k = 0; k < Kp; k++) {
+        const int o = o0 + k;
+        if (o < KK) {
+            const int oi = o / K, oj = o - oi * K;
+            int si, sj;  // R = rot90(A, k): k=1 R[i][j] = A[j][K-1-i]; k=2 A[K-1-i][K-1-j]; k=3 A[K-1-j][i]
+            if (rot == 0) { si = oi; sj = oj; }
+            else if (rot == 1) { si = oj; sj = K - 1 - oi; }
+            else if (rot == 2) { si = K - 1 - oi; sj = K - 1 - oj; }
+            else { si = K - 1 - oj; sj = oi; }
+            const int yy = y - r + si, xx = x - r + sj;
+            const bool in = (unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W;
+            uint32_t gb = 0, fl = 0;
+            if (in) { gb = l.g[yy * W + xx]; fl = l.highway[yy * W + xx]; }
+            for (int li = 0; li < p.n_layers; li++) {
+                const int ly = p.img_layers[li];
+                bool v;
+                if (ly == 0) v = (gb & RW_G_SHELF) != 0;
+                else if (ly == 1) v = (gb & RW_G_REQ) != 0;
+                else if (ly == 2) v = (gb & RW_G_AGENT) != 0;
+                else if (ly == 5) v = (fl & 2u) != 0;
+                else v = in && !(gb & RW_G_AGENT);  // ACCESSIBLE
+                out[li * KK + o] = v ? 1.0f : 0.0f;
+            }
+        }
+    }
+    if (part == 0 && p.obs_kind == 3) {
+        float *f = out + p.n_layers * KK;
+        f[0] = d == 0 ? 1.0f : 0.0f;
+        f[1] = d == 1 ? 1.0f : 0.0f;
+        f[2] = d == 2 ? 1.0f : 0.0f;
+        f[3] = d == 3 ? 1.0f : 0.0f;
+        f[4] = (l.highway[y * W + x] & 1) ? 1.0f : 0.0f;
+        f[5] = rw_acarry(aw) ? 1.0f : 0.0f;
+    }
+}
+
+// dispatch on the configured observation type
+template <class C, int nparts>
+RW_HD void rw_obs_row(const RwParams &p, const RwLane &l, int i, float *out, int part) {
+    if (p.obs_kind == 0) rw_obs_agent<C, nparts>(p, l, i, out, part);
+    else rw_obs_image_agent<C, nparts>(p, l, i, out, part);
 }

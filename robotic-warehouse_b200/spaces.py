@@ -5,7 +5,7 @@ import numpy as np
 
 try:  # pragma: no cover - depends on the environment
     import gymnasium as _gym
-    from gymnasium.spaces import Box, Discrete, MultiDiscrete, Tuple  # noqa: F401
+    from gymnasium.spaces import Box, Dict, Discrete, MultiBinary, MultiDiscrete, Tuple  # noqa: F401
     HAVE_GYMNASIUM = True
 except Exception:  # gymnasium absent
     _gym = None
@@ -87,6 +87,54 @@ except Exception:  # gymnasium absent
 
         def __repr__(self):
             return f"Box({self.shape}, {self.dtype})"
+
+    class MultiBinary(_Space):
+        def __init__(self, n):
+            self.n = n
+            self.shape = (n,) if isinstance(n, (int, np.integer)) else tuple(n)
+            self.dtype = np.dtype(np.int8)
+
+        def sample(self):
+            return self.np_random.integers(0, 2, size=self.shape, dtype=np.int8)
+
+        def contains(self, x):
+            x = np.asarray(x)
+            return x.shape == self.shape and bool(np.all((x == 0) | (x == 1)))
+
+        def __eq__(self, other):
+            return isinstance(other, MultiBinary) and self.shape == other.shape
+
+        def __repr__(self):
+            return f"MultiBinary({self.n})"
+
+    class Dict(_Space):
+        def __init__(self, spaces):
+            from collections import OrderedDict
+            self.spaces = OrderedDict(spaces if isinstance(spaces, OrderedDict) else sorted(dict(spaces).items()))
+
+        def sample(self):
+            return {k: s.sample() for k, s in self.spaces.items()}
+
+        def contains(self, x):
+            return set(x.keys()) == set(self.spaces.keys()) and all(s.contains(x[k]) for k, s in self.spaces.items())
+
+        def __getitem__(self, k):
+            return self.spaces[k]
+
+        def keys(self):
+            return self.spaces.keys()
+
+        def __iter__(self):
+            return iter(self.spaces)
+
+        def __len__(self):
+            return len(self.spaces)
+
+        def __eq__(self, other):
+            return isinstance(other, Dict) and self.spaces == other.spaces
+
+        def __repr__(self):
+            return "Dict(" + ", ".join(f"{k!r}: {v!r}" for k, v in self.spaces.items()) + ")"
 
     class Tuple(_Space):
         def __init__(self, spaces):

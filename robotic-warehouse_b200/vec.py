@@ -21,14 +21,16 @@ from ._capi import STATE_FIELDS, CudaBackend, EnvConfig
 class VecWarehouse:
     def __init__(self, num_envs, shelf_columns=None, column_height=None, shelf_rows=None, n_agents=1, msg_bits=0,
                  sensor_range=1, request_queue_size=1, max_inactivity_steps=None, max_steps=None, reward_type=1,
-                 layout=None, normalised_coordinates=False, device=None, auto_reset=False, _backend_factory=None):
+                 layout=None, normalised_coordinates=False, device=None, auto_reset=False, _backend_factory=None,
+                 observation_type=1, image_observation_layers=(0, 1, 2, 5, 6), image_observation_directional=True):
         if not layout:
             self.grid_size, self.highways, self.goals = _layout.layout_from_params(shelf_columns, shelf_rows, column_height)
             self.column_height = column_height
         else:
             self.grid_size, self.highways, self.goals = _layout.layout_from_str(layout)
         self.cfg = EnvConfig(self.highways, self.goals, n_agents, msg_bits, sensor_range, request_queue_size,
-                             max_inactivity_steps, max_steps, reward_type, normalised_coordinates)
+                             max_inactivity_steps, max_steps, reward_type, normalised_coordinates,
+                             observation_type, image_observation_layers, image_observation_directional)
         self.num_envs = int(num_envs)
         self.n_agents, self.msg_bits, self.sensor_range = self.cfg.n_agents, self.cfg.msg_bits, self.cfg.sensor_range
         self.request_queue_size = self.cfg.request_queue_size
@@ -43,6 +45,15 @@ class VecWarehouse:
         self._done = torch.empty((E,), dtype=torch.uint8, device=self.device)
         self.auto_reset = bool(auto_reset)
         self.backend.set_auto_reset(self.auto_reset)
+
+    def split_image_obs(self, obs):
+        """For the image observation types: (image [E, n, C, K, K], features [E, n, 6] or None) views of an obs tensor."""
+        c = self.cfg
+        assert c.observation_type >= 2
+        K = 2 * c.sensor_range + 1
+        C = len(c.image_layers)
+        img = obs[..., : C * K * K].reshape(*obs.shape[:-1], C, K, K)
+        return img, (obs[..., C * K * K:] if c.observation_type == 3 else None)
 
     # ------------------------------------------------------------------ seeding / reset
     def seed(self, seed, mask=None):

@@ -103,13 +103,21 @@ class Warehouse:
                  observation_type: ObservationType = ObservationType.FLATTENED, image_observation_layers=None,
                  image_observation_directional: bool = True, normalised_coordinates: bool = False,
                  render_mode: str = "human", device=None, _backend_factory=None):
-        if observation_type != ObservationType.FLATTENED:
-            raise NotImplementedError(
-                "rware_b200 implements the default FLATTENED observation type; DICT/IMAGE/IMAGE_DICT are outside the "
-                "accelerated step path (DESIGN.md, scope)")
+        if image_observation_layers is None:  # warehouse.py:160-166
+            image_observation_layers = [ImageLayer.SHELVES, ImageLayer.REQUESTS, ImageLayer.AGENTS, ImageLayer.GOALS,
+                                        ImageLayer.ACCESSIBLE]
+        self.observation_type = ObservationType(getattr(observation_type, "value", observation_type))
+        self.image_observation_layers = [ImageLayer(getattr(v, "value", v)) for v in image_observation_layers]
+        self.image_observation_directional = image_observation_directional
+        # DICT observations carry the same information as FLATTENED rows: the device produces the rows, the host
+        # unflattens them (warehouse.py:676-720).  IMAGE / IMAGE_DICT rows come from the image gather on the device.
+        dev_type = ObservationType.FLATTENED if self.observation_type == ObservationType.DICT else self.observation_type
         self._vec = VecWarehouse(1, shelf_columns, column_height, shelf_rows, n_agents, msg_bits, sensor_range,
                                  request_queue_size, max_inactivity_steps, max_steps, reward_type, layout,
-                                 normalised_coordinates, device=device, _backend_factory=_backend_factory)
+                                 normalised_coordinates, device=device, _backend_factory=_backend_factory,
+                                 observation_type=dev_type.value,
+                                 image_observation_layers=[v.value for v in self.image_observation_layers],
+                                 image_observation_directional=image_observation_directional)
         v = self._vec
         self.grid_size = v.grid_size
         self.highways = v.highways
@@ -134,19 +142,18 @@ class Warehouse:
         self.request_queue: List[Shelf] = []
         self.agents: List[Agent] = []
         self.shelfs: List[Shelf] = []
-        self.fast_obs = True
-        self.image_obs = None
-        self.image_dict_obs = None
+        self.fast_obs = self.observation_type == ObservationType.FLATTENED
+        self.image_obs = self.observation_type == ObservationType.IMAGE
+        self.image_dict_obs = self.observation_type == ObservationType.IMAGE_DICT
         # rware/warehouse.py:432-443, 505-522
         self._obs_bits_for_self = 4 + len(Direction)
         self._obs_bits_per_agent = 1 + len(Direction) + msg_bits
         self._obs_bits_per_shelf = 2
         self._obs_bits_for_requests = 2
         self._obs_sensor_locations = (1 + 2 * sensor_range) ** 2
-        self._obs_length = v.obs_len
-        self.observation_space = spaces.Tuple(tuple(
-            spaces.Box(low=-float("inf"), high=float("inf"), shape=(self._obs_length,), dtype=np.float32)
-            for _ in range(n_agents)))
+        self._obs_length = (self._obs_bits_for_self + self._obs_sensor_locations * self._obs_bits_per_agent
+                            + self._obs_sensor_locations * self._obs_bits_per_shelf)
+        self.observation_space = self._make_observation_space()
         self.global_image = None
         self.renderer = None
         self.render_mode = render_mode
@@ -206,9 +213,68 @@ class Warehouse:
         self._cur_inactive_steps = int(st["cur_inactive"])
         self._recalc_grid()
 
+    def _make_observation_space(self):
+        n, K = self.n_agents, 1 + 2 * self.sensor_range
+        inf = float("inf")
+        if self.observation_type == ObservationType.FLATTENED:  # warehouse.py:505-522
+            return spaces.Tuple(tuple(spaces.Box(low=-inf, high=inf, shape=(self._obs_length,), dtype=np.float32)
+                                      for _ in range(n)))
+        if self.observation_type in (ObservationType.IMAGE, ObservationType.IMAGE_DICT):  # warehouse.py:352-427
+            C = len(self.image_observation_layers)
+            hi = np.ones((C, K, K), np.float32)
+            for i, layer in enumerate(self.image_observation_layers):
+                if layer == ImageLayer.AGENT_DIRECTION:
+                    hi[i] *= 4
+            image = spaces.Box(np.zeros((C, K, K), np.float32), hi, dtype=np.float32)
+            if self.observation_type == ObservationType.IMAGE:
+                return spaces.Tuple(tuple([image] * n))
+            feats = spaces.Box(low=-inf, high=inf, shape=(6,), dtype=np.float32)
+            return spaces.Tuple(tuple(spaces.Dict({"image": image, "features": feats}) for _ in range(n)))
+        # DICT, warehouse.py:429-503
+        from collections import OrderedDict
+        hi = np.ones(2) if self.normalised_coordinates else np.ones(2) * max(self.grid_size)
+        loc = spaces.Box(low=np.zeros(2), high=hi, shape=(2,), dtype=np.float32 if self.normalised_coordinates else np.int32)
+        self_space = spaces.Dict(OrderedDict([("location", loc), ("carrying_shelf", spaces.MultiBinary(1)),
+                                              ("direction", spaces.Discrete(4)), ("on_highway", spaces.MultiBinary(1))]))
+        per = OrderedDict([("has_agent", spaces.MultiBinary(1)), ("direction", spaces.Discrete(4))])
+        if self.msg_bits > 0:
+            per["local_message"] = spaces.MultiBinary(self.msg_bits)
+        per.update([("has_shelf", spaces.MultiBinary(1)), ("shelf_requested", spaces.MultiBinary(1))])
+        return spaces.Tuple(tuple(
+            spaces.Dict(OrderedDict([("self", self_space),
+                                     ("sensors", spaces.Tuple(self._obs_sensor_locations * (spaces.Dict(per),)))]))
+            for _ in range(n)))
+
+    def _unflatten(self, row, agent):
+        """FLATTENED row -> the nested DICT observation of warehouse.py:676-720."""
+        mb, per = self.msg_bits, 7 + self.msg_bits
+        ax, ay = (agent.x / (self.grid_size[1] - 1), agent.y / (self.grid_size[0] - 1)) if self.normalised_coordinates \
+            else (agent.x, agent.y)
+        obs = {"self": {"location": np.array([ax, ay], dtype=np.int32), "carrying_shelf": [int(row[2])],
+                        "direction": int(np.argmax(row[3:7])), "on_highway": [int(row[7])]}}
+        sensors = []
+        for c in range(self._obs_sensor_locations):
+            cell = row[8 + c * per: 8 + (c + 1) * per]
+            has_agent = int(cell[0])
+            msg = None
+            if mb > 0:
+                msg = np.asarray(cell[5:5 + mb], dtype=np.float64) if has_agent else mb * [0]
+            sensors.append({"has_agent": [has_agent], "direction": int(np.argmax(cell[1:5])) if has_agent else 0,
+                            "local_message": msg, "has_shelf": [int(cell[5 + mb])], "shelf_requested": [int(cell[6 + mb])]})
+        obs["sensors"] = tuple(sensors)
+        return obs
+
     def _obs_tuple(self, obs_tensor):
         o = obs_tensor[0].cpu().numpy()
-        return tuple(o[i].copy() for i in range(self.n_agents))
+        if self.observation_type == ObservationType.FLATTENED:
+            return tuple(o[i].copy() for i in range(self.n_agents))
+        if self.observation_type == ObservationType.DICT:
+            return tuple(self._unflatten(o[i], a) for i, a in enumerate(self.agents))
+        K, C = 1 + 2 * self.sensor_range, len(self.image_observation_layers)
+        imgs = [o[i, : C * K * K].reshape(C, K, K).copy() for i in range(self.n_agents)]
+        if self.observation_type == ObservationType.IMAGE:
+            return tuple(imgs)
+        return tuple({"image": imgs[i], "features": o[i, C * K * K:].copy()} for i in range(self.n_agents))
 
     # ------------------------------------------------------------------ Gymnasium surface
     def seed(self, seed=None):  # rware/warehouse.py:962-964
@@ -241,8 +307,8 @@ class Warehouse:
         obs, reward, done = self._vec.step(torch.from_numpy(acts))
         rewards = [np.float64(r) for r in reward[0].cpu().numpy()]
         done = bool(done[0].item())
-        new_obs = self._obs_tuple(obs)
         self._pull()
+        new_obs = self._obs_tuple(obs)
         return new_obs, rewards, done, False, self._get_info()
 
     def _make_obs(self, agent):  # rware/warehouse.py:722-744 (FLATTENED)

@@ -144,8 +144,70 @@ def layouts(wh):
     np.savez_compressed(os.path.join(HERE, "layouts.npz"), **out)
 
 
+def _jsonable(o):
+    if isinstance(o, dict):
+        return {k: _jsonable(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return [_jsonable(v) for v in o]
+    if isinstance(o, np.ndarray):
+        return o.tolist()
+    if isinstance(o, np.generic):
+        return o.item()
+    return o
+
+
+def record_obs_types(wh):
+    """Non-default observation types of the reference (warehouse.py:352-427, 527-596, 676-742) on short trajectories."""
+    OT, IL = wh.ObservationType, wh.ImageLayer
+    cases = {
+        "image_default": dict(n=4, msg=0, r=1, ot=OT.IMAGE, extra={}),
+        "image_nd_subset": dict(n=3, msg=0, r=2, ot=OT.IMAGE, extra=dict(image_observation_directional=False,
+                                image_observation_layers=[IL.GOALS, IL.SHELVES, IL.ACCESSIBLE])),
+        "imagedict_r2": dict(n=5, msg=0, r=2, ot=OT.IMAGE_DICT, extra={}),
+        "dict_msg2": dict(n=3, msg=2, r=1, ot=OT.DICT, extra={}),
+        "dict_norm": dict(n=2, msg=0, r=1, ot=OT.DICT, extra=dict(normalised_coordinates=True)),
+    }
+    out = {}
+    for name, cs in cases.items():
+        kwargs = dict(shelf_columns=3, column_height=8, shelf_rows=1, n_agents=cs["n"], msg_bits=cs["msg"],
+                      sensor_range=cs["r"], request_queue_size=cs["n"], max_inactivity_steps=None, max_steps=50,
+                      reward_type=wh.RewardType.INDIVIDUAL, observation_type=cs["ot"], **cs["extra"])
+        env = wh.Warehouse(**kwargs)
+        rs = np.random.default_rng(len(name))
+        T = 80
+        acts = np.concatenate([rs.choice(5, size=(T, cs["n"], 1), p=[.1, .5, .15, .15, .1]),
+                               rs.integers(0, 2, size=(T, cs["n"], cs["msg"]))], axis=2).astype(np.int8)
+        snap = (lambda o: _jsonable(o)) if cs["ot"] == OT.DICT else (lambda o: o)  # DICT obs alias agent.message: copy now
+        obs, _ = env.reset(seed=77)
+        seq = [snap(obs)]
+        for t in range(T):
+            a = [list(map(int, r)) for r in acts[t]] if cs["msg"] else [int(r[0]) for r in acts[t]]
+            obs, rew, done, _, _ = env.step(a)
+            seq.append(snap(obs))
+            if done:
+                obs, _ = env.reset()
+                seq[-1] = snap(obs)  # the observation the caller continues from
+        kw_json = {k: (v.value if hasattr(v, "value") else ([x.value for x in v] if isinstance(v, list) else v))
+                   for k, v in kwargs.items()}
+        rec = dict(kwargs=kw_json, seed=77, actions=acts.tolist())
+        if cs["ot"] == OT.DICT:
+            rec["obs"] = _jsonable(seq)
+        elif cs["ot"] == OT.IMAGE:
+            rec["image"] = np.stack([np.stack(o) for o in seq]).astype(np.float32).tolist()
+        else:
+            rec["image"] = np.stack([np.stack([a["image"] for a in o]) for o in seq]).astype(np.float32).tolist()
+            rec["features"] = np.stack([np.stack([a["features"] for a in o]) for o in seq]).astype(np.float32).tolist()
+        out[name] = rec
+        print("obs-type fixture", name, len(seq), "observations")
+    with open(os.path.join(HERE, "obs_types.json"), "w") as f:
+        json.dump(out, f)
+
+
 def main():
     gym, wh = refenv.load_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "obs_types":
+        record_obs_types(wh)
+        return
     G, I, T = 0, 1, 2
     record(wh, "tiny2_indiv", kw(3, 8, 1, 2, 0, 1, 2, None, 500, I), 700, 0.3, 9, seed=0)
     record(wh, "tiny4_indiv", kw(3, 8, 1, 4, 0, 1, 4, None, 500, I), 1100, 0.3, 7, seed=1)
@@ -160,6 +222,7 @@ def main():
     record(wh, "tiny1_hard_r0", kw(3, 8, 1, 1, 0, 1, 0, None, 100, I), 250, 0.5, 0, seed=9)
     known_answers(gym)
     layouts(wh)
+    record_obs_types(wh)
 
 
 if __name__ == "__main__":

@@ -44,7 +44,9 @@ extern "C" {
 Sim *sim_create(const rw_config *cfg, int64_t num_envs) {
     Sim *s = new Sim();
     int cells = cfg->grid_h * cfg->grid_w;
-    s->highway.assign(cfg->highways, cfg->highways + cells);
+    s->highway.resize(cells);
+    for (int c = 0; c < cells; c++) s->highway[c] = cfg->highways[c] ? 1 : 0;
+    for (int g = 0; g < cfg->n_goals; g++) s->highway[cfg->goals_xy[2 * g + 1] * cfg->grid_w + cfg->goals_xy[2 * g]] |= 2;  // goal flag
     for (int c = 0; c < cells; c++)
         if (!cfg->highways[c]) s->home.push_back((uint16_t)c);
     s->home_id.assign(cells, 0);
@@ -132,8 +134,8 @@ static void sim_run_t(Sim *s, int mode, const int32_t *actions, float *obs, floa
                 RwLane l = lane_view(s, lane);
                 for (int a = 0; a < p.n; a++)
                     for (int part = 0; part < p.obs_parts; part++) {
-                        if (p.obs_parts == 2) rw_obs_agent<C, 2>(p, l, a, obs + (env * p.n + a) * p.L, part);
-                        else rw_obs_agent<C, 1>(p, l, a, obs + (env * p.n + a) * p.L, 0);
+                        if (p.obs_parts == 2) rw_obs_row<C, 2>(p, l, a, obs + (env * p.n + a) * p.L, part);
+                        else rw_obs_row<C, 1>(p, l, a, obs + (env * p.n + a) * p.L, 0);
                     }
             }
     }
