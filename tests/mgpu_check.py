@@ -20,7 +20,8 @@ def main():
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl", device_id=dev)
-    kw = rware_b200.env_kwargs("rware-tiny-4ag-v1")
+    env_id = os.environ.get("MGPU_ENV_ID", "rware-tiny-4ag-v1")
+    kw = rware_b200.env_kwargs(env_id)
     E_local = int(os.environ.get("MGPU_ENVS", "65536"))
     total = E_local * world
     a = ShardedVecWarehouse(total, auto_reset=True, device=dev, **kw)  # NCCL gather
@@ -28,7 +29,7 @@ def main():
     b.enable_fused_gather()
     a.reset(seed=3)
     b.reset(seed=3)
-    acts = [torch.empty((E_local, 4), dtype=torch.int32, device=dev) for _ in range(8)]
+    acts = [torch.empty((E_local, kw["n_agents"]), dtype=torch.int32, device=dev) for _ in range(8)]
     for i, t in enumerate(acts):
         a.local.backend.random_actions(t, 100 + rank, i)
     ok = True
@@ -59,8 +60,8 @@ def main():
     t_nccl = timed(lambda i: a.step(acts[i % 8], gather=True))
     t_fused = timed(lambda i: b.step(acts[i % 8], gather=True))
     if rank == 0:
-        obs_bytes = total * 4 * a.obs_len * 4
-        print(json.dumps({"world": world, "worlds_per_gpu": E_local, "fused_equals_nccl": bool(flag.item()),
+        obs_bytes = total * kw["n_agents"] * a.obs_len * 4
+        print(json.dumps({"env_id": env_id, "world": world, "worlds_per_gpu": E_local, "fused_equals_nccl": bool(flag.item()),
                           "ms_per_step": {"no_gather": t_none, "nccl_all_gather": t_nccl, "fused_push": t_fused},
                           "env_steps_per_s": {k: total / (v * 1e-3) for k, v in
                                               (("no_gather", t_none), ("nccl_all_gather", t_nccl), ("fused_push", t_fused))},
