@@ -1,311 +1,10 @@
-// rw_kernels.cu -- sm_100a kernels of the batched RWARE step path.
-//
-// rw_main_kernel<MODE>: ONE launch does the whole env.step for every world:
-//   warp = tile of 32 worlds (rw_common.h).  Per warp:
-//     1. lane 0 issues one TMA bulk copy (cp.async.bulk.shared::cluster.global + mbarrier complete_tx) that lands the
-//        tile's packed state (nw*128 B, contiguous in HBM) in shared memory; meanwhile all lanes zero the tile's
-//        occupancy grids in shared memory;
-//     2. lane e advances world e (rw_logic.cuh): grid build, decode, proposals, collision resolution, apply,
-//        deliveries/resample, counters, optional auto-reset -- all on shared memory, no HBM traffic;
-//     3. the updated tile goes back with one TMA bulk store (cp.async.bulk.global.shared::cta);
-//     4. the observation gather runs with one lane per (world, agent), assembling [chunk][n][L] float32 blocks
-//        in shared memory that leave through double-buffered TMA bulk stores (the obs block of consecutive
-//        worlds is contiguous in the caller's [E][n][L] tensor).
-//   Rewards/done are tiny and written directly (coalesced).  HBM-bound integer work: no tensor cores.
-// MODE: 0 = step, 1 = observation gather only (state read + obs write), 2 = reset (+ obs).
+// rw_kernels.cu -- cold-path kernels (state views, seeding, synthetic actions, L2 flush), kernel selection and the launch
+// wrappers of the batched RWARE step path.  The fused kernel itself is rw_main_kernel.cuh / rw_inst.cu.
 #include <cstdlib>
 
 #include "rw_launch.h"
 #include "rw_logic.cuh"
-#include "rw_coop.cuh"
 #include "../../include/rware_b200.h"
-
-// ---------------------------------------------------------------- PTX helpers (TMA bulk copies + mbarrier)
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(smem_dst)),
-                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void *gmem_dst, const void *smem_src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-
-// ---------------------------------------------------------------- the fused kernel
-__device__ __forceinline__ unsigned long long rw_gtime() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-#define RW_STAMP(k)                                                                                     \
-    do {                                                                                                \
-        if (p.dbg_clock && lane == 0) p.dbg_clock[((size_t)blockIdx.x * 32 + warp) * 8 + (k)] = rw_gtime(); \
-    } while (0)
-
-__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-
-// Two warps serve one tile.  The PRIMARY warp (even) runs the per-world logic, one lane per world.  The HELPER warp
-// (odd) zeroes the grids, then sleeps on a named barrier until the post-step state is in shared memory; after that
-// both warps run the observation gather on alternate chunks, each with its own staging buffer and its own TMA bulk
-// stores.  p.warps_per_cta counts TILES per CTA (blockDim = 64 * tiles).
-template <int MODE, class C>
-__global__ void __launch_bounds__(960, 1) rw_main_kernel(const __grid_constant__ RwParams p, const int32_t *__restrict__ actions,
-                                                       float *__restrict__ obs, float *__restrict__ reward,
-                                                       uint8_t *__restrict__ done, const uint8_t *__restrict__ mask) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tl = warp >> 1, role = warp & 1;  // tile slot in this CTA; 0 = primary, 1 = helper
-    const int tile = blockIdx.x * p.warps_per_cta + tl;
-    const bool active = tile < p.tiles;
-    uint8_t *wb = smem + p.sm_cta_bytes + (size_t)tl * p.sm_warp_bytes;
-    int32_t *tilew = reinterpret_cast<int32_t *>(wb + p.sm_tile);
-    uint8_t *grid = wb + p.sm_grid;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(wb + p.sm_bar);
-    const uint32_t tile_bytes = (uint32_t)p.nw * RW_TILE * 4u;
-    int32_t *gtile = p.state + (size_t)(active ? tile : 0) * p.nw * RW_TILE;
-    const int64_t env = (int64_t)tile * RW_TILE + lane;
-    const bool valid = active && env < p.E;
-    uint8_t *s_highway = smem;
-    uint16_t *s_home_id = reinterpret_cast<uint16_t *>(smem + ((p.cells + 1) & ~1));
-    RwLane l;
-    l.tile = tilew + lane;
-    l.g = grid + lane * p.grid_env_stride;
-    l.sc = reinterpret_cast<uint32_t *>(wb + p.sm_scratch) + lane;
-    l.sc_step = RW_TILE;
-    l.highway = s_highway;
-    l.home_id = s_home_id;
-
-    // Programmatic dependent launch: this grid may have been scheduled while the previous grid on the stream was still
-    // draining; nothing it wrote may be read before this point.  Dependents of this grid may start launching right away
-    // (they wait at the same instruction).  Both are no-ops for an ordinary launch.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    RW_STAMP(0);
-    // ---- 1. prologue.  Thread 0: the CTA-shared static tables (highway bytes + home ids) arrive through one TMA bulk
-    //         copy on a CTA-level mbarrier.  Primary lane 0: this tile's packed state through another TMA bulk copy on
-    //         the tile's mbarrier.  While they are in flight: helper zeroes the occupancy grids, primary issues its
-    //         action loads.
-    // the fully static specialisations carry only the one-lane-per-world step (select_kernel routes p.coop elsewhere)
-    const bool coop = !C::full_static && (MODE == RW_MODE_STEP) && p.coop;
-    uint64_t *cta_bar = reinterpret_cast<uint64_t *>(smem + p.sm_cta_bytes - 8);
-    if (threadIdx.x == 0) {
-        mbar_init(cta_bar, 1);
-        fence_mbar_init();
-        mbar_expect_tx(cta_bar, (uint32_t)p.sm_cta_tx);
-        bulk_g2s(smem, p.cta_tables, (uint32_t)p.sm_cta_tx, cta_bar);
-    }
-    RwActRegs<C> areg;
-    const bool pre = rw_can_prefetch_actions<C>(p);
-    if (role == 0) {
-        if (active && lane == 0) {
-            mbar_init(bar, 1);
-            fence_mbar_init();
-            mbar_expect_tx(bar, tile_bytes);
-            bulk_g2s(tilew, gtile, tile_bytes, bar);
-        }
-        if (MODE == RW_MODE_STEP && !coop && valid) {
-            if (pre) rw_prefetch_actions<C>(p, actions + env * p.n * p.A, areg);  // loads in flight, consumed below
-            else rw_load_actions<C>(p, l, actions + env * p.n * p.A);
-        }
-    } else if (active) {
-        int4 *g4 = reinterpret_cast<int4 *>(grid);
-        const int n16 = (p.grid_env_stride * RW_TILE) >> 4;
-        for (int i = lane; i < n16; i += 32) g4[i] = make_int4(0, 0, 0, 0);
-    }
-    __syncthreads();  // mbarrier inits and the zeroed grids are visible CTA-wide
-    if (!active) return;
-    mbar_wait(cta_bar, 0);  // static tables landed
-    if (role == 0 && MODE == RW_MODE_STEP && !coop && valid && pre) rw_commit_actions<C>(p, l, areg);
-    RW_STAMP(1);
-
-    // Observation staging of this warp: chunk of CH worlds starting at world c0 of the tile -> its slice of the caller's
-    // [E][n][L] tensor.  One lane per (world, agent, half row); the chunk leaves as one TMA bulk store.
-    const int CH = p.obs_chunk_envs;
-    const int64_t tile_env0 = (int64_t)tile * RW_TILE;
-    const bool fast = (tile_env0 + RW_TILE <= p.E) && p.obs_bulk && (RW_TILE % CH == 0);
-    float *buf = reinterpret_cast<float *>(wb + p.sm_obs + role * p.obs_buf_stride);
-    bool buf_busy = false;
-    auto emit_chunk = [&](int c0) {
-        const int n = p.n, L = p.L, P = p.obs_parts;
-        const int items = CH * n * P;
-        if (buf_busy) {  // this warp's previous bulk store must have drained the buffer
-            if (lane == 0) bulk_wait_read<0>();
-            __syncwarp();
-        }
-        for (int it = lane; it < items; it += 32) {
-            const int part = P == 2 ? (it & 1) : 0;
-            const int ea = P == 2 ? (it >> 1) : it;  // (world, agent) row inside the chunk
-            const int el = (int)rw_div((uint32_t)ea, p.divN);
-            const int e = c0 + el;
-            if (e < RW_TILE && tile_env0 + e < p.E) {
-                RwLane le;
-                le.tile = tilew + e;
-                le.g = grid + e * p.grid_env_stride;
-                le.sc = nullptr;
-                le.sc_step = 0;
-                le.highway = s_highway;
-                le.home_id = s_home_id;
-                if (P == 2) rw_obs_row<C, 2>(p, le, ea - el * n, buf + ea * L, part);
-                else rw_obs_row<C, 1>(p, le, ea - el * n, buf + ea * L, 0);
-            }
-        }
-        float *gdst = obs + (tile_env0 + c0) * n * L;
-        if (fast && p.obs_tma && p.n_peers > 0) {
-            // fused push all-gather: the same staged chunk goes to this rank's slot of every rank's gathered tensor
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-                const size_t off = (size_t)(p.gather_env0 + tile_env0 + c0) * n * L;
-                for (int d = 0; d < p.n_peers; d++) {
-                    const int dst = (p.my_rank + d) % p.n_peers;  // start with the local copy, then spread over the links
-                    bulk_s2g(p.peer_obs[dst] + off, buf, (uint32_t)p.obs_chunk_bytes);
-                }
-                bulk_commit();
-            }
-            buf_busy = true;
-        } else if (fast && p.obs_tma) {
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-                bulk_s2g(gdst, buf, (uint32_t)p.obs_chunk_bytes);
-                bulk_commit();
-            }
-            buf_busy = true;
-        } else if (fast) {  // 16-byte coalesced stores: 512 B per warp instruction
-            __syncwarp();
-            const int4 *src = reinterpret_cast<const int4 *>(buf);
-            int4 *dst = reinterpret_cast<int4 *>(gdst);
-            const int n16 = p.obs_chunk_bytes >> 4;
-#pragma unroll 4
-            for (int i = lane; i < n16; i += 32) __stcs(dst + i, src[i]);
-            __syncwarp();
-        } else {  // ragged tail / unaligned geometry: plain coalesced stores
-            __syncwarp();
-            int64_t envs_here = p.E - (tile_env0 + c0);
-            if (envs_here > CH) envs_here = CH;
-            if (envs_here > RW_TILE - c0) envs_here = RW_TILE - c0;
-            const int nf = (int)(envs_here > 0 ? envs_here : 0) * n * L;
-            for (int i = lane; i < nf; i += 32) gdst[i] = buf[i];
-            __syncwarp();
-        }
-    };
-
-    // ---- 2. the step
-    const int passes = 1 << p.gshift;
-    const bool interleave = coop && p.coop == 2 && passes >= 2 && CH <= RW_TILE / 2;  // measured slower: opt-in (RWARE_B200_COOP=2)
-    if (coop) {
-        // a group of 2^gshift lanes per world (rw_coop.cuh).  Each warp of the pair owns half of the tile's worlds and
-        // emits the observations of a chunk as soon as its worlds are stepped, so that the TMA stores of one pass drain
-        // while the next pass computes.
-        mbar_wait(bar, 0);
-        RW_STAMP(2);
-        RwCoopCtx cx;
-        cx.tilew = tilew; cx.grid = grid;
-        cx.tiebuf = reinterpret_cast<uint32_t *>(wb + p.sm_tie) + 32 * role;
-        cx.highway = s_highway; cx.home_id = s_home_id;
-        cx.tile_env0 = tile_env0;
-        cx.actions = actions + tile_env0 * p.n * p.A;
-        cx.reward = reward + tile_env0 * p.n;
-        cx.done = done + tile_env0;
-        if (interleave) {
-            const int half = passes >> 1, epp = RW_TILE >> p.gshift;
-            int ready = role * (RW_TILE / 2), emitted = ready;
-            for (int pass = role * half; pass < (role + 1) * half; pass++) {
-                rw_step_coop_pass<C>(p, cx, pass, p.gshift);
-                ready += epp;
-                if (obs != nullptr)
-                    for (; ready - emitted >= CH; emitted += CH) emit_chunk(emitted);
-            }
-        } else {
-            for (int pass = role; pass < passes; pass += 2) rw_step_coop_pass<C>(p, cx, pass, p.gshift);
-        }
-        RW_STAMP(3);
-        pair_barrier(1 + tl);  // every world of the tile is in its post-step state
-        RW_STAMP(4);
-    } else if (role == 0) {
-        // primary: lane e advances world e
-        mbar_wait(bar, 0);
-        RW_STAMP(2);
-        if (valid) {
-            if (MODE == RW_MODE_RESET) {
-                if (mask == nullptr || mask[env]) rw_reset_lane<C>(p, l, env);
-            }
-            rw_build_grid<C>(p, l);
-            if (MODE == RW_MODE_STEP) {
-                bool d = rw_step_lane<C>(p, l, reward + env * p.n, env);
-                done[env] = d ? 1 : 0;
-                if (d && p.auto_reset) {
-                    rw_reset_lane<C>(p, l, env);
-                    uint32_t *gz = reinterpret_cast<uint32_t *>(l.g);
-                    for (int i = 0; i < (p.grid_env_stride >> 2); i++) gz[i] = 0;
-                    rw_build_grid<C>(p, l);
-                }
-            }
-        }
-        __syncwarp();
-        RW_STAMP(3);
-    }
-    // ---- 3. updated tile shared memory -> HBM
-    if (role == 0 && MODE != RW_MODE_OBS) {
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-            bulk_s2g(gtile, tilew, tile_bytes);
-            bulk_commit();
-        }
-    }
-    if (obs != nullptr && !interleave) {
-        if (!coop) {
-            pair_barrier(1 + tl);  // post-step tile + grids are visible to the helper
-            RW_STAMP(4);
-        }
-        // ---- 4. observation gather after the fact: this warp takes every second chunk
-        for (int c0 = role * CH; c0 < RW_TILE; c0 += 2 * CH) emit_chunk(c0);
-        if (MODE == RW_MODE_STEP && p.n_peers > 1 && role == 1) {
-            // rewards / done of this tile -> every peer's gathered tensors (the primary wrote the local copy)
-            const int n = p.n;
-            const size_t r0 = (size_t)(p.gather_env0 + tile_env0) * n, d0 = (size_t)(p.gather_env0 + tile_env0);
-            const int live = (int)((p.E - tile_env0) < RW_TILE ? (p.E - tile_env0) : RW_TILE);
-            for (int d = 1; d < p.n_peers; d++) {
-                const int dst = (p.my_rank + d) % p.n_peers;
-                for (int i = lane; i < live * n; i += 32) p.peer_rew[dst][r0 + i] = p.peer_rew[p.my_rank][r0 + i];
-                if (lane < live) p.peer_done[dst][d0 + lane] = p.peer_done[p.my_rank][d0 + lane];
-            }
-        }
-    }
-    RW_STAMP(5);
-    if (lane == 0) bulk_wait_read<0>();  // shared memory must stay valid until the TMA has read it
-    __syncwarp();
-    RW_STAMP(6);
-}
 
 // ---------------------------------------------------------------- cold-path kernels (state views, seeding, synthetic actions)
 __global__ void rw_get_state_kernel(const RwParams p, const rw_state_view v) {
@@ -418,34 +117,21 @@ cudaError_t rw_launch_flush_l2(void *buf, size_t bytes, int value, int smem_byte
 }
 
 // ---------------------------------------------------------------- launch wrappers
-// Static specialisations: the four registered warehouse sizes (rware/__init__.py:7-12 with column_height 8) at
-// sensor range 1 and 2 without message bits; every other geometry runs the RwDynamic instantiation.
-#include "rw_static_configs.h"
-
+// Kernel selection.  The instantiations live in rw_inst.cu, compiled as several translation units (RW_INST_GROUP);
+// group order = priority: fully static BASELINE configurations, then the registered geometries, then RwDynamic.
 typedef void (*rw_kernel_fn)(const RwParams, const int32_t *, float *, float *, uint8_t *, const uint8_t *);
-
-template <class C>
-static rw_kernel_fn kernel_for_mode(RwMode mode) {
-    switch (mode) {
-        case RW_MODE_STEP: return rw_main_kernel<RW_MODE_STEP, C>;
-        case RW_MODE_OBS: return rw_main_kernel<RW_MODE_OBS, C>;
-        default: return rw_main_kernel<RW_MODE_RESET, C>;
-    }
-}
+#define RW_DECLARE_GROUP(g) rw_kernel_fn rw_select_group_##g(RwMode mode, const RwParams &p, bool force_dynamic);
+RW_DECLARE_GROUP(0) RW_DECLARE_GROUP(1) RW_DECLARE_GROUP(2) RW_DECLARE_GROUP(3) RW_DECLARE_GROUP(4) RW_DECLARE_GROUP(5) RW_DECLARE_GROUP(6)
 
 static rw_kernel_fn select_kernel(RwMode mode, const RwParams &p, bool force_dynamic) {
-    if (!force_dynamic && p.msg_bits == 0) {
-#define X(H_, W_, S_, R_, N_, RQ_) \
-    if (!p.coop && p.H == H_ && p.W == W_ && p.S == S_ && p.r == R_ && p.n == N_ && p.R == RQ_) \
-        return kernel_for_mode<RwStatic<H_, W_, S_, R_, 0, N_, RQ_>>(mode);
-        RW_FULL_STATIC_CONFIGS(X)
-#undef X
-#define X(H_, W_, S_, R_) \
-    if (p.H == H_ && p.W == W_ && p.S == S_ && p.r == R_) return kernel_for_mode<RwStatic<H_, W_, S_, R_, 0>>(mode);
-        RW_STATIC_CONFIGS(X)
-#undef X
+    rw_kernel_fn (*groups[])(RwMode, const RwParams &, bool) = {rw_select_group_0, rw_select_group_1, rw_select_group_2,
+                                                               rw_select_group_3, rw_select_group_4, rw_select_group_5,
+                                                               rw_select_group_6};
+    for (auto g : groups) {
+        rw_kernel_fn f = g(mode, p, force_dynamic);
+        if (f) return f;
     }
-    return kernel_for_mode<RwDynamic>(mode);
+    return nullptr;  // unreachable: group 6 ends with RwDynamic
 }
 
 static bool g_force_dynamic = false;
