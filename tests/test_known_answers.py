@@ -89,3 +89,24 @@ def test_full_size_batch_properties_and_sampled_oracle_parity():
     sx = torch.gather(st["shelf_x"], 1, (carry - 1).clamp(min=0))
     sy = torch.gather(st["shelf_y"], 1, (carry - 1).clamp(min=0))
     assert bool(((sx == st["agent_x"]) | ~has).all()) and bool(((sy == st["agent_y"]) | ~has).all())
+
+
+@pytest.mark.gpu
+def test_host_buffer_entry_points_match_the_device_ones():
+    """rw_reset_host / rw_step_host (pinned host buffers, the end-to-end path of bench.py) against rw_reset / rw_step."""
+    E = 1000
+    a = rware_b200.make_vec("rware-small-4ag-v1", E)
+    b = rware_b200.make_vec("rware-small-4ag-v1", E)
+    seeds = np.arange(E, dtype=np.uint64) + 9
+    obs_d = a.reset(seed=seeds).cpu()
+    h_obs = torch.empty((E, 4, a.obs_len), dtype=torch.float32).pin_memory()
+    h_rew = torch.empty((E, 4), dtype=torch.float32).pin_memory()
+    h_done = torch.empty((E,), dtype=torch.uint8).pin_memory()
+    b.backend.reset_host(seeds, h_obs)
+    assert torch.equal(h_obs, obs_d)
+    g = torch.Generator().manual_seed(1)
+    for _ in range(25):
+        acts = torch.randint(0, 5, (E, 4), generator=g, dtype=torch.int32).pin_memory()
+        obs_d, rew_d, done_d = a.step(acts.cuda())
+        b.backend.step_host(acts, h_obs, h_rew, h_done)
+        assert torch.equal(h_obs, obs_d.cpu()) and torch.equal(h_rew, rew_d.cpu()) and torch.equal(h_done, done_d.cpu())
