@@ -1,0 +1,86 @@
+"""C-ABI / VecWarehouse semantics that the trajectory replays do not isolate: masked resets, state round trips,
+stepping past `done` without auto-reset (the reference keeps stepping and keeps reporting done), determinism of seeds."""
+import numpy as np
+import pytest
+import torch
+
+import oracle_py
+import rware_b200
+from conftest import backend_factory, backend_params
+
+KW = dict(shelf_columns=3, column_height=8, shelf_rows=1, n_agents=3, request_queue_size=3, max_steps=12)
+
+
+def _vec(backend, E, **extra):
+    return rware_b200.VecWarehouse(E, _backend_factory=backend_factory(backend), **{**KW, **extra})
+
+
+@pytest.mark.parametrize("backend", backend_params())
+def test_masked_reset_only_touches_selected_worlds(backend):
+    E = 70
+    vec = _vec(backend, E)
+    vec.reset(seed=1)
+    rs = np.random.default_rng(0)
+    for _ in range(5):
+        vec.step(torch.from_numpy(rs.integers(0, 5, size=(E, 3)).astype(np.int32)))
+    before = {k: v.clone() for k, v in vec.get_state().items()}
+    mask = torch.zeros(E, dtype=torch.uint8)
+    mask[[0, 31, 32, 69]] = 1
+    obs = vec.reset(mask=mask).clone()
+    after = vec.get_state()
+    keep = ~mask.bool()
+    for k in before:
+        assert torch.equal(before[k].cpu()[keep], after[k].cpu()[keep]), k
+    assert bool((after["cur_steps"].cpu()[mask.bool()] == 0).all()) and bool((before["cur_steps"].cpu()[keep] == 5).all())
+    assert torch.equal(obs, vec.observations())  # the reset returns every world's current observation
+    # the reset worlds continued their own generator streams: compare with the oracle
+    for e in (0, 69):
+        o = oracle_py.OracleEnv(vec.highways, vec.goals, 3, 0, 1, 3, None, 12, 1)
+        o.reset(1 + e)
+        o.set_state(rng=before["rng"][e].cpu().numpy().astype(np.int64).astype(np.uint32))
+        assert np.array_equal(o.reset(), obs[e].cpu().numpy())
+
+
+@pytest.mark.parametrize("backend", backend_params())
+def test_state_round_trip_and_checkpoint_resume(backend):
+    E = 40
+    a, b = _vec(backend, E), _vec(backend, E)
+    a.reset(seed=5)
+    rs = np.random.default_rng(3)
+    acts = [torch.from_numpy(rs.integers(0, 5, size=(E, 3)).astype(np.int32)) for _ in range(20)]
+    for t in range(8):
+        a.step(acts[t])
+    b.set_state(**{k: v.cpu() for k, v in a.get_state().items()})  # "checkpoint" -> fresh handle
+    sa, sb = a.get_state(), b.get_state()
+    assert all(torch.equal(sa[k].cpu(), sb[k].cpu()) for k in sa)
+    for t in range(8, 20):
+        oa, ra, da = a.step(acts[t])
+        ob, rb, db = b.step(acts[t])
+        assert torch.equal(oa.cpu(), ob.cpu()) and torch.equal(ra.cpu(), rb.cpu()) and torch.equal(da.cpu(), db.cpu())
+
+
+@pytest.mark.parametrize("backend", backend_params())
+def test_stepping_past_done_without_auto_reset(backend):
+    """warehouse.py:929-941: counters keep counting, done stays True, nothing resets."""
+    vec = _vec(backend, 4)
+    vec.reset(seed=2)
+    o = oracle_py.OracleEnv(vec.highways, vec.goals, 3, 0, 1, 3, None, 12, 1)
+    o.reset(2)
+    rs = np.random.default_rng(8)
+    for t in range(20):
+        a = rs.integers(0, 5, size=3).astype(np.int32)
+        obs, rew, done = vec.step(torch.from_numpy(np.broadcast_to(a, (4, 3)).copy()))
+        oo, orw, od = o.step(a)
+        assert bool(done[0]) == od == (t >= 11)
+        assert np.array_equal(obs[0].cpu().numpy(), oo)
+    assert int(vec.get_state()["cur_steps"][0]) == 20
+
+
+@pytest.mark.parametrize("backend", backend_params())
+def test_seed_array_and_scalar_forms(backend):
+    a, b = _vec(backend, 6), _vec(backend, 6)
+    oa = a.reset(seed=10).clone()
+    ob = b.reset(seed=np.arange(10, 16, dtype=np.uint64)).clone()
+    assert torch.equal(oa, ob)
+    oc = b.reset(seed=np.full(6, 10, np.uint64))
+    assert all(torch.equal(oc[0], oc[i]) for i in range(6)) and torch.equal(oc[0], oa[0])
