@@ -1,5 +1,9 @@
 cd $GRAFT_REPO_ROOT
-timeout 600 python -m pytest tests/test_known_answers.py -m gpu -q 2>&1 | tail -2
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 tests/mgpu_check.py 2>&1 | tail -1
-MGPU_ENVS=1000 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29542 tests/mgpu_check.py 2>&1 | tail -1
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29543 bench.py --gpus 2 --steps 50 --warmup 5 --no-cpu-baseline --e2e-steps 2 --gather fused 2>&1 | tail -1 | cut -c1-420
+P='import sys,json; d=json.loads(sys.stdin.read()); print(sys.argv[1], d["value"], d["ms_per_step"], d["roofline"]["frac"], "obs_us", d["obs_gather"]["kernel_us"], d["obs_gather"]["frac_of_hbm_peak"])'
+for parts in 2 4; do for wl in tiny-4ag tiny-2ag small-4ag medium-8ag-hard; do RWARE_B200_OBS_PARTS=$parts python bench.py --workload $wl --steps 200 --warmup 20 --no-cpu-baseline --e2e-steps 2 2>&1 | tail -1 | python -c "$P" parts$parts-$wl; done; done
+RWARE_B200_OBS_PARTS=4 timeout 900 python -m pytest tests/test_hostsim_golden.py tests/test_known_answers.py -m gpu -q 2>&1 | tail -1
+RWARE_B200_OBS_PARTS=4 python profiles/phase_timeline.py 2>&1 | python -c "
+import sys, json
+d = json.loads(sys.stdin.read())
+for m in d: print(m, {k[5]+k[9:12]: (round(v,1) if isinstance(v,float) else v) for k,v in d[m]['primary'].items() if 'mean' in k}, 'span', round(d[m]['kernel_span_us'],1))
+"

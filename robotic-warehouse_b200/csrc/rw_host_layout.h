@@ -114,7 +114,8 @@ static inline void rw_fill_params(RwParams &p, const rw_config &c, int64_t num_e
         p.obs_parts = p.K >= 2 ? 2 : 1;
         {
             const char *ev = getenv("RWARE_B200_OBS_PARTS");
-            if (ev && (atoi(ev) == 1 || atoi(ev) == 2)) p.obs_parts = atoi(ev);
+            if (ev && (atoi(ev) == 1 || atoi(ev) == 2 || atoi(ev) == 4)) p.obs_parts = atoi(ev);
+            if (p.obs_parts == 4 && p.K < 4) p.obs_parts = 2;
         }
         int best = 0;
         for (int C = 1; C <= RW_TILE; C *= 2) {
@@ -129,7 +130,9 @@ static inline void rw_fill_params(RwParams &p, const rw_config &c, int64_t num_e
         }
         p.obs_chunk_envs = best;
         p.obs_chunk_bytes = best * p.obs_env_bytes;
-        p.obs_nbuf = 2;  // one staging buffer per warp of the pair
+        // staging buffers per tile: one per warp of the pair; with quarter-row slices (obs_parts == 4) the chunks are half
+        // as large, so each warp double-buffers (its next chunk is assembled while the previous TMA store drains)
+        p.obs_nbuf = (p.obs_parts == 4 && RW_TILE / best >= 4) ? 4 : 2;
         p.obs_buf_stride = rw_round_up(p.obs_chunk_bytes, 128);
     }
     int off = 0;

@@ -822,19 +822,31 @@ RW_HD void rw_obs_agent(const RwParams &p, const RwLane &l, int i, float *out, i
         out[6] = d == 3 ? 1.0f : 0.0f;
         out[7] = (l.highway[y * W + x] & 1) ? 1.0f : 0.0f;  // ref:647
     }
-    // Slice s covers window cells [s*Kp, min(K, (s+1)*Kp)).  `part` varies across lanes, so everything that depends on
-    // it is a select between the compile-time values of slice 0 and slice 1 (no divergence, no integer division).
+    // Slice s covers window cells [s*Kp, min(K, (s+1)*Kp)).  `part` varies across lanes: with two slices everything
+    // that depends on it is a select between the compile-time values of slice 0 and slice 1 (no divergence, no
+    // integer division); with more slices the cell index is computed (division by the compile-time window width).
     const int Kp = (K + nparts - 1) / nparts;
     const bool hi = part != 0;
     const uint8_t *gc = l.g + (y * W + x);
-    float *ob = out + 8 + (hi ? Kp * cellF : 0);
+    float *ob = out + 8 + (nparts <= 2 ? (hi ? Kp * cellF : 0) : part * Kp * cellF);
 #pragma unroll
     for (int k = 0; k < Kp; k++) {                        // ref:628-629 window cells, rows outer, columns inner
-        const int ca = k, cb = Kp + k;                    // cell index in slice 0 / slice 1 (compile time when unrolled)
-        const int dya = ca / win - r, dxa = ca % win - r;
-        const int dyb = (cb < K ? cb : K - 1) / win - r, dxb = (cb < K ? cb : K - 1) % win - r;
-        const int dy = hi ? dyb : dya, dx = hi ? dxb : dxa;
-        const bool live = hi ? (cb < K) : (ca < K);
+        int dy, dx;
+        bool live;
+        if (nparts <= 2) {
+            const int ca = k, cb = Kp + k;                // cell index in slice 0 / slice 1 (compile time when unrolled)
+            const int dya = ca / win - r, dxa = ca % win - r;
+            const int dyb = (cb < K ? cb : K - 1) / win - r, dxb = (cb < K ? cb : K - 1) % win - r;
+            dy = hi ? dyb : dya;
+            dx = hi ? dxb : dxa;
+            live = hi ? (cb < K) : (ca < K);
+        } else {
+            const int c = part * Kp + k;
+            const int cc = c < K ? c : K - 1;
+            dy = cc / win - r;
+            dx = cc - (cc / win) * win - r;
+            live = c < K;
+        }
         if (live) {
             uint32_t gb = 0;                              // zero padding outside the map (ref:606-626)
             if ((unsigned)(y + dy) < (unsigned)H && (unsigned)(x + dx) < (unsigned)W) gb = gc[dy * W + dx];

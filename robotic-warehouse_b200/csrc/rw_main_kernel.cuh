@@ -154,18 +154,24 @@ __global__ void __launch_bounds__(960, 1) rw_main_kernel(const __grid_constant__
     const int CH = p.obs_chunk_envs;
     const int64_t tile_env0 = (int64_t)tile * RW_TILE;
     const bool fast = (tile_env0 + RW_TILE <= p.E) && p.obs_bulk && (RW_TILE % CH == 0);
-    float *buf = reinterpret_cast<float *>(wb + p.sm_obs + role * p.obs_buf_stride);
-    bool buf_busy = false;
+    const int nbw = p.obs_nbuf >> 1;  // staging buffers of this warp (1, or 2 = double buffering)
+    float *buf0 = reinterpret_cast<float *>(wb + p.sm_obs + role * nbw * p.obs_buf_stride);
+    int stores_in_flight = 0, chunk_no = 0;
     auto emit_chunk = [&](int c0) {
         const int n = p.n, L = p.L, P = p.obs_parts;
         const int items = CH * n * P;
-        if (buf_busy) {  // this warp's previous bulk store must have drained the buffer
-            if (lane == 0) bulk_wait_read<0>();
+        float *buf = buf0 + (nbw == 2 ? (chunk_no & 1) * (p.obs_buf_stride >> 2) : 0);
+        chunk_no++;
+        if (stores_in_flight >= nbw) {  // the bulk store that last read this buffer must have drained it
+            if (lane == 0) {
+                if (nbw == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+            }
             __syncwarp();
+            stores_in_flight = nbw - 1;
         }
         for (int it = lane; it < items; it += 32) {
-            const int part = P == 2 ? (it & 1) : 0;
-            const int ea = P == 2 ? (it >> 1) : it;  // (world, agent) row inside the chunk
+            const int part = P == 4 ? (it & 3) : P == 2 ? (it & 1) : 0;
+            const int ea = P == 4 ? (it >> 2) : P == 2 ? (it >> 1) : it;  // (world, agent) row inside the chunk
             const int el = (int)rw_div((uint32_t)ea, p.divN);
             const int e = c0 + el;
             if (e < RW_TILE && tile_env0 + e < p.E) {
@@ -176,7 +182,8 @@ __global__ void __launch_bounds__(960, 1) rw_main_kernel(const __grid_constant__
                 le.sc_step = 0;
                 le.highway = s_highway;
                 le.home_id = s_home_id;
-                if (P == 2) rw_obs_row<C, 2>(p, le, ea - el * n, buf + ea * L, part);
+                if (P == 4) rw_obs_row<C, 4>(p, le, ea - el * n, buf + ea * L, part);
+                else if (P == 2) rw_obs_row<C, 2>(p, le, ea - el * n, buf + ea * L, part);
                 else rw_obs_row<C, 1>(p, le, ea - el * n, buf + ea * L, 0);
             }
         }
@@ -195,7 +202,7 @@ __global__ void __launch_bounds__(960, 1) rw_main_kernel(const __grid_constant__
                 for (int d = 0; d < ndst; d++) bulk_s2g(dst_ptr(d), buf, (uint32_t)p.obs_chunk_bytes);
                 bulk_commit();
             }
-            buf_busy = true;
+            stores_in_flight++;
         } else if (fast) {  // 16-byte coalesced stores: 512 B per warp instruction
             __syncwarp();
             const int4 *src = reinterpret_cast<const int4 *>(buf);

@@ -134,7 +134,8 @@ static void sim_run_t(Sim *s, int mode, const int32_t *actions, float *obs, floa
                 RwLane l = lane_view(s, lane);
                 for (int a = 0; a < p.n; a++)
                     for (int part = 0; part < p.obs_parts; part++) {
-                        if (p.obs_parts == 2) rw_obs_row<C, 2>(p, l, a, obs + (env * p.n + a) * p.L, part);
+                        if (p.obs_parts == 4) rw_obs_row<C, 4>(p, l, a, obs + (env * p.n + a) * p.L, part);
+                        else if (p.obs_parts == 2) rw_obs_row<C, 2>(p, l, a, obs + (env * p.n + a) * p.L, part);
                         else rw_obs_row<C, 1>(p, l, a, obs + (env * p.n + a) * p.L, 0);
                     }
             }
