@@ -121,6 +121,24 @@ int rw_step(rw_handle *h, const int32_t *actions_dev, float *obs_dev, float *rew
 /* tuple(_make_obs(agent) for agent in agents) (warehouse.py:722-744 -> 598-674): the observation gather alone. */
 int rw_obs(rw_handle *h, float *obs_dev, void *stream);
 
+/* Warehouse.get_global_image(image_layers, recompute=True, pad_to_shape) (warehouse.py:966-1040) for every world:
+ * out_dev [E][C'][H'][W'] float32, where (C', H', W') = pad_to_shape, or (n_layers, H, W) when pad_to_shape is NULL; padding is
+ * the reference's (pad_before = diff / 2, constant 0; 1021-1039).  layers (host pointer): ImageLayer values 0 SHELVES 1 REQUESTS
+ * 2 AGENTS 3 AGENT_DIRECTION 4 AGENT_LOAD 5 GOALS 6 ACCESSIBLE.  Layers 3 and 4 are written as the reference writes them,
+ * transposed (`layer[ag.x, ag.y]`, 1004, 1009); where the reference raises IndexError for it (an agent with x >= H or y >= W)
+ * the entry is skipped and the world is counted in rw_error_count.  rw_global_image_shape resolves (C', H', W'). */
+int rw_global_image_shape(const rw_handle *h, int32_t n_layers, const int32_t *pad_to_shape /*[3] or NULL*/, int32_t *shape_out /*[3]*/);
+int rw_global_image(rw_handle *h, const int32_t *layers, int32_t n_layers, const int32_t *pad_to_shape /*[3] or NULL*/,
+                    float *out_dev, void *stream);
+
+/* Warehouse.render() with render_mode="rgb_array" (warehouse.py:948-956 -> rendering.py:121-139) for the worlds
+ * [first_env, first_env + n_envs): out_dev [n_envs][height][width][3] uint8 with (height, width) = (2 + 31 H, 1 + 31 W) as the
+ * reference Viewer sizes its window (rendering.py:93-98).  Geometry and colours follow rendering.py:140-333 (grid, goal cells,
+ * shelves, requested shelves, agents, loaded agents, heading line); the "G" glyph on goals is not drawn.  Pixel coverage is
+ * stated in csrc/rw_views.cuh; no OpenGL frame could be recorded where this was written, so this view is not pixel-pinned. */
+int rw_render_shape(const rw_handle *h, int32_t *height, int32_t *width);
+int rw_render_rgb(rw_handle *h, int64_t first_env, int64_t n_envs, uint8_t *out_dev, void *stream);
+
 /* When on, a world whose step returned done is reset inside the same kernel (as `reset()` without a seed would,
  * continuing its generator) and the returned observation is the first one of the new episode.  Default off
  * (the reference never auto-resets). */
@@ -132,7 +150,8 @@ int rw_get_state(rw_handle *h, const rw_state_view *dev, void *stream);
 int rw_set_state(rw_handle *h, const rw_state_view *dev, void *stream);
 
 /* Count of invalid action values seen so far (the reference raises ValueError from Action(a), warehouse.py:811-814;
- * the batched kernel treats them as NOOP and counts them).  Synchronises `stream`. */
+ * the batched kernel treats them as NOOP and counts them), plus the worlds whose transposed global-image layers would have
+ * raised IndexError (see rw_global_image).  Synchronises `stream`. */
 int rw_error_count(rw_handle *h, int64_t *out, void *stream);
 
 /* End-to-end convenience with HOST buffers (pinned memory recommended, see rw_host_alloc): copies the actions

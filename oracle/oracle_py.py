@@ -53,6 +53,8 @@ def lib():
         L.orc_get_grid.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.orc_obs_image.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_obs_image.restype = ctypes.c_int
+        L.orc_global_image.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        L.orc_global_image.restype = ctypes.c_int
         L.orc_last_step_stats.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 3
         L.orc_py_tuple_hash.restype = ctypes.c_uint64
         L.orc_py_tuple_hash.argtypes = [ctypes.c_int64, ctypes.c_int64]
@@ -149,6 +151,21 @@ class OracleEnv:
         if rc:
             raise ValueError(f"orc_obs_image failed: {rc}")
         return (out, feat) if with_features else out
+
+    def global_image(self, layers=(0, 5), pad_to_shape=None):
+        """get_global_image (warehouse.py:966-1040): [C, H, W] float32, zero-padded to pad_to_shape as the reference does."""
+        lay = np.ascontiguousarray(layers, np.int32)
+        out = np.zeros((len(lay), self.H, self.W), np.float32)
+        rc = lib().orc_global_image(self._h, _p(lay), len(lay), _p(out))
+        if rc == -1:
+            raise IndexError("AGENT_DIRECTION / AGENT_LOAD layer: transposed index out of bounds (as in the reference)")
+        if rc:
+            raise ValueError(f"Unknown image layer type (orc_global_image: {rc})")
+        if pad_to_shape is not None:  # 1021-1039
+            diff = [p - g for p, g in zip(pad_to_shape, out.shape)]
+            assert all(d >= 0 for d in diff)
+            out = np.pad(out, tuple((d // 2, d // 2 if d % 2 == 0 else d // 2 + 1) for d in diff))
+        return out
 
     def get_state(self):
         n, S, R, mb = self.n, self.S, self.R, self.msg_bits

@@ -48,7 +48,7 @@ def run_config(gym, wh, name, kwargs, steps, p_forward, teleport_every, seed):
     for t in range(steps):
         if not ok:
             break
-        if teleport_every and t % teleport_every == teleport_every - 1:
+        if teleport_every and kwargs["request_queue_size"] and t % teleport_every == teleport_every - 1:
             st = refenv.ref_state(env)
             a = int(rs.integers(n))
             gx, gy = env.goals[int(rs.integers(len(env.goals)))]
@@ -111,10 +111,43 @@ def run_config(gym, wh, name, kwargs, steps, p_forward, teleport_every, seed):
     return ok, stats
 
 
+def random_config(rs, RT):
+    """Random custom ASCII maps / parametric layouts with random agent count, sensor range, message bits, queue size,
+    reward type and limits (same distribution as tests/test_fuzz_configs.py, which checks the device code against the oracle)."""
+    if rs.random() < 0.5:
+        H, W = int(rs.integers(3, 9)), int(rs.integers(3, 11))
+        while True:
+            cells = rs.choice(list("x.."), size=(H, W))
+            for _ in range(int(rs.integers(1, 4))):
+                cells[int(rs.integers(H)), int(rs.integers(W))] = "g"
+            if (cells == "x").sum() >= 2:
+                break
+        kw = dict(layout="\n".join("".join(r) for r in cells), shelf_columns=1, column_height=1, shelf_rows=1)
+        n_shelves, n_cells = int((cells == "x").sum()), H * W
+    else:
+        cols, rows, height = int(rs.choice([1, 3, 5])), int(rs.integers(1, 3)), int(rs.integers(1, 5))
+        kw = dict(shelf_columns=cols, shelf_rows=rows, column_height=height)
+        _, _, hw, _ = oracle_py.layout_from_params(cols, rows, height)
+        if int((hw == 0).sum()) < 2:
+            cols = 3
+            kw["shelf_columns"] = 3
+            _, _, hw, _ = oracle_py.layout_from_params(cols, rows, height)
+        n_shelves, n_cells = int((hw == 0).sum()), hw.size
+    n = int(rs.integers(1, min(n_cells, 20) + 1))
+    rq = int(rs.integers(0, min(n_shelves - 1, 6) + 1))  # rq == n_shelves makes the reference raise on a delivery
+    kw.update(n_agents=n, msg_bits=int(rs.choice([0, 0, 1, 3])), sensor_range=int(rs.integers(1, 4)), request_queue_size=rq,
+              reward_type=RT(int(rs.integers(0, 3))), max_steps=int(rs.choice([0, 15, 40])) or None,
+              max_inactivity_steps=int(rs.choice([0, 0, 10])) or None, normalised_coordinates=bool(rs.random() < 0.3))
+    return kw, float(rs.choice([0.3, 0.6, 0.85]))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=4000)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--fuzz", type=int, default=0, help="additionally run this many random configurations")
+    ap.add_argument("--fuzz-steps", type=int, default=300)
+    ap.add_argument("--fuzz-seed", type=int, default=0)
     args = ap.parse_args()
     gym, wh = refenv.load_reference()
     RT = wh.RewardType
@@ -143,6 +176,17 @@ def main():
         ok, stats = run_config(gym, wh, name, kwargs, steps, pf, tele, seed=hash(name) % 1000)
         print(f"{name:28s} steps={steps:6d} {'OK ' if ok else 'FAIL'} {stats}")
         all_ok &= ok
+    rs = np.random.default_rng(args.fuzz_seed)
+    n_fuzz_ok = 0
+    for i in range(args.fuzz):
+        kwargs, pf = random_config(rs, RT)
+        ok, stats = run_config(gym, wh, f"fuzz{i}", kwargs, args.fuzz_steps, pf, int(rs.choice([0, 3, 6])), seed=int(rs.integers(1 << 20)))
+        n_fuzz_ok += ok
+        if not ok:
+            print(f"fuzz{i} FAIL {kwargs}")
+        all_ok &= ok
+    if args.fuzz:
+        print(f"fuzz: {n_fuzz_ok}/{args.fuzz} random configurations x {args.fuzz_steps} steps OK (seed {args.fuzz_seed})")
     print(f"total {time.time() - t0:.1f}s -> {'ALL OK' if all_ok else 'MISMATCH'}")
     sys.exit(0 if all_ok else 1)
 

@@ -223,6 +223,49 @@ int orc_obs_image(const orc_env *e, const int32_t *layers, int n_layers, int dir
     return 0;
 }
 
+/* ---------------------------------------------------------------- global image (warehouse.py:966-1040), before padding */
+int orc_global_image(const orc_env *e, const int32_t *layers, int n_layers, float *out) {
+    const orc_config *c = &e->cfg;
+    const int H = c->H, W = c->W, n = c->n_agents;
+    memset(out, 0, sizeof(float) * (size_t)n_layers * H * W);
+    for (int li = 0; li < n_layers; li++) {
+        float *L = out + (size_t)li * H * W;
+        switch (layers[li]) {
+            case 0: /* SHELVES 988-991: grid[_LAYER_SHELFS] > 0 */
+                for (int k = 0; k < H * W; k++) L[k] = e->grid[H * W + k] > 0 ? 1.0f : 0.0f;
+                break;
+            case 1: /* REQUESTS 992-995 */
+                for (int q = 0; q < c->request_queue_size; q++) { int s = e->queue[q] - 1; L[e->sy[s] * W + e->sx[s]] = 1.0f; }
+                break;
+            case 2: /* AGENTS 996-999 */
+                for (int k = 0; k < H * W; k++) L[k] = e->grid[k] > 0 ? 1.0f : 0.0f;
+                break;
+            case 3: /* AGENT_DIRECTION 1000-1004: layer[ag.x, ag.y] (sic) */
+                for (int a = 0; a < n; a++) {
+                    if (e->ax[a] >= H || e->ay[a] >= W) return -1;
+                    L[e->ax[a] * W + e->ay[a]] = (float)(e->adir[a] + 1);
+                }
+                break;
+            case 4: /* AGENT_LOAD 1005-1009: layer[ag.x, ag.y] (sic) */
+                for (int a = 0; a < n; a++)
+                    if (e->acarry[a]) {
+                        if (e->ax[a] >= H || e->ay[a] >= W) return -1;
+                        L[e->ax[a] * W + e->ay[a]] = 1.0f;
+                    }
+                break;
+            case 5: /* GOALS 1010-1013: goals hold (x, y); the loop names them (goal_y, goal_x) and writes layer[goal_x, goal_y] = [y][x] */
+                for (int g = 0; g < c->n_goals; g++) L[c->goals_xy[2 * g + 1] * W + c->goals_xy[2 * g]] = 1.0f;
+                break;
+            case 6: /* ACCESSIBLE 1014-1017 */
+                for (int k = 0; k < H * W; k++) L[k] = 1.0f;
+                for (int a = 0; a < n; a++) L[e->ay[a] * W + e->ax[a]] = 0.0f;
+                break;
+            default: return -2; /* ValueError 1018-1019 */
+        }
+    }
+    return 0;
+}
+
 /* ---------------------------------------------------------------- seeding / reset (warehouse.py:757-802, 962-964) */
 void orc_seed(orc_env *e, uint64_t seed) {
     np_seed(&e->rng, seed);

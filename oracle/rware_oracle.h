@@ -66,6 +66,10 @@ void orc_obs(const orc_env *e, float *obs);
  * features (IMAGE_DICT, warehouse.py:726-742): [n][6] = one-hot direction, on_highway, carrying; may be NULL. */
 int orc_obs_image(const orc_env *e, const int32_t *layers, int n_layers, int directional, float *out, float *features);
 
+/* warehouse.py:966-1040 (get_global_image) before the optional padding: out [n_layers][H][W] float32.  Same layer ids and
+ * the same literal transposed writes for layers 3 and 4 (1004, 1009); returns -1 where the reference raises IndexError. */
+int orc_global_image(const orc_env *e, const int32_t *layers, int n_layers, float *out);
+
 /* plain-array state access (what the reference's tests poke through env.agents[i].x etc.).
  * agent arrays [n]; carry = shelf id (1-based) or 0; msg [n][msg_bits]; shelf arrays [S]; queue [R] ids;
  * counters[2] = {cur_steps, cur_inactive_steps}; rng[10] = np_export() words.  NULL pointers are skipped. */

@@ -92,9 +92,14 @@ def load_library():
     L.rw_gather_create.argtypes = [vp, ci, ci, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp), vp]
     L.rw_gather_open.argtypes = [vp, vp]
     L.rw_step_gather.argtypes = [vp, vp, vp]
+    L.rw_global_image_shape.argtypes = [vp, ctypes.c_int32, vp, vp]
+    L.rw_global_image.argtypes = [vp, vp, ctypes.c_int32, vp, vp, vp]
+    L.rw_render_shape.argtypes = [vp, vp, vp]
+    L.rw_render_rgb.argtypes = [vp, i64, i64, vp, vp]
     for name in ("rw_create", "rw_destroy", "rw_get_info", "rw_seed", "rw_reset", "rw_step", "rw_obs", "rw_set_auto_reset",
                  "rw_get_state", "rw_set_state", "rw_error_count", "rw_step_host", "rw_reset_host", "rw_host_alloc",
-                 "rw_host_free", "rw_random_actions", "rw_debug_set_clock_buffer", "rw_flush_l2", "rw_gather_create", "rw_gather_open", "rw_step_gather"):
+                 "rw_host_free", "rw_random_actions", "rw_debug_set_clock_buffer", "rw_flush_l2", "rw_gather_create", "rw_gather_open", "rw_step_gather",
+                 "rw_global_image_shape", "rw_global_image", "rw_render_shape", "rw_render_rgb"):
         getattr(L, name).restype = ci
     _lib = L
     return L
@@ -215,6 +220,27 @@ class CudaBackend:
         out = ctypes.c_int64()
         self._check(self.lib.rw_error_count(self._h, ctypes.byref(out), self._stream()))
         return out.value
+
+    # ---- whole-warehouse views
+    def global_image_shape(self, n_layers, pad_to_shape=None):
+        pad = None if pad_to_shape is None else (ctypes.c_int32 * 3)(*[int(v) for v in pad_to_shape])
+        shape = (ctypes.c_int32 * 3)()
+        if len(pad_to_shape or (0, 0, 0)) != 3 or self.lib.rw_global_image_shape(self._h, int(n_layers), pad, shape):
+            raise RuntimeError("pad_to_shape must be >= (n_layers, H, W) elementwise (1..8 layers)")
+        return tuple(shape)
+
+    def global_image(self, layers, pad_to_shape, out):
+        lay = (ctypes.c_int32 * len(layers))(*[int(v) for v in layers])
+        pad = None if pad_to_shape is None else (ctypes.c_int32 * 3)(*[int(v) for v in pad_to_shape])
+        self._check(self.lib.rw_global_image(self._h, lay, len(layers), pad, _ptr(out), self._stream()))
+
+    def render_shape(self):
+        h, w = ctypes.c_int32(), ctypes.c_int32()
+        self._check(self.lib.rw_render_shape(self._h, ctypes.byref(h), ctypes.byref(w)))
+        return h.value, w.value
+
+    def render_rgb(self, first_env, n_envs, out):
+        self._check(self.lib.rw_render_rgb(self._h, int(first_env), int(n_envs), _ptr(out), self._stream()))
 
     # ---- fused push all-gather (multi-GPU)
     def gather_create(self, world_size, rank):

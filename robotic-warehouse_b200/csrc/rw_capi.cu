@@ -14,6 +14,7 @@
 #include "../../include/rware_b200.h"
 #include "rw_launch.h"
 #include "rw_host_layout.h"
+#include "rw_views.cuh"
 
 struct rw_handle {
     RwParams p;
@@ -394,6 +395,52 @@ int rw_random_actions(rw_handle *h, int32_t *actions_dev, uint64_t seed, uint64_
     if (!h || !actions_dev) return RW_EINVAL;
     CK(cudaSetDevice(h->device));
     CK(rw_launch_random_actions(h->p, actions_dev, seed, step, (cudaStream_t)stream));
+    return RW_OK;
+}
+
+int rw_global_image_shape(const rw_handle *h, int32_t n_layers, const int32_t *pad_to_shape, int32_t *shape_out) {
+    if (!h || !shape_out || n_layers < 1 || n_layers > 8) return RW_EINVAL;
+    const int32_t dims[3] = {n_layers, h->p.H, h->p.W};
+    for (int k = 0; k < 3; k++) {
+        shape_out[k] = pad_to_shape ? pad_to_shape[k] : dims[k];
+        if (shape_out[k] < dims[k]) return RW_EINVAL;  // the reference asserts every padding is >= 0 (warehouse.py:1027)
+    }
+    return RW_OK;
+}
+
+int rw_global_image(rw_handle *h, const int32_t *layers, int32_t n_layers, const int32_t *pad_to_shape, float *out_dev, void *stream) {
+    if (!h || !layers || !out_dev) return fail(h, RW_EINVAL, "rw_global_image: null argument");
+    if (!h->ready) return fail(h, RW_ESTATE, "rw_global_image before rw_reset / rw_set_state");
+    RwViewSpec s;
+    memset(&s, 0, sizeof(s));
+    int32_t shape[3];
+    if (rw_global_image_shape(h, n_layers, pad_to_shape, shape) != RW_OK)
+        return fail(h, RW_EINVAL, "rw_global_image: 1..8 layers, pad_to_shape >= (n_layers, H, W) elementwise");
+    for (int c = 0; c < n_layers; c++) {
+        if (layers[c] < 0 || layers[c] > 6) return fail(h, RW_EINVAL, "rw_global_image: unknown image layer type");  // ValueError 1018-1019
+        s.layers[c] = layers[c];
+    }
+    s.n_layers = n_layers;
+    s.C = shape[0]; s.Hp = shape[1]; s.Wp = shape[2];
+    s.c0 = (shape[0] - n_layers) / 2; s.y0 = (shape[1] - h->p.H) / 2; s.x0 = (shape[2] - h->p.W) / 2;  // pad_before 1028
+    CK(cudaSetDevice(h->device));
+    CK(rw_launch_global_image(h->p, s, out_dev, (cudaStream_t)stream));
+    return RW_OK;
+}
+
+int rw_render_shape(const rw_handle *h, int32_t *height, int32_t *width) {
+    if (!h || !height || !width) return RW_EINVAL;
+    *height = rw_render_height(h->p);
+    *width = rw_render_width(h->p);
+    return RW_OK;
+}
+
+int rw_render_rgb(rw_handle *h, int64_t first_env, int64_t n_envs, uint8_t *out_dev, void *stream) {
+    if (!h || !out_dev) return fail(h, RW_EINVAL, "rw_render_rgb: null argument");
+    if (!h->ready) return fail(h, RW_ESTATE, "rw_render_rgb before rw_reset / rw_set_state");
+    if (first_env < 0 || n_envs < 1 || first_env + n_envs > h->p.E) return fail(h, RW_EINVAL, "rw_render_rgb: world range out of bounds");
+    CK(cudaSetDevice(h->device));
+    CK(rw_launch_render(h->p, out_dev, first_env, n_envs, (cudaStream_t)stream));
     return RW_OK;
 }
 

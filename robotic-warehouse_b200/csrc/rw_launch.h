@@ -17,3 +17,8 @@ cudaError_t rw_launch_seed_scatter(const RwParams &p, const uint32_t *staging /*
 cudaError_t rw_launch_random_actions(const RwParams &p, int32_t *actions, uint64_t seed, uint64_t step,
                                      cudaStream_t stream);
 cudaError_t rw_launch_flush_l2(void *buf, size_t bytes, int value, int smem_bytes, cudaStream_t stream);
+
+// whole-warehouse views (rw_views.cu)
+struct RwViewSpec;
+cudaError_t rw_launch_global_image(const RwParams &p, const RwViewSpec &spec, float *out, cudaStream_t stream);
+cudaError_t rw_launch_render(const RwParams &p, uint8_t *out, int64_t env0, int64_t count, cudaStream_t stream);

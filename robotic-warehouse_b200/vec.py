@@ -89,6 +89,36 @@ class VecWarehouse:
         self.backend.obs(self._obs)
         return self._obs
 
+    # ------------------------------------------------------------------ whole-warehouse views
+    def global_image(self, image_layers=(0, 5), pad_to_shape=None, out=None):
+        """Warehouse.get_global_image(image_layers, recompute=True, pad_to_shape) (rware/warehouse.py:966-1040) of every world:
+        float32 [E, C', H', W'] on the device (input of a centralised critic).  Layers AGENT_DIRECTION / AGENT_LOAD are written
+        transposed exactly as the reference writes them; worlds where the reference would raise IndexError for that are
+        counted in `error_count()`."""
+        layers = [int(getattr(v, "value", v)) for v in image_layers]
+        if not layers or any(v < 0 or v > 6 for v in layers):
+            raise ValueError(f"Unknown image layer type: {image_layers}")  # warehouse.py:1018-1019
+        shape = self.backend.global_image_shape(len(layers), pad_to_shape)
+        if out is None:
+            out = torch.empty((self.num_envs, *shape), dtype=torch.float32, device=self.device)
+        assert out.is_contiguous() and out.dtype == torch.float32 and tuple(out.shape) == (self.num_envs, *shape)
+        self.backend.global_image(layers, pad_to_shape, out)
+        return out
+
+    def render_rgb(self, first_env=0, n_envs=1, out=None):
+        """`render()` of render_mode="rgb_array" (rware/warehouse.py:948-956, rware/rendering.py) for the worlds
+        [first_env, first_env + n_envs): uint8 [n_envs, 2 + 31 H, 1 + 31 W, 3] on the device."""
+        h, w = self.backend.render_shape()
+        if out is None:
+            out = torch.empty((n_envs, h, w, 3), dtype=torch.uint8, device=self.device)
+        assert out.is_contiguous() and out.dtype == torch.uint8 and tuple(out.shape) == (n_envs, h, w, 3)
+        self.backend.render_rgb(first_env, n_envs, out)
+        return out
+
+    def error_count(self):
+        """Invalid action values seen so far (the reference raises ValueError) + transposed-layer index errors."""
+        return self.backend.error_count()
+
     # ------------------------------------------------------------------ state access (checkpoint / test injection)
     def _state_shapes(self):
         E, n, S, R, mb = self.num_envs, self.n_agents, self.n_shelves, self.request_queue_size, self.msg_bits

@@ -319,7 +319,31 @@ class Warehouse:
         return {}
 
     def render(self):
-        raise NotImplementedError("rendering is out of scope of the accelerated step path (BASELINE.json north_star)")
+        """rware/warehouse.py:948-956.  render_mode="rgb_array" returns the frame rasterised on the device from the world
+        state (uint8 [2 + 31 H, 1 + 31 W, 3], the reference Viewer's window size); "human" needs a window system and is not
+        part of the accelerated path."""
+        if self.render_mode != "rgb_array":
+            raise NotImplementedError('render_mode="human" opens a pyglet window in the reference; use render_mode="rgb_array"')
+        self._push()
+        return self._vec.render_rgb(0, 1)[0].cpu().numpy()
+
+    def get_global_image(self, image_layers=(ImageLayer.SHELVES, ImageLayer.GOALS), recompute=False, pad_to_shape=None):
+        """rware/warehouse.py:966-1040: stacked layers of the whole grid, computed on the device; cached in
+        `self.global_image` until `recompute=True`, as in the reference."""
+        if recompute or self.global_image is None:
+            layers = [ImageLayer(getattr(v, "value", v)) for v in image_layers]
+            for layer in layers:  # layer[ag.x, ag.y] (sic, 1004 / 1009): same IndexError as numpy raises in the reference
+                if layer in (ImageLayer.AGENT_DIRECTION, ImageLayer.AGENT_LOAD):
+                    for ag in self.agents:
+                        if (layer == ImageLayer.AGENT_DIRECTION or ag.carrying_shelf is not None) and (
+                                ag.x >= self.grid_size[0] or ag.y >= self.grid_size[1]):
+                            bad_axis, bad = (0, ag.x) if ag.x >= self.grid_size[0] else (1, ag.y)
+                            raise IndexError(f"index {bad} is out of bounds for axis {bad_axis} with size {self.grid_size[bad_axis]}")
+            if pad_to_shape is not None:
+                assert all(p >= g for p, g in zip(pad_to_shape, (len(layers), *self.grid_size)))  # 1027
+            self._push()
+            self.global_image = self._vec.global_image(layers, pad_to_shape)[0].cpu().numpy()
+        return self.global_image
 
     def close(self):
         self._vec.close()

@@ -203,10 +203,66 @@ def record_obs_types(wh):
         json.dump(out, f)
 
 
+def record_global_images(wh):
+    """get_global_image (warehouse.py:966-1040) of the unmodified reference along short trajectories: every layer, the padding
+    rule, and the IndexError of the transposed AGENT_DIRECTION / AGENT_LOAD layers on a non-square grid."""
+    IL = wh.ImageLayer
+    cases = {
+        "default_tiny": dict(kw=dict(shelf_columns=3, column_height=8, shelf_rows=1), n=4, layers=[IL.SHELVES, IL.GOALS], pad=None),
+        "all_plain_tiny_padded": dict(kw=dict(shelf_columns=3, column_height=8, shelf_rows=1), n=5,
+                                      layers=[IL.ACCESSIBLE, IL.AGENTS, IL.REQUESTS, IL.SHELVES, IL.GOALS], pad=(7, 14, 13)),
+        "all_layers_square": dict(kw=dict(shelf_columns=1, column_height=1, shelf_rows=1,
+                                          layout="..x..x.\n.xx.xx.\n.......\nx..g..x\n.x...x.\n..xgx..\n......."), n=6,
+                                  layers=[IL.SHELVES, IL.REQUESTS, IL.AGENTS, IL.AGENT_DIRECTION, IL.AGENT_LOAD, IL.GOALS, IL.ACCESSIBLE],
+                                  pad=(7, 8, 10)),
+        "transposed_tiny": dict(kw=dict(shelf_columns=3, column_height=8, shelf_rows=1), n=6,
+                                layers=[IL.AGENT_DIRECTION, IL.AGENT_LOAD, IL.AGENTS], pad=None),
+    }
+    out, meta = {}, {}
+    for name, cs in cases.items():
+        n = cs["n"]
+        kwargs = dict(n_agents=n, msg_bits=0, sensor_range=1, request_queue_size=3, max_inactivity_steps=None, max_steps=60,
+                      reward_type=wh.RewardType.INDIVIDUAL, **cs["kw"])
+        env = wh.Warehouse(**kwargs)
+        rs = np.random.default_rng(len(name))
+        T = 120
+        acts = rs.choice(5, size=(T, n), p=[.05, .5, .1, .1, .25]).astype(np.int8)
+        imgs, raised = [], []
+
+        def snap():
+            try:
+                imgs.append(env.get_global_image(image_layers=cs["layers"], recompute=True, pad_to_shape=cs["pad"]).astype(np.float32))
+                raised.append(0)
+            except IndexError:
+                imgs.append(np.zeros_like(imgs[-1]) if imgs else None)
+                raised.append(1)
+        env.reset(seed=5)
+        snap()
+        for t in range(T):
+            _, _, done, _, _ = env.step([int(a) for a in acts[t]])
+            if done:
+                env.reset()
+            snap()
+        first = next(i for i in imgs if i is not None)
+        imgs = [np.zeros_like(first) if i is None else i for i in imgs]
+        out[name + "_images"] = np.stack(imgs)
+        out[name + "_raised"] = np.asarray(raised, np.uint8)
+        out[name + "_actions"] = acts
+        meta[name] = dict(kwargs={k: (v.value if hasattr(v, "value") else v) for k, v in kwargs.items()}, seed=5,
+                          layers=[l.value for l in cs["layers"]], pad=cs["pad"])
+        print("global-image fixture", name, out[name + "_images"].shape, "raised", int(sum(raised)))
+    np.savez_compressed(os.path.join(HERE, "global_image.npz"), **out)
+    with open(os.path.join(HERE, "global_image.json"), "w") as f:
+        json.dump(meta, f)
+
+
 def main():
     gym, wh = refenv.load_reference()
     if len(sys.argv) > 1 and sys.argv[1] == "obs_types":
         record_obs_types(wh)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "global_image":
+        record_global_images(wh)
         return
     G, I, T = 0, 1, 2
     record(wh, "tiny2_indiv", kw(3, 8, 1, 2, 0, 1, 2, None, 500, I), 700, 0.3, 9, seed=0)
@@ -223,6 +279,7 @@ def main():
     known_answers(gym)
     layouts(wh)
     record_obs_types(wh)
+    record_global_images(wh)
 
 
 if __name__ == "__main__":

@@ -20,7 +20,7 @@ def _load():
     if _lib is None:
         src = os.path.join(_HERE, "hostsim.cpp")
         csrc = os.path.join(os.path.dirname(os.path.dirname(_HERE)), "robotic-warehouse_b200", "csrc")
-        deps = [src] + [os.path.join(csrc, f) for f in ("rw_logic.cuh", "rw_common.h", "rw_host_layout.h", "rw_static_configs.h")]
+        deps = [src] + [os.path.join(csrc, f) for f in ("rw_logic.cuh", "rw_coop.cuh", "rw_views.cuh", "rw_common.h", "rw_host_layout.h", "rw_static_configs.h")]
         if not os.path.exists(_LIB) or os.path.getmtime(_LIB) < max(os.path.getmtime(d) for d in deps):
             os.makedirs(os.path.dirname(_LIB), exist_ok=True)
             subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", _LIB, src], check=True)
@@ -40,6 +40,9 @@ def _load():
         L.sim_set_coop.argtypes = [vp, ctypes.c_int]
         L.sim_get_state.argtypes = [vp, ctypes.POINTER(RwStateView)]
         L.sim_set_state.argtypes = [vp, ctypes.POINTER(RwStateView)]
+        L.sim_global_image.argtypes = [vp, vp, ctypes.c_int, vp, vp]
+        L.sim_render_shape.argtypes = [vp, vp, vp]
+        L.sim_render_rgb.argtypes = [vp, ctypes.c_int64, ctypes.c_int64, vp]
         _lib = L
     return _lib
 
@@ -102,3 +105,26 @@ class HostSimBackend:
 
     def error_count(self):
         return int(self.lib.sim_error_count(self._h))
+
+    def global_image_shape(self, n_layers, pad_to_shape=None):
+        H, W = self.cfg.grid_size
+        shape = (n_layers, H, W) if pad_to_shape is None else tuple(int(v) for v in pad_to_shape)
+        if len(shape) != 3 or any(a < b for a, b in zip(shape, (n_layers, H, W))):
+            raise RuntimeError("pad_to_shape must be >= (n_layers, H, W) elementwise")
+        return shape
+
+    def global_image(self, layers, pad_to_shape, out):
+        lay = np.ascontiguousarray(layers, np.int32)
+        pad = None if pad_to_shape is None else np.ascontiguousarray(pad_to_shape, np.int32)
+        rc = self.lib.sim_global_image(self._h, lay.ctypes.data, len(lay), None if pad is None else pad.ctypes.data, _ptr(out))
+        if rc:
+            raise RuntimeError("rware_b200 C-ABI call failed: unknown image layer type or bad pad_to_shape")
+
+    def render_shape(self):
+        h, w = ctypes.c_int32(), ctypes.c_int32()
+        self.lib.sim_render_shape(self._h, ctypes.byref(h), ctypes.byref(w))
+        return h.value, w.value
+
+    def render_rgb(self, first_env, n_envs, out):
+        if self.lib.sim_render_rgb(self._h, int(first_env), int(n_envs), _ptr(out)):
+            raise RuntimeError("render_rgb: world range out of bounds")

@@ -7,12 +7,14 @@
 // fallback: nothing in the product package loads it, and the product raises when the CUDA library is missing.
 #include <cstdint>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
 #include "../../robotic-warehouse_b200/csrc/rw_host_layout.h"
 #include "../../robotic-warehouse_b200/csrc/rw_logic.cuh"
 #include "../../robotic-warehouse_b200/csrc/rw_coop.cuh"
+#include "../../robotic-warehouse_b200/csrc/rw_views.cuh"
 
 struct Sim {
     RwParams p;
@@ -61,6 +63,7 @@ Sim *sim_create(const rw_config *cfg, int64_t num_envs) {
     s->rng.assign((size_t)RW_RNG_WORDS * p.E_pad, 0);
     s->smem.assign((size_t)p.sm_warp_bytes, 0);
     p.highway = s->highway.data();
+    p.cta_tables = s->highway.data();  // bit 1 marks goal cells, as the head of the device's table image
     p.home_cell = s->home.data();
     p.home_id = s->home_id.data();
     p.normx = s->nx.data();
@@ -234,6 +237,52 @@ void sim_set_state(Sim *s, const rw_state_view *v) {
         if (v->rng)
             for (int w = 0; w < RW_RNG_WORDS; w++) p.rng[(size_t)w * p.E_pad + env] = v->rng[env * RW_RNG_WORDS + w];
     }
+}
+
+// whole-warehouse views (rw_views.cuh), same per-element functions as rw_views.cu
+int sim_global_image(Sim *s, const int32_t *layers, int n_layers, const int32_t *pad, float *out) {
+    const RwParams &p = s->p;
+    RwViewSpec sp;
+    memset(&sp, 0, sizeof(sp));
+    const int32_t dims[3] = {n_layers, p.H, p.W};
+    int32_t shape[3];
+    for (int k = 0; k < 3; k++) { shape[k] = pad ? pad[k] : dims[k]; if (shape[k] < dims[k]) return -1; }
+    bool dirl = false, loadl = false;
+    for (int c = 0; c < n_layers; c++) {
+        if (layers[c] < 0 || layers[c] > 6) return -1;
+        sp.layers[c] = layers[c]; dirl |= layers[c] == 3; loadl |= layers[c] == 4;
+    }
+    sp.n_layers = n_layers; sp.C = shape[0]; sp.Hp = shape[1]; sp.Wp = shape[2];
+    sp.c0 = (shape[0] - n_layers) / 2; sp.y0 = (shape[1] - p.H) / 2; sp.x0 = (shape[2] - p.W) / 2;
+    std::vector<uint8_t> g(p.cells);
+    const int per = sp.C * sp.Hp * sp.Wp;
+    for (int64_t env = 0; env < p.E; env++) {
+        std::fill(g.begin(), g.end(), 0);
+        RwLane l{p.state + (size_t)(env >> 5) * p.nw * RW_TILE + (env & 31), g.data(), nullptr, 0, nullptr, nullptr};
+        s->err += rw_view_build(p, l, dirl, loadl);
+        for (int i = 0; i < per; i++) out[(size_t)env * per + i] = rw_gimg_element(p, l, p.cta_tables, sp, i);
+    }
+    return 0;
+}
+
+void sim_render_shape(Sim *s, int32_t *h, int32_t *w) { *h = rw_render_height(s->p); *w = rw_render_width(s->p); }
+
+int sim_render_rgb(Sim *s, int64_t env0, int64_t count, uint8_t *out) {
+    const RwParams &p = s->p;
+    if (env0 < 0 || count < 1 || env0 + count > p.E) return -1;
+    std::vector<uint8_t> g(p.cells);
+    const int fw = rw_render_width(p), fh = rw_render_height(p);
+    for (int64_t env = env0; env < env0 + count; env++) {
+        std::fill(g.begin(), g.end(), 0);
+        RwLane l{p.state + (size_t)(env >> 5) * p.nw * RW_TILE + (env & 31), g.data(), nullptr, 0, nullptr, nullptr};
+        rw_view_build(p, l, false, false);
+        uint8_t *o = out + (size_t)(env - env0) * fw * fh * 3;
+        for (int k = 0; k < fw * fh; k++) {
+            uint32_t c = rw_render_pixel(p, l, p.cta_tables, k / fw, k % fw);
+            o[3 * k] = (uint8_t)c; o[3 * k + 1] = (uint8_t)(c >> 8); o[3 * k + 2] = (uint8_t)(c >> 16);
+        }
+    }
+    return 0;
 }
 
 }  // extern "C"
