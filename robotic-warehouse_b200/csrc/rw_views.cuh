@@ -34,35 +34,49 @@ RW_HD int rw_view_build(const RwParams &p, const RwLane &l, bool has_dir_layer, 
     return bad;
 }
 
-// value of layer `layer` at row y, column x (0 <= y < H, 0 <= x < W).  goal_flags[cell] & 2 marks goal cells.
-RW_HD float rw_gimg_value(const RwParams &p, const RwLane &l, const uint8_t *goal_flags, int layer, int y, int x) {
-    const int cell = y * p.W + x;
-    const uint32_t gb = l.g[cell];
-    switch (layer) {
-        case 0: return (gb & RW_G_SHELF) ? 1.0f : 0.0f;   // SHELVES 988-991
-        case 1: return (gb & RW_G_REQ) ? 1.0f : 0.0f;     // REQUESTS 992-995
-        case 2: return (gb & RW_G_AGENT) ? 1.0f : 0.0f;   // AGENTS 996-999
-        case 5: return (goal_flags[cell] & 2) ? 1.0f : 0.0f;  // GOALS 1010-1013 (the swapped loop names cancel: layer[y][x])
-        case 6: return (gb & RW_G_AGENT) ? 0.0f : 1.0f;   // ACCESSIBLE 1014-1017
+// Every output element is "classified" once (which cell it looks at and how; independent of the world) and then "shaded" per
+// world from that world's occupancy byte, so a thread that owns an element position pays the index arithmetic once per tile.
+// code: bits 0-15 cell, 16-23 mask over the occupancy byte, 24 invert, 25-27 special (3 / 4: transposed agent layers)
+#define RW_GC_INV (1u << 24)
+#define RW_GC_SPECIAL(code) (((code) >> 25) & 7u)
+
+// element [cp][yp][xp] of the padded output: np.pad constant 0 outside (1033-1038), else layer s.layers[c] at row y, column x
+RW_HD uint32_t rw_gimg_classify(const RwParams &p, const uint8_t *goal_flags, const RwViewSpec &s, int cp, int yp, int xp) {
+    const int c = cp - s.c0, y = yp - s.y0, x = xp - s.x0;
+    if (c < 0 || c >= s.n_layers || y < 0 || y >= p.H || x < 0 || x >= p.W) return 0u;  // mask 0, no invert: constant 0
+    const uint32_t cell = (uint32_t)(y * p.W + x);
+    switch (s.layers[c]) {
+        case 0: return cell | (RW_G_SHELF << 16);             // SHELVES 988-991
+        case 1: return cell | (RW_G_REQ << 16);               // REQUESTS 992-995
+        case 2: return cell | (RW_G_AGENT << 16);             // AGENTS 996-999
+        case 6: return cell | (RW_G_AGENT << 16) | RW_GC_INV; // ACCESSIBLE 1014-1017
+        case 5: return (goal_flags[cell] & 2) ? RW_GC_INV : 0u;  // GOALS 1010-1013 (the swapped loop names cancel: layer[y][x])
         case 3:
-        case 4: {  // layer[ag.x, ag.y] (sic): element [y][x] belongs to the agent standing at column y, row x
-            if (x >= p.H || y >= p.W) return 0.0f;
-            uint32_t id = l.g[x * p.W + y] & RW_G_AGENT;
-            if (!id) return 0.0f;
-            uint32_t aw = rw_agent(l, (int)id - 1);
-            if (layer == 3) return (float)(rw_adir(aw) + 1);  // AGENT_DIRECTION 1000-1004
-            return rw_acarry(aw) ? 1.0f : 0.0f;               // AGENT_LOAD 1005-1009
-        }
+        case 4:  // layer[ag.x, ag.y] (sic, 1004 / 1009): element [y][x] belongs to the agent standing at column y, row x
+            if (x >= p.H || y >= p.W) return 0u;
+            return (uint32_t)(x * p.W + y) | ((uint32_t)s.layers[c] << 25);
     }
-    return 0.0f;
+    return 0u;
+}
+
+RW_HD float rw_gimg_shade(const RwLane &l, uint32_t code) {
+    const uint32_t gb = l.g[code & 0xffffu];
+    const uint32_t special = RW_GC_SPECIAL(code);
+    if (special) {
+        const uint32_t id = gb & RW_G_AGENT;
+        if (!id) return 0.0f;
+        const uint32_t aw = rw_agent(l, (int)id - 1);
+        if (special == 3) return (float)(rw_adir(aw) + 1);  // AGENT_DIRECTION 1000-1004
+        return rw_acarry(aw) ? 1.0f : 0.0f;                 // AGENT_LOAD 1005-1009
+    }
+    const bool on = (gb & (code >> 16) & 0xffu) != 0;
+    return (on != ((code & RW_GC_INV) != 0)) ? 1.0f : 0.0f;
 }
 
 RW_HD float rw_gimg_element(const RwParams &p, const RwLane &l, const uint8_t *goal_flags, const RwViewSpec &s, int idx) {
     const int plane = s.Hp * s.Wp;
     const int cp = idx / plane, rem = idx - cp * plane, yp = rem / s.Wp, xp = rem - yp * s.Wp;
-    const int c = cp - s.c0, y = yp - s.y0, x = xp - s.x0;
-    if (c < 0 || c >= s.n_layers || y < 0 || y >= p.H || x < 0 || x >= p.W) return 0.0f;  // np.pad constant 0 (1033-1038)
-    return rw_gimg_value(p, l, goal_flags, s.layers[c], y, x);
+    return rw_gimg_shade(l, rw_gimg_classify(p, goal_flags, s, cp, yp, xp));
 }
 
 // ---------------------------------------------------------------- rgb_array frame (rware/rendering.py)
@@ -80,38 +94,48 @@ RW_HD int rw_render_height(const RwParams &p) { return 2 + p.H * RW_RENDER_CELL;
 
 RW_HD uint32_t rw_rgb(uint32_t r, uint32_t g, uint32_t b) { return r | (g << 8) | (b << 16); }
 
-// colour (r | g<<8 | b<<16) of frame pixel (row i from the top, column j)
-RW_HD uint32_t rw_render_pixel(const RwParams &p, const RwLane &l, const uint8_t *goal_flags, int i, int j) {
-    const uint32_t white = rw_rgb(255, 255, 255), black = rw_rgb(0, 0, 0);
+// A frame pixel is classified once (constant colour, or a cell plus which primitives of that cell cover the pixel) and shaded
+// per world.  code: bit 31 constant (bits 0-23 colour); else bits 0-15 cell, 16-19 covered by the heading line of direction d,
+// 20 inside the agent hexagon, 21 inside the shelf quad, 22 goal cell.
+RW_HD uint32_t rw_render_classify(const RwParams &p, const uint8_t *goal_flags, int i, int j) {
+    const uint32_t white = rw_rgb(255, 255, 255) | (1u << 31), black = rw_rgb(0, 0, 0) | (1u << 31);
     const int gy = rw_render_height(p) - 1 - i;  // OpenGL row (origin bottom-left)
     const int cx = j / RW_RENDER_CELL, px = j - cx * RW_RENDER_CELL;  // px == 0: vertical grid line
     const int cyg = gy / RW_RENDER_CELL, py = gy - cyg * RW_RENDER_CELL;  // py == 0: horizontal grid line
-    const bool in_x = cx < p.W, in_y = cyg < p.H;
     // grid lines: horizontal x in [0, 31 W), rows 31 r (r = 0..H); vertical y in [0, 31 H), columns 31 c (c = 0..W)
     if (py == 0 && cyg <= p.H && j < p.W * RW_RENDER_CELL) return black;
     if (px == 0 && cx <= p.W && gy < p.H * RW_RENDER_CELL) return black;
-    if (!in_x || !in_y) return white;
+    if (cx >= p.W || cyg >= p.H) return white;
     const int y = p.H - 1 - cyg;  // "pyglet rendering is reversed" (186, 213, 273)
-    const int cell = y * p.W + cx;
-    const uint32_t gb = l.g[cell];
-    // agent: heading line, then hexagon, both relative to the centre (16, 16) of the 31-pixel cell, pixel centre (px+.5, py+.5)
-    if (gb & RW_G_AGENT) {
+    uint32_t code = (uint32_t)(y * p.W + cx);
+    // heading line from the cell centre (16, 16) to (16, 16) + 10 * heading: 10 pixels along the axis, on pixel 15 across it
+    if (px == 15 && py >= 16 && py < 26) code |= 1u << 16;  // UP: +y in GL
+    if (px == 15 && py >= 6 && py < 16) code |= 1u << 17;   // DOWN
+    if (py == 15 && px >= 6 && px < 16) code |= 1u << 18;   // LEFT
+    if (py == 15 && px >= 16 && px < 26) code |= 1u << 19;  // RIGHT
+    // regular hexagon, circumradius 10, vertices at angles 0, 60, ...: |dy| <= 10 sin60 and |dy| <= sqrt(3) (10 - |dx|)
+    const float dx = (float)px + 0.5f - 16.0f, dy = (float)py + 0.5f - 16.0f;
+    const float ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy;
+    if (ay <= 8.660254f && ay <= 1.7320508f * (10.0f - ax)) code |= 1u << 20;
+    if (px >= 3 && px <= 28 && py >= 3 && py <= 28) code |= 1u << 21;  // shelf quad: [31 c + 3, 31 c + 29) -> pixels 3..28
+    if (goal_flags[code & 0xffffu] & 2) code |= 1u << 22;              // goal quad fills the cell interior, pixels 1..30
+    return code;
+}
+
+RW_HD uint32_t rw_render_shade(const RwLane &l, uint32_t code) {
+    if (code >> 31) return code & 0xffffffu;
+    const uint32_t gb = l.g[code & 0xffffu];
+    if (gb & RW_G_AGENT) {  // agents are drawn last: heading line over hexagon over everything else
         const uint32_t aw = rw_agent(l, (int)(gb & RW_G_AGENT) - 1);
-        const int d = rw_adir(aw);
-        // line from (16,16) to (16,16) + 10 * heading: covers 10 pixels along the axis, on pixel 15 across it
-        const bool on_line = d == 0   ? (px == 15 && py >= 16 && py < 26)    // UP: +y in GL
-                             : d == 1 ? (px == 15 && py >= 6 && py < 16)     // DOWN
-                             : d == 2 ? (py == 15 && px >= 6 && px < 16)     // LEFT
-                                      : (py == 15 && px >= 16 && px < 26);   // RIGHT
-        if (on_line) return black;
-        // regular hexagon, circumradius 10, vertices at angles 0, 60, ...: |dy| <= 10 sin60 and |dy| <= sqrt(3) (10 - |dx|)
-        const float dx = (float)px + 0.5f - 16.0f, dy = (float)py + 0.5f - 16.0f;
-        const float ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy;
-        if (ay <= 8.660254f && ay <= 1.7320508f * (10.0f - ax)) return rw_acarry(aw) ? rw_rgb(255, 0, 0) : rw_rgb(255, 140, 0);
+        if ((code >> (16 + rw_adir(aw))) & 1u) return rw_rgb(0, 0, 0);
+        if ((code >> 20) & 1u) return rw_acarry(aw) ? rw_rgb(255, 0, 0) : rw_rgb(255, 140, 0);
     }
-    // shelf quad: x, y in [31 c + 3, 31 c + 29) continuous -> pixels 3..28
-    if ((gb & RW_G_SHELF) && px >= 3 && px <= 28 && py >= 3 && py <= 28)
-        return (gb & RW_G_REQ) ? rw_rgb(0, 128, 128) : rw_rgb(72, 61, 139);
-    if (goal_flags[cell] & 2) return rw_rgb(60, 60, 60);  // goal quad fills the cell interior, pixels 1..30
-    return white;
+    if ((gb & RW_G_SHELF) && ((code >> 21) & 1u)) return (gb & RW_G_REQ) ? rw_rgb(0, 128, 128) : rw_rgb(72, 61, 139);
+    if ((code >> 22) & 1u) return rw_rgb(60, 60, 60);
+    return rw_rgb(255, 255, 255);
+}
+
+// colour (r | g<<8 | b<<16) of frame pixel (row i from the top, column j)
+RW_HD uint32_t rw_render_pixel(const RwParams &p, const RwLane &l, const uint8_t *goal_flags, int i, int j) {
+    return rw_render_shade(l, rw_render_classify(p, goal_flags, i, j));
 }
