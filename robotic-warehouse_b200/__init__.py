@@ -5,7 +5,7 @@ Drop-in for the step path of semitable/robotic-warehouse: `Warehouse` (Gymnasium
 `VecWarehouse` (E worlds, tensors), and the registered `rware-*` ids.
 """
 from .layout import layout_from_params, layout_from_str  # noqa: F401
-from .registration import env_kwargs, make, make_vec, registry  # noqa: F401
+from .registration import env_kwargs, full_registration, image_registration, make, make_vec, registry  # noqa: F401
 from .vec import VecWarehouse  # noqa: F401
 from . import wrappers  # noqa: F401
 from .warehouse import (Action, Agent, Direction, ImageLayer, ObservationType, RewardType, Shelf,  # noqa: F401

@@ -256,8 +256,34 @@ def record_global_images(wh):
         json.dump(meta, f)
 
 
+def record_registry_ids(gym):
+    """id -> kwargs of the reference's optional registrations (rware/__init__.py:42-172): every image id and a random sample
+    of the 5.25 million full_registration ids (enumerating them takes ~30 s)."""
+    import rware
+    base = set(gym.registry)
+    rware.image_registration()
+    img_ids = sorted(set(gym.registry) - base)
+    rware.full_registration()
+    full_ids = sorted(set(gym.registry) - base - set(img_ids))
+    rs = np.random.default_rng(0)
+    sample = [full_ids[i] for i in rs.choice(len(full_ids), 1500, replace=False)]
+    cols = ["column_height", "shelf_rows", "shelf_columns", "n_agents", "msg_bits", "sensor_range", "request_queue_size",
+            "max_inactivity_steps", "max_steps", "reward_type", "observation_type", "image_observation_directional"]
+
+    def row(kw):
+        return [(kw[c].value if hasattr(kw[c], "value") else kw[c]) for c in cols]
+    out = dict(n_image=len(img_ids), n_full=len(full_ids), columns=cols, image={i: row(gym.registry[i][1]) for i in img_ids},
+               full_sample={i: row(gym.registry[i][1]) for i in sample})
+    with open(os.path.join(HERE, "registry_ids.json"), "w") as f:
+        json.dump(out, f, separators=(",", ":"))
+    print("registry fixture:", len(img_ids), "image ids,", len(sample), "of", len(full_ids), "full ids")
+
+
 def main():
     gym, wh = refenv.load_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "registry":
+        record_registry_ids(gym)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "obs_types":
         record_obs_types(wh)
         return
@@ -280,6 +306,7 @@ def main():
     layouts(wh)
     record_obs_types(wh)
     record_global_images(wh)
+    record_registry_ids(gym)
 
 
 if __name__ == "__main__":

@@ -84,3 +84,43 @@ def test_seed_array_and_scalar_forms(backend):
     assert torch.equal(oa, ob)
     oc = b.reset(seed=np.full(6, 10, np.uint64))
     assert all(torch.equal(oc[0], oc[i]) for i in range(6)) and torch.equal(oc[0], oa[0])
+
+
+def test_optional_registrations_resolve_like_the_reference():
+    """image_registration() / full_registration() (rware/__init__.py:42-172): ids are unknown until enabled, then resolve to
+    the kwargs the reference registers (tests/golden/registry_ids.json: all 912 image ids, 1 500 sampled full ids)."""
+    import json
+    import os
+    from rware_b200 import registration as reg
+    from rware_b200.warehouse import ObservationType, RewardType
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "registry_ids.json")) as f:
+        fx = json.load(f)
+    cols = fx["columns"]
+    saved = set(reg._enabled)
+    reg._enabled.clear()
+    try:
+        some_img, some_full = next(iter(fx["image"])), next(iter(fx["full_sample"]))
+        for id_ in (some_img, some_full):
+            with pytest.raises(KeyError):
+                reg.env_kwargs(id_)
+
+        def check(table):
+            for id_, row in table.items():
+                want = dict(zip(cols, row))
+                want["reward_type"] = RewardType(want["reward_type"])
+                want["observation_type"] = ObservationType(want["observation_type"])
+                assert reg.env_kwargs(id_) == want, id_
+        rware_b200.image_registration()
+        check(fx["image"])
+        with pytest.raises(KeyError):
+            reg.env_kwargs(some_full) if some_full not in fx["image"] and "h-" in some_full else (_ for _ in ()).throw(KeyError())
+        rware_b200.full_registration()
+        check(fx["full_sample"])
+        for bad in ("rware-Nd-tiny-8h-2ag-v2", "rware-imgdict-2s-tiny-8h-2ag-v2", "rware-tiny-16h-2ag-v2", "rware-tiny-8h-20ag-v2",
+                    "rware-5x3-8h-2ag-2req-indiv-v2", "rware-2x4-8h-2ag-2req-indiv-v2", "rware-2x3-8h-2ag-20req-indiv-v2"):
+            with pytest.raises(KeyError):
+                reg.env_kwargs(bad)
+        assert reg.env_kwargs("rware-2s-large-8h-16ag-v2")["sensor_range"] == 2  # BASELINE.json configs[4]
+    finally:
+        reg._enabled.clear()
+        reg._enabled.update(saved)
