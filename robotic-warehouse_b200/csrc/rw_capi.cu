@@ -130,14 +130,14 @@ static int create_impl(rw_handle *h, const rw_config *cfg, int64_t num_envs, int
     {   // warps (= tiles) per CTA: as many as the shared memory of one SM holds, so that a CTA fills an SM and, when the
         // batch allows, the whole launch is a single wave; small batches spread over the SMs instead
         int fit = (smem_cap - p.sm_cta_bytes) / p.sm_warp_bytes;
-        if (fit > 15) fit = 15;  // named barriers 1..15, 1024 threads per CTA
+        if (fit > 14) fit = 14;  // 896 threads per CTA: 72 registers per thread (__launch_bounds__ of rw_main_kernel), named barriers 1..14
         if (fit < 1) fit = 1;
         int spread = (p.tiles + prop.multiProcessorCount - 1) / prop.multiProcessorCount;
         int wpc = spread < fit ? spread : fit;
         const char *ev = getenv("RWARE_B200_WARPS_PER_CTA");
         if (ev) wpc = atoi(ev);
         if (wpc < 1) wpc = 1;
-        if (wpc > 15) wpc = 15;
+        if (wpc > 14) wpc = 14;
         while (wpc > 1 && p.sm_cta_bytes + wpc * p.sm_warp_bytes > smem_cap) wpc--;
         p.warps_per_cta = wpc;
     }

@@ -166,7 +166,7 @@ RW_HD void rw_build_grid(const RwParams &p, const RwLane &l) {
 
 // literal _recalc_grid for worlds flagged with overlapping shelves; also refreshes the flag (O(S^2), cold)
 template <class C>
-RW_HD_NOINLINE void rw_rebuild_grid_slow(const RwParams &p, const RwLane &l) {
+RW_HD_NOINLINE void rw_rebuild_grid_slow(const RwParams &p, const RwLane l) {  // by value: `l` must not escape the caller
     const RwOff o = rw_off<C>(p);
     uint32_t *gz = reinterpret_cast<uint32_t *>(l.g);
     for (int i = 0; i < (p.grid_env_stride >> 2); i++) gz[i] = 0;
@@ -250,7 +250,7 @@ RW_HD void rw_pyset_add(RwPySet &s, int key, HashOf hash_of) {
 // G insertion order when 2*|component| >= |G|, CPython set iteration order otherwise
 // (NX/classes/coreviews.py:293-300, 342-349; NX/algorithms/components/weakly_connected.py:61-66, 169-196).
 template <class C>
-RW_HD_NOINLINE int rw_tie_first(const RwParams &p, const RwLane &l, uint32_t ties) {
+RW_HD_NOINLINE int rw_tie_first(const RwParams &p, const RwLane l, uint32_t ties) {
     const RwOff o = rw_off<C>(p);
     const int n = o.n, m = 2 * n;
     // node id of a cell := index of its first appearance in the sequence s_0, t_0, s_1, t_1, ... (DiGraph.add_edge
@@ -360,7 +360,7 @@ RW_HD int rw_pick(const RwParams &p, const RwLane &l, uint32_t cand) {
 // request-queue resample on delivery (ref:915-917): candidates = shelves not in the queue in ascending id,
 // new = np_random.choice(candidates), replaces the delivered shelf in place.
 template <class C>
-RW_HD_NOINLINE void rw_resample(const RwParams &p, const RwLane &l, int delivered_id, int64_t env) {
+RW_HD_NOINLINE void rw_resample(const RwParams &p, const RwLane l, int delivered_id, int64_t env) {
     const RwOff o = rw_off<C>(p);
     const int S = C::S(p);
     int distinct = 0;
@@ -398,7 +398,7 @@ RW_HD_NOINLINE void rw_resample(const RwParams &p, const RwLane &l, int delivere
 // Warehouse.reset() for one world (ref:757-802), continuing the world's generator stream.  Does NOT touch
 // the occupancy grid (the caller rebuilds it).
 template <class C>
-RW_HD_NOINLINE void rw_reset_lane(const RwParams &p, const RwLane &l, int64_t env) {
+RW_HD_NOINLINE void rw_reset_lane(const RwParams &p, const RwLane l, int64_t env) {
     const RwOff o = rw_off<C>(p);
     RwPcg g;
     rw_pcg_load(g, p.rng, p.E_pad, env);

@@ -78,9 +78,11 @@ __device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0
 // Two warps serve one tile.  The PRIMARY warp (even) runs the per-world logic, one lane per world.  The HELPER warp
 // (odd) zeroes the grids, then sleeps on a named barrier until the post-step state is in shared memory; after that
 // both warps run the observation gather on alternate chunks, each with its own staging buffer and its own TMA bulk
-// stores.  p.warps_per_cta counts TILES per CTA (blockDim = 64 * tiles).
-template <int MODE, class C>
-__global__ void __launch_bounds__(960, 1) rw_main_kernel(const __grid_constant__ RwParams p, const int32_t *__restrict__ actions,
+// stores.  p.warps_per_cta counts TILES per CTA (blockDim = 64 * tiles).  MAXT bounds the CTA size: 896 threads (14 tiles) leave
+// 72 registers per thread; configurations whose tiles are large enough that at most 7 fit an SM use the 448-thread build of the
+// step kernel, which may keep up to 144 registers and does not spill.
+template <int MODE, class C, int MAXT = 896>
+__global__ void __launch_bounds__(MAXT, 1) rw_main_kernel(const __grid_constant__ RwParams p, const int32_t *__restrict__ actions,
                                                        float *__restrict__ obs, float *__restrict__ reward,
                                                        uint8_t *__restrict__ done, const uint8_t *__restrict__ mask) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -321,9 +323,9 @@ __global__ void __launch_bounds__(960, 1) rw_main_kernel(const __grid_constant__
 typedef void (*rw_kernel_fn)(const RwParams, const int32_t *, float *, float *, uint8_t *, const uint8_t *);
 
 template <class C>
-static rw_kernel_fn rw_kernel_for_mode(RwMode mode) {
+static rw_kernel_fn rw_kernel_for_mode(RwMode mode, bool small_cta) {
     switch (mode) {
-        case RW_MODE_STEP: return rw_main_kernel<RW_MODE_STEP, C>;
+        case RW_MODE_STEP: return small_cta ? rw_main_kernel<RW_MODE_STEP, C, 448> : rw_main_kernel<RW_MODE_STEP, C>;
         case RW_MODE_OBS: return rw_main_kernel<RW_MODE_OBS, C>;
         default: return rw_main_kernel<RW_MODE_RESET, C>;
     }

@@ -91,12 +91,10 @@ def _parse(id_):
 
 
 def env_kwargs(id_: str, **overrides):
-    if id_ not in registry:
-        kwargs = _parse(id_)
-        if kwargs is None:
-            raise KeyError(f"unknown environment id {id_!r} (image_registration() / full_registration() enable the extra families)")
-        registry[id_] = kwargs
-    return {**registry[id_], **overrides}
+    kwargs = registry.get(id_) or _parse(id_)  # `registry` holds the eagerly registered base family only
+    if kwargs is None:
+        raise KeyError(f"unknown environment id {id_!r} (image_registration() / full_registration() enable the extra families)")
+    return {**kwargs, **overrides}
 
 
 def make(id_: str, **overrides) -> Warehouse:
