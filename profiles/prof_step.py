@@ -1,4 +1,7 @@
-"""Tiny driver for `ncu` captures of the step kernel: a few launches of one workload."""
+"""Tiny driver for `ncu` captures: reset + 6 step launches + 1 observation-gather launch of one workload, e.g.
+    ncu --set full --clock-control none --import-source on -k regex:rw_main_kernel --launch-skip 6 --launch-count 2 \
+        -o gpurun_out/prof_r1 python profiles/prof_step.py
+captures the last step kernel and the stand-alone gather kernel."""
 import os
 import sys
 
@@ -15,4 +18,6 @@ a = torch.empty((E, v.n_agents), dtype=torch.int32, device="cuda")
 for i in range(6):
     v.backend.random_actions(a, 1, i)
     v.step(a)
+torch.cuda.synchronize()
+v.observations()
 torch.cuda.synchronize()
