@@ -150,6 +150,9 @@ def main():
     ap.add_argument("--gather", nargs="?", const="nccl", default=None, choices=["nccl", "fused"],
                     help="all-gather obs/reward/done across ranks every step: NCCL all_gather_into_tensor, or the fused "
                          "push (the step kernel's TMA stores write into every rank's gathered tensor over NVLink)")
+    ap.add_argument("--streams", type=int, default=2,
+                    help="additionally measure the same K launches dealt round-robin to this many CUDA streams "
+                         "(independent world sets in flight concurrently; reported as `concurrent_streams`, not as `value`)")
     ap.add_argument("--l2", default="rotate", choices=["rotate", "flush", "none"],
                     help="cold-L2 protocol: rotate over 16 world sets (default), flush 512 MiB between launches, or none")
     ap.add_argument("--flush-with", default="library", choices=["library", "torch"],
@@ -265,6 +268,31 @@ def main():
         dist.barrier()
     t_wall = time.perf_counter() - t_wall0
 
+    # optional: the same K launches dealt round-robin to several streams, i.e. independent world sets stepped concurrently
+    # (an asynchronous vector environment).  With CTAs of at most half an SM (RWARE_B200_WARPS_PER_CTA=7) the serial head
+    # of one launch (state fetch + logic) overlaps the observation write phase of the other.
+    multi = None
+    if args.streams > 1 and args.l2 == "rotate" and fused is None and gathered is None:
+        streams = [torch.cuda.Stream(device=dev) for _ in range(args.streams)]
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for rep in range(2):  # first pass warms the streams up
+            m0.record()
+            for st in streams:
+                st.wait_event(m0)
+            for i in range(args.steps):
+                with torch.cuda.stream(streams[i % args.streams]):
+                    one_step(args.warmup + i)
+            for st in streams:
+                e = torch.cuda.Event()
+                e.record(st)
+                torch.cuda.current_stream(dev).wait_event(e)
+            m1.record()
+            torch.cuda.synchronize()
+        multi_ms = float(m0.elapsed_time(m1))
+        multi = {"streams": args.streams, "ms_per_step": multi_ms / args.steps, "value": E * args.steps / (multi_ms * 1e-3),
+                 "tiles_per_cta": int(info["warps_per_cta"]),
+                 "note": "K launches over independent world sets, round-robin on the streams, one event pair around all of them"}
+
     # one world set stepped back to back (its 83 MB working set stays in the 126 MB L2): upper bound, for reference
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0.record()
@@ -375,6 +403,8 @@ def main():
     }
     if cb:
         out["cpu_baseline"] = cb
+    if multi:
+        out["concurrent_streams"] = multi
     print(json.dumps(out))
     if dist:
         dist.destroy_process_group()

@@ -1,8 +1,7 @@
 cd $GRAFT_REPO_ROOT
-python bench.py > gpurun_out/bench_r1.json 2> gpurun_out/bench_r1.err; tail -2 gpurun_out/bench_r1.err; cut -c1-300 gpurun_out/bench_r1.json
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1.csv python bench.py --steps 20 --warmup 3 --no-cpu-baseline --e2e-steps 2 > gpurun_out/bench_under_ncu.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:rw_main_kernel --launch-skip 6 --launch-count 2 -f -o gpurun_out/prof_r1_final2 python profiles/prof_step.py > gpurun_out/ncu_final2.log 2>&1; tail -2 gpurun_out/ncu_final2.log
-python profiles/phase_timeline.py > gpurun_out/phase_timeline_tiny4ag.json 2>/dev/null
-P='import sys,json; d=json.loads(sys.stdin.read()); print(json.dumps({k:d[k] for k in ("value","ms_per_step","roofline","obs_gather","config","e2e")}))'
-for wl in tiny-2ag small-4ag medium-8ag-hard large-16ag-r2 tiny-4ag-image; do python bench.py --workload $wl --steps 200 --warmup 20 --no-cpu-baseline --e2e-steps 4 2>/dev/null | tail -1 | python -c "$P" >> gpurun_out/bench_other_workloads.jsonl; done
-cat gpurun_out/bench_other_workloads.jsonl | cut -c1-200
+timeout 600 python -m pytest tests/test_obs_types.py tests/test_hostsim_golden.py -m gpu -x -q 2>&1 | tail -2
+P='import sys,json; d=json.loads(sys.stdin.read()); print(sys.argv[1], "%.3e" % d["value"], round(d["ms_per_step"]*1000,2), "us frac", round(d["roofline"]["frac"],3), "obs_us", round(d["obs_gather"]["kernel_us"],2), "multi", d.get("concurrent_streams"))'
+for wl in tiny-4ag-image tiny-4ag-imagedict; do python bench.py --workload $wl --steps 200 --warmup 20 --no-cpu-baseline --e2e-steps 2 2>&1 | tail -1 | python -c "$P" $wl; done
+for wpc in 14 7 5; do for st in 2 3; do RWARE_B200_WARPS_PER_CTA=$wpc python bench.py --streams $st --steps 200 --warmup 20 --no-cpu-baseline --e2e-steps 2 2>&1 | tail -1 | python -c "$P" wpc$wpc-streams$st; done; done
+RWARE_B200_WARPS_PER_CTA=7 python bench.py --workload medium-8ag-hard --streams 2 --steps 200 --warmup 20 --no-cpu-baseline --e2e-steps 2 2>&1 | tail -1 | python -c "$P" medium-wpc7-streams2
+RWARE_B200_WARPS_PER_CTA=2 python bench.py --workload medium-8ag-hard --streams 2 --steps 200 --warmup 20 --no-cpu-baseline --e2e-steps 2 2>&1 | tail -1 | python -c "$P" medium-wpc2-streams2

@@ -58,6 +58,7 @@ struct RwParams {
     int32_t goal_cell[RW_MAX_GOALS];
     int32_t obs_kind;             // 0 flattened vector, 2 image, 3 image + features (ObservationType values)
     int32_t img_directional, n_layers, img_layers[8];
+    uint32_t img_mask[8];         // per image layer: test mask over (grid byte | table byte << 8 | outside-the-map << 16), bit 31 = invert
     // tile layout
     int32_t nw, w_agent, w_msg, w_shelf, w_queue, w_steps, w_inact;
     // static device tables
@@ -88,7 +89,6 @@ struct RwParams {
     int32_t obs_parts;     // lanes per agent row in the observation gather (1 or 2)
     int32_t obs_tma;       // 1: observation chunks leave through cp.async.bulk, 0: 16-byte st.global from all lanes
     int32_t grid_env_stride;  // bytes per world of the occupancy grid: one byte per cell (see RW_G_*)
-    int32_t ga_off;           // unused (kept for layout stability)
     int32_t obs_chunk_envs, obs_chunk_bytes, obs_nbuf, obs_env_bytes;
     int32_t obs_buf_stride;  // bytes between the primary's and the helper's staging buffer
     int32_t warps_per_cta;  // TILES per CTA (each tile is served by a warp pair)

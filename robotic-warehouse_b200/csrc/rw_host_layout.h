@@ -78,7 +78,16 @@ static inline void rw_fill_params(RwParams &p, const rw_config &c, int64_t num_e
         p.obs_kind = cfg->observation_type;
         p.img_directional = cfg->image_directional ? 1 : 0;
         p.n_layers = cfg->n_image_layers;
-        for (int i = 0; i < 8; i++) p.img_layers[i] = cfg->image_layers[i];
+        for (int i = 0; i < 8; i++) {
+            p.img_layers[i] = cfg->image_layers[i];
+            switch (cfg->image_layers[i]) {  // see rw_obs_image_agent
+                case 0: p.img_mask[i] = RW_G_SHELF; break;
+                case 1: p.img_mask[i] = RW_G_REQ; break;
+                case 2: p.img_mask[i] = RW_G_AGENT; break;
+                case 5: p.img_mask[i] = 2u << 8; break;                        // goal flag of the static table byte
+                default: p.img_mask[i] = RW_G_AGENT | (1u << 16) | (1u << 31);  // ACCESSIBLE: inside the map and no agent
+            }
+        }
         p.L = p.n_layers * p.K + (p.obs_kind == RW_OBS_IMAGE_DICT ? 6 : 0);  // warehouse.py:365-388, 400-427
     }
     p.R = cfg->request_queue_size; p.S = S;
@@ -104,7 +113,6 @@ static inline void rw_fill_params(RwParams &p, const rw_config &c, int64_t num_e
     int stride = rw_round_up(cells, 4);       // one byte per cell
     if (((stride / 4) & 1) == 0) stride += 4;  // odd word stride: same-cell accesses of the 32 lanes hit 32 banks
     p.grid_env_stride = stride;
-    p.ga_off = 0;
     p.obs_env_bytes = n * p.L * 4;
     // Observation staging: a chunk of C consecutive worlds is assembled in shared memory and leaves as one TMA bulk
     // store (C*n*L*4 bytes, must be a 16-byte multiple).  Two lanes share an agent row (obs_parts = 2) so that a

@@ -896,18 +896,16 @@ RW_HD void rw_obs_image_agent(const RwParams &p, const RwLane &l, int i, float *
             else { si = K - 1 - oj; sj = oi; }
             const int yy = y - r + si, xx = x - r + sj;
             const bool in = (unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W;
-            uint32_t gb = 0, fl = 0;
-            if (in) { gb = l.g[yy * W + xx]; fl = l.highway[yy * W + xx]; }
-            for (int li = 0; li < p.n_layers; li++) {
-                const int ly = p.img_layers[li];
-                bool v;
-                if (ly == 0) v = (gb & RW_G_SHELF) != 0;
-                else if (ly == 1) v = (gb & RW_G_REQ) != 0;
-                else if (ly == 2) v = (gb & RW_G_AGENT) != 0;
-                else if (ly == 5) v = (fl & 2u) != 0;
-                else v = in && !(gb & RW_G_AGENT);  // ACCESSIBLE
-                out[li * KK + o] = v ? 1.0f : 0.0f;
-            }
+            // one word per window cell: occupancy byte | static table byte << 8, or only bit 16 outside the map (the
+            // reference pads with zeros, ref:573); every layer is a mask test over it (p.img_mask, bit 31 inverts)
+            uint32_t word = 1u << 16;
+            if (in) word = (uint32_t)l.g[yy * W + xx] | ((uint32_t)l.highway[yy * W + xx] << 8);
+#pragma unroll
+            for (int li = 0; li < 8; li++)
+                if (li < p.n_layers) {
+                    const uint32_t m = p.img_mask[li];
+                    out[li * KK + o] = (((word & m & 0x1ffffu) != 0) != ((m >> 31) != 0)) ? 1.0f : 0.0f;
+                }
         }
     }
     if (part == 0 && p.obs_kind == 3) {
