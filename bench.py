@@ -106,7 +106,13 @@ def cpu_baseline(env_id, overrides, target_seconds=10.0, threads=None):
     t0 = time.perf_counter()
     done, _ = oracle_py.rollout_random(env, n_envs, steps, seed=2, n_threads=threads)
     dt = time.perf_counter() - t0
-    return {"value": done / dt, "unit": "env-steps/s", "cores": threads, "kind": "port",
+    quota = None
+    try:  # the container's CFS quota, if any: `threads` host threads run, but only this many CPUs' worth of time is granted
+        q, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        quota = None if q == "max" else float(q) / float(period)
+    except Exception:
+        pass
+    return {"value": done / dt, "unit": "env-steps/s", "cores": threads, "cgroup_cpu_quota": quota, "kind": "port",
             "sample": f"{n_envs} worlds x {steps} random-action steps of {env_id} {overrides or ''} with reset on done, "
                       f"{dt:.1f} s on {threads} host threads (C oracle port; the Python reference itself cannot travel to the GPU box)",
             "seconds": dt}
@@ -338,20 +344,38 @@ def main():
     h_obs = torch.empty((E, n, L), dtype=torch.float32).pin_memory()
     h_rew = torch.empty((E, n), dtype=torch.float32).pin_memory()
     h_done = torch.empty((E,), dtype=torch.uint8).pin_memory()
-    for _ in range(3):
-        vec.backend.step_host(h_act, h_obs, h_rew, h_done)
-    torch.cuda.synchronize()
-    if dist:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        vec.backend.step_host(h_act, h_obs, h_rew, h_done)  # synchronises internally
-    e2e_s = time.perf_counter() - t0
+    def time_e2e(packed):
+        vec.backend.set_host_transport(packed)
+        for _ in range(3):
+            vec.backend.step_host(h_act, h_obs, h_rew, h_done)
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            vec.backend.step_host(h_act, h_obs, h_rew, h_done)  # synchronises internally
+        return time.perf_counter() - t0
+    e2e_plain_s = time_e2e(False)   # float32 observations over PCIe
+    e2e_s = time_e2e(True)          # default transport: one byte per value over PCIe, widened to float32 by host threads
+    packed_used = (not overrides.get("normalised_coordinates")) and E * n * L >= (1 << 20)
 
-    tot = torch.tensor([total_ms, warm_ms, e2e_s, obs_kernel_ms], dtype=torch.float64, device=dev)
+    # transport roofline of the end-to-end call: the same device->host bytes moved by a bare pinned-memory copy
+    d2h_ms = []
+    for _ in range(5):
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        h_obs.copy_(vec._obs, non_blocking=True)
+        h_rew.copy_(vec._reward, non_blocking=True)
+        h_done.copy_(vec._done, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        d2h_ms.append(c0.elapsed_time(c1))
+    d2h_ms = min(d2h_ms)
+
+    tot = torch.tensor([total_ms, warm_ms, e2e_s, obs_kernel_ms, e2e_plain_s], dtype=torch.float64, device=dev)
     if dist:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-    total_ms, warm_ms, e2e_s, obs_kernel_ms = (float(x) for x in tot.tolist())
+    total_ms, warm_ms, e2e_s, obs_kernel_ms, e2e_plain_s = (float(x) for x in tot.tolist())
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -399,8 +423,18 @@ def main():
                        "frac_of_hbm_peak": int(info["algorithmic_bytes_obs"]) * E / (obs_kernel_ms * 1e-3) / 1e9 / peak,
                        "layout_bytes_per_env": int(info["packed_bytes_obs"])},
         "e2e": {"value": world * E * e2e_steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": E * n * A * 4,
-                "d2h_bytes_per_step": E * n * L * 4 + E * n * 4 + E, "steps": e2e_steps,
-                "api": "rw_step_host (pinned host buffers, copies + kernel + sync inside the timed region)"},
+                "d2h_bytes_per_step": E * n * L * (1 if packed_used else 4) + E * n * 4 + E, "steps": e2e_steps,
+                "api": "rw_step_host: pinned host buffers in and out (int32 actions, float32 observations / rewards, uint8 done); "
+                       "copies, kernel and synchronisation inside the timed region",
+                "transport": ("packed: observation values (exact integers < 256) cross PCIe as one byte each in 8 chunks and are "
+                              "widened to float32 into the caller's buffer by the library's host threads while the next chunk is "
+                              "in flight; results bit-identical to the plain copy") if packed_used else "plain float32 copy",
+                "ms_per_step": e2e_s / e2e_steps * 1e3,
+                "plain_float32_transport": {"value": world * E * e2e_steps / e2e_plain_s, "ms_per_step": e2e_plain_s / e2e_steps * 1e3,
+                                            "d2h_bytes_per_step": E * n * L * 4 + E * n * 4 + E,
+                                            "bare_d2h_copy_ms": d2h_ms,
+                                            "pcie_d2h_gbs": (E * n * L * 4 + E * n * 4 + E) / (d2h_ms * 1e-3) / 1e9,
+                                            "frac_of_transport": d2h_ms / (e2e_plain_s / e2e_steps * 1e3)}},
         "gpu_launches": args.steps,
         "clocks": clocks,
         "wall_s_timed_region": t_wall,

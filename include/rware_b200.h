@@ -158,6 +158,17 @@ int rw_error_count(rw_handle *h, int64_t *out, void *stream);
  * to the device, runs rw_step, copies obs/reward/done back and synchronises.  Any output pointer may be NULL. */
 int rw_step_host(rw_handle *h, const int32_t *actions_host, float *obs_host, float *reward_host, uint8_t *done_host);
 int rw_reset_host(rw_handle *h, const uint64_t *seeds_host, float *obs_host);
+/* Transport of rw_step_host.  The call is bound by PCIe (74 MB of float32 observations per step of 65 536 tiny-4ag worlds), and
+ * every observation value is an exact integer < 256 unless normalised_coordinates is set.  With the packed transport (default
+ * for batches of >= 2^20 values) the device sends one byte per value in chunks and a pool of host threads widens each chunk to
+ * float32 into obs_host while the next one is in flight; the buffers the caller gets back are bit-identical either way.
+ * Host threads and host memory bandwidth are shared resources, so the call times itself: it samples the plain copy on its
+ * third call and every 64 calls, and serves 64 calls with plain copies whenever two packed calls in a row were 25 % slower
+ * than the plain estimate.  rw_set_host_transport(h, 0) selects the plain float32 copy for good, (h, 1) the adaptive default.  Environment: RWARE_B200_HOST_PACK=0|1, RWARE_B200_HOST_THREADS. */
+int rw_set_host_transport(rw_handle *h, int packed);
+/* The widening step alone (dst[i] = (float)src[i] with the same thread pool); returns the number of threads used.  Needs no GPU:
+ * exposed so that the host half of the transport can be tested where there is none. */
+int rw_host_widen_u8(const uint8_t *src, float *dst, int64_t n);
 int rw_host_alloc(void **out, int64_t bytes); /* cudaHostAlloc */
 int rw_host_free(void *p);
 

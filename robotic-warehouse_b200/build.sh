@@ -15,10 +15,12 @@ $NVCC $FLAGS -c -o build/rw_kernels.o csrc/rw_kernels.cu "$@" > build/rw_kernels
 pids+=($!)
 $NVCC $FLAGS -c -o build/rw_views.o csrc/rw_views.cu "$@" > build/rw_views.log 2>&1 &
 pids+=($!)
+g++ -O3 -std=c++17 -fPIC -pthread -c -o build/rw_hostpack.o csrc/rw_hostpack.cpp > build/rw_hostpack.log 2>&1 &
+pids+=($!)
 $NVCC $FLAGS -c -o build/rw_capi.o csrc/rw_capi.cu "$@" > build/rw_capi.log 2>&1 &
 pids+=($!)
 fail=0
 for p in "${pids[@]}"; do wait "$p" || fail=1; done
 cat build/*.log
 if [ "$fail" != 0 ]; then echo "nvcc failed" >&2; exit 1; fi
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared --cudart static -o lib/librware_b200.so build/rw_inst_*.o build/rw_kernels.o build/rw_views.o build/rw_capi.o
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared --cudart static -o lib/librware_b200.so build/rw_inst_*.o build/rw_kernels.o build/rw_views.o build/rw_hostpack.o build/rw_capi.o -lpthread

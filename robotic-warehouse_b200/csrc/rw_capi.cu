@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <ctime>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -29,6 +30,15 @@ struct rw_handle {
     float *d_obs = nullptr, *d_reward = nullptr;
     uint8_t *d_done = nullptr;
     cudaStream_t host_stream = nullptr;
+    // packed transport of rw_step_host: byte image of the observations on the device and in pinned host memory
+    uint8_t *d_pack = nullptr, *h_pack = nullptr;
+    cudaEvent_t pack_ev[8] = {};
+    int host_pack = 1;
+    // the packed transport depends on host threads and host memory bandwidth, which other tenants of the machine can take
+    // away; rw_step_host times its own calls and falls back to the plain copy while that one is measured faster
+    double us_packed = 0, us_plain = 0;  // smoothed call durations, 0 = not measured yet
+    int64_t host_calls = 0;
+    int slow_streak = 0, plain_until = 0;
     // fused push all-gather
     void *d_gather = nullptr;
     void *peer_base[RW_MAX_PEERS] = {};
@@ -141,6 +151,10 @@ static int create_impl(rw_handle *h, const rw_config *cfg, int64_t num_envs, int
         while (wpc > 1 && p.sm_cta_bytes + wpc * p.sm_warp_bytes > smem_cap) wpc--;
         p.warps_per_cta = wpc;
     }
+    // packed host transport: on by default unless more than 4 ranks share this node's memory controllers (then the plain copy,
+    // which only loads the PCIe links, is the safer choice); RWARE_B200_HOST_PACK overrides
+    if (const char *lw = getenv("LOCAL_WORLD_SIZE")) h->host_pack = atoi(lw) <= 4;
+    if (getenv("RWARE_B200_HOST_PACK")) h->host_pack = atoi(getenv("RWARE_B200_HOST_PACK")) != 0;
     if (getenv("RWARE_B200_FORCE_DYNAMIC")) rw_force_dynamic_kernels(atoi(getenv("RWARE_B200_FORCE_DYNAMIC")) != 0);
     CK(rw_configure_kernels(p, p.sm_cta_bytes + p.sm_warp_bytes * p.warps_per_cta));
 
@@ -208,6 +222,11 @@ extern "C" {
 int rw_destroy(rw_handle *h) {
     if (!h) return RW_OK;
     cudaSetDevice(h->device);
+    if (h->d_pack) {
+        cudaFree(h->d_pack);
+        cudaFreeHost(h->h_pack);
+        for (auto &e : h->pack_ev) if (e) cudaEventDestroy(e);
+    }
     cudaFree(h->d_highway); cudaFree(h->d_home); cudaFree(h->d_home_id); cudaFree(h->d_cta_tables); cudaFree(h->d_normx); cudaFree(h->d_normy);
     cudaFree(h->d_state); cudaFree(h->d_rng); cudaFree(h->d_err);
     for (int r = 0; r < h->gather_world; r++)
@@ -462,14 +481,99 @@ int rw_step_host(rw_handle *h, const int32_t *actions_host, float *obs_host, flo
     if (rc) return rc;
     const RwParams &p = h->p;
     cudaStream_t st = h->host_stream;
+    const size_t n_obs = (size_t)p.E * p.n * p.L;
+    // The call is bound by PCIe.  Observation values are exact integers < 256 unless the coordinates are normalised, so
+    // large batches travel as one byte per value (4x fewer bytes) in 8 chunks and are widened to float32 by the host pool
+    // while the following chunk is in flight.  Small batches and normalised coordinates take the plain float32 copy.
+    bool pack = obs_host && h->host_pack && !p.norm_coords && n_obs >= ((size_t)1 << 20);
+    const bool adaptive = pack;
+    auto wall_us = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
+    const double t_call = wall_us();
+    if (adaptive) {
+        const int64_t k = h->host_calls++;
+        if (k == 2 || (k > 2 && k % 64 == 0)) pack = false;       // sample the plain copy now and then
+        else if (k < (int64_t)h->plain_until) pack = false;       // serving a fallback period
+    }
+    struct PoolGuard {  // the pool is woken first, so that its wake-up latency hides behind the copies and the kernel
+        bool on;
+        explicit PoolGuard(bool use, const void *dst) : on(use) { if (on) rw_hostpack_begin(dst); }
+        ~PoolGuard() { if (on) rw_hostpack_end(); }
+    } pool(pack, obs_host);
     CK(cudaMemcpyAsync(h->d_actions, actions_host, (size_t)p.E * p.n * p.A * 4, cudaMemcpyHostToDevice, st));
     rc = rw_step(h, h->d_actions, obs_host ? h->d_obs : nullptr, h->d_reward, h->d_done, st);
     if (rc) return rc;
-    if (obs_host) CK(cudaMemcpyAsync(obs_host, h->d_obs, (size_t)p.E * p.n * p.L * 4, cudaMemcpyDeviceToHost, st));
+    if (pack) {
+        if (!h->d_pack) {
+            CK(cudaMalloc(&h->d_pack, n_obs + 64));
+            CK(cudaHostAlloc((void **)&h->h_pack, n_obs + 64, cudaHostAllocDefault));
+            for (auto &e : h->pack_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        CK(rw_launch_pack_u8(h->d_obs, h->d_pack, n_obs, st));
+        const int NCH = 8;
+        const size_t per = ((n_obs + NCH - 1) / NCH + 255) & ~(size_t)255;
+        for (int c = 0; c < NCH; c++) {
+            const size_t a = (size_t)c * per, len = a >= n_obs ? 0 : (a + per > n_obs ? n_obs - a : per);
+            if (len) CK(cudaMemcpyAsync(h->h_pack + a, h->d_pack + a, len, cudaMemcpyDeviceToHost, st));
+            CK(cudaEventRecord(h->pack_ev[c], st));
+        }
+    } else if (obs_host) {
+        CK(cudaMemcpyAsync(obs_host, h->d_obs, n_obs * 4, cudaMemcpyDeviceToHost, st));
+    }
     if (reward_host) CK(cudaMemcpyAsync(reward_host, h->d_reward, (size_t)p.E * p.n * 4, cudaMemcpyDeviceToHost, st));
     if (done_host) CK(cudaMemcpyAsync(done_host, h->d_done, (size_t)p.E, cudaMemcpyDeviceToHost, st));
+    if (pack) {
+        const int NCH = 8;
+        const size_t per = ((n_obs + NCH - 1) / NCH + 255) & ~(size_t)255;
+        static const bool trace = getenv("RWARE_B200_HOST_TRACE") != nullptr;  // diagnostics: where the call spends its time
+        auto now_us = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
+        double tw[NCH], te[NCH];
+        const double t1 = trace ? now_us() : 0;
+        cudaError_t err = cudaSuccess;
+        for (int c = 0; c < NCH && err == cudaSuccess; c++) {
+            const size_t a = (size_t)c * per, len = a >= n_obs ? 0 : (a + per > n_obs ? n_obs - a : per);
+            err = cudaEventSynchronize(h->pack_ev[c]);
+            if (trace) tw[c] = now_us();
+            if (err == cudaSuccess && len) rw_hostpack_widen(h->h_pack + a, obs_host + a, len);
+            if (trace) te[c] = now_us();
+        }
+        if (trace) {
+            fprintf(stderr, "[rw_step_host]");
+            for (int c = 0; c < NCH; c++) fprintf(stderr, " c%d wait %.0f widen %.0f;", c, tw[c] - (c ? te[c - 1] : t1), te[c] - tw[c]);
+            fprintf(stderr, " threads %d\n", rw_hostpack_threads());
+        }
+        CK(err);
+    }
     CK(cudaStreamSynchronize(st));
+    if (adaptive) {
+        const double us = wall_us() - t_call;
+        double &avg = pack ? h->us_packed : h->us_plain;
+        avg = avg == 0 ? us : 0.75 * avg + 0.25 * us;
+        if (pack && h->us_plain > 0 && us > 1.25 * h->us_plain) {
+            if (++h->slow_streak >= 2) {  // two slow packed calls in a row: plain copies for the next 64 calls
+                h->plain_until = (int)(h->host_calls + 64);
+                h->slow_streak = 0;
+                h->us_packed = 0;
+            }
+        } else if (pack) {
+            h->slow_streak = 0;
+        }
+    }
     return RW_OK;
+}
+
+int rw_set_host_transport(rw_handle *h, int packed) {
+    if (!h) return RW_EINVAL;
+    h->host_pack = packed ? 1 : 0;
+    h->host_calls = 0; h->us_packed = h->us_plain = 0; h->slow_streak = 0; h->plain_until = 0;
+    return RW_OK;
+}
+
+int rw_host_widen_u8(const uint8_t *src, float *dst, int64_t n) {
+    if (!src || !dst || n < 0) return RW_EINVAL;
+    rw_hostpack_begin(dst);
+    rw_hostpack_widen(src, dst, (size_t)n);
+    rw_hostpack_end();
+    return rw_hostpack_threads();
 }
 
 int rw_reset_host(rw_handle *h, const uint64_t *seeds_host, float *obs_host) {

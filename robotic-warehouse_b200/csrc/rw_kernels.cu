@@ -96,6 +96,22 @@ __global__ void rw_random_actions_kernel(const RwParams p, int32_t *__restrict__
     for (int b = 0; b < p.msg_bits; b++) actions[idx * p.A + 1 + b] = (int32_t)((z >> b) & 1ULL);
 }
 
+// Transport packing for rw_step_host: observations are exact integers < 256 stored as float32; four of them become one 32-bit
+// word of bytes (widened back on the host, rw_hostpack.cpp).
+__global__ void rw_pack_u8_kernel(const float *__restrict__ in, uint8_t *__restrict__ out, size_t n) {
+    const size_t n4 = n / 4, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = reinterpret_cast<const float4 *>(in)[i];
+        reinterpret_cast<uint32_t *>(out)[i] = (uint32_t)v.x | ((uint32_t)v.y << 8) | ((uint32_t)v.z << 16) | ((uint32_t)v.w << 24);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) out[n4 * 4 + threadIdx.x] = (uint8_t)in[n4 * 4 + threadIdx.x];
+}
+
+cudaError_t rw_launch_pack_u8(const float *in, uint8_t *out, size_t n, cudaStream_t stream) {
+    rw_pack_u8_kernel<<<148 * 8, 256, 0, stream>>>(in, out, n);
+    return cudaGetLastError();
+}
+
 // L2 flush for benchmarks: streams `bytes` of writes through the L2 with the SAME shared-memory carve-out as the step
 // kernel (a flush kernel with a different carve-out makes the next launch pay an SM reconfiguration).
 __global__ void rw_flush_l2_kernel(int4 *buf, size_t n16, int value) {

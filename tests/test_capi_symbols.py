@@ -48,3 +48,23 @@ def test_product_path_raises_without_cuda():
         pytest.skip("CUDA present")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         rware_b200.make("rware-tiny-2ag-v2")
+
+
+def test_host_widening_of_the_packed_transport():
+    """rw_host_widen_u8: the host half of rw_step_host's packed transport (one byte per observation value over PCIe, widened
+    to float32 by a thread pool).  Needs no GPU: exact for every byte value, any length and alignment, repeated calls."""
+    import numpy as np
+    from rware_b200 import _capi
+    lib = _capi.load_library()
+    rs = np.random.default_rng(0)
+    for n in (0, 1, 7, 31, 32, 33, 255, 256, 1000, 4097, 300_001, 2_000_003):
+        for shift in (0, 1, 5):
+            src = rs.integers(0, 256, size=n, dtype=np.uint8)
+            if n >= 256:
+                src[:256] = np.arange(256, dtype=np.uint8)
+            buf = np.full(n + 16, -1.0, np.float32)
+            dst = buf[shift:shift + n]
+            threads = lib.rw_host_widen_u8(src.ctypes.data, dst.ctypes.data, n)
+            assert threads >= 1
+            assert np.array_equal(dst, src.astype(np.float32)), (n, shift)
+            assert np.all(buf[:shift] == -1.0) and np.all(buf[shift + n:] == -1.0)  # nothing written outside

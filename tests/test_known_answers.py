@@ -92,11 +92,15 @@ def test_full_size_batch_properties_and_sampled_oracle_parity():
 
 
 @pytest.mark.gpu
-def test_host_buffer_entry_points_match_the_device_ones():
-    """rw_reset_host / rw_step_host (pinned host buffers, the end-to-end path of bench.py) against rw_reset / rw_step."""
-    E = 1000
-    a = rware_b200.make_vec("rware-small-4ag-v1", E)
-    b = rware_b200.make_vec("rware-small-4ag-v1", E)
+@pytest.mark.parametrize("E,packed,kw", [(1000, True, {}), (6000, True, {}), (6000, False, {}), (5000, True, {"normalised_coordinates": True}),
+                                         (4099, True, {"msg_bits": 2})],
+                         ids=["small-batch-plain-copy", "packed-transport", "plain-transport", "normalised-falls-back", "packed-ragged-msg"])
+def test_host_buffer_entry_points_match_the_device_ones(E, packed, kw):
+    """rw_reset_host / rw_step_host (pinned host buffers, the end-to-end path of bench.py) against rw_reset / rw_step, with the
+    packed transport (one byte per value over PCIe, widened on the host; batches of >= 2^20 values) and the plain float32 copy."""
+    a = rware_b200.make_vec("rware-small-4ag-v1", E, **kw)
+    b = rware_b200.make_vec("rware-small-4ag-v1", E, **kw)
+    b.backend.set_host_transport(packed)
     seeds = np.arange(E, dtype=np.uint64) + 9
     obs_d = a.reset(seed=seeds).cpu()
     h_obs = torch.empty((E, 4, a.obs_len), dtype=torch.float32).pin_memory()
@@ -106,7 +110,8 @@ def test_host_buffer_entry_points_match_the_device_ones():
     assert torch.equal(h_obs, obs_d)
     g = torch.Generator().manual_seed(1)
     for _ in range(25):
-        acts = torch.randint(0, 5, (E, 4), generator=g, dtype=torch.int32).pin_memory()
+        acts = torch.cat([torch.randint(0, 5, (E, 4, 1), generator=g, dtype=torch.int32),
+                          torch.randint(0, 2, (E, 4, a.msg_bits), generator=g, dtype=torch.int32)], dim=2).contiguous().pin_memory()
         obs_d, rew_d, done_d = a.step(acts.cuda())
         b.backend.step_host(acts, h_obs, h_rew, h_done)
         assert torch.equal(h_obs, obs_d.cpu()) and torch.equal(h_rew, rew_d.cpu()) and torch.equal(h_done, done_d.cpu())
