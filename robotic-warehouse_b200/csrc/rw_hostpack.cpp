@@ -209,10 +209,18 @@ int default_threads() {
 
 }  // namespace
 
+// a forked child inherits the pool object but none of its threads: start over there (the parent's pool is simply abandoned)
+static void rw_hostpack_after_fork_in_child() {
+    g_pool = nullptr;
+    pthread_mutex_init(&g_pool_mu, nullptr);
+}
+
 // internal interface used by rw_capi.cu
 void rw_hostpack_begin(const void *dst) {
     pthread_mutex_lock(&g_pool_mu);
     if (!g_pool) {
+        static const int registered = pthread_atfork(nullptr, nullptr, rw_hostpack_after_fork_in_child);
+        (void)registered;
         g_pool = new Pool();
         g_pool->start(default_threads());
     }

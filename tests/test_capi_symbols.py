@@ -68,3 +68,33 @@ def test_host_widening_of_the_packed_transport():
             assert threads >= 1
             assert np.array_equal(dst, src.astype(np.float32)), (n, shift)
             assert np.all(buf[:shift] == -1.0) and np.all(buf[shift + n:] == -1.0)  # nothing written outside
+
+
+def test_host_widening_from_several_threads_and_after_fork():
+    """The pool serves one widening at a time (callers queue on a mutex) and a forked child starts its own pool."""
+    import os
+    import threading
+    import numpy as np
+    from rware_b200 import _capi
+    lib = _capi.load_library()
+    n = 500_000
+    srcs = [np.random.default_rng(k).integers(0, 256, size=n, dtype=np.uint8) for k in range(4)]
+    dsts = [np.zeros(n, np.float32) for _ in range(4)]
+
+    def work(k):
+        for _ in range(5):
+            lib.rw_host_widen_u8(srcs[k].ctypes.data, dsts[k].ctypes.data, n)
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for k in range(4):
+        assert np.array_equal(dsts[k], srcs[k].astype(np.float32))
+    pid = os.fork()
+    if pid == 0:  # child: the parent's worker threads do not exist here
+        out = np.zeros(n, np.float32)
+        lib.rw_host_widen_u8(srcs[0].ctypes.data, out.ctypes.data, n)
+        os._exit(0 if np.array_equal(out, srcs[0].astype(np.float32)) else 1)
+    _, status = os.waitpid(pid, 0)
+    assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0
