@@ -150,6 +150,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="tiny-4ag", choices=sorted(WORKLOADS))
     ap.add_argument("--envs", type=int, default=None, help="worlds per GPU (default: the workload's)")
+    ap.add_argument("--p-forward", type=float, default=None,
+                    help="action distribution: P(FORWARD) = p, the other four actions share the rest (default: uniform); "
+                         "0.68 is the dense-collision stress of SURVEY.md section 8(d)")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--ref-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -197,6 +200,11 @@ def main():
     actions = [torch.empty((E, n, A), dtype=torch.int32, device=dev) for _ in range(RING)]
     for i, a in enumerate(actions):
         vec.backend.random_actions(a, 12345 + rank, i)
+        if args.p_forward is not None:  # dense-collision stress: FORWARD with probability p
+            g = torch.Generator(device=dev).manual_seed(777 + 16 * rank + i)
+            u = torch.rand((E, n), device=dev, generator=g)
+            other = torch.tensor([0, 2, 3, 4], device=dev, dtype=torch.int32)[torch.randint(0, 4, (E, n), device=dev, generator=g)]
+            a[..., 0] = torch.where(u < args.p_forward, torch.ones_like(other), other)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
     def do_flush(i):
         if args.flush_with == "torch":
@@ -400,7 +408,8 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": kernel_ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32 (state) / float32 (obs)",
         "data": "synthetic",
-        "config": {"workload": f"{env_id} {overrides or ''}".strip() + f", {E} worlds per GPU, random-action rollout, auto-reset",
+        "config": {"workload": f"{env_id} {overrides or ''}".strip() + f", {E} worlds per GPU, random-action rollout"
+                               + (f" with P(FORWARD)={args.p_forward}" if args.p_forward is not None else " (uniform actions)") + ", auto-reset",
                    "worlds_per_gpu": E, "n_agents": n, "obs_len": L, "parallelism": f"dp{world} (independent worlds, no exchange"
                    + (f", obs/reward/done all-gathered ({args.gather})" if args.gather and world > 1 else "") + ")",
                    "l2": {"rotate": f"inputs larger than L2: launches rotate over {NSETS} independent world sets "
