@@ -61,8 +61,9 @@ typedef struct rw_config {
                                      host facade), RW_OBS_IMAGE or RW_OBS_IMAGE_DICT (warehouse.py:527-596, 726-742) */
     int32_t image_directional;    /* image_observation_directional (warehouse.py:584-595) */
     int32_t n_image_layers;       /* 0..7 */
-    int32_t image_layers[8];      /* RW_LAYER_*; AGENT_DIRECTION / AGENT_LOAD are rejected: the reference writes them with
-                                     transposed indices (warehouse.py:552, 558) and raises IndexError off the diagonal */
+    int32_t image_layers[8];      /* RW_LAYER_*; AGENT_DIRECTION / AGENT_LOAD are written as the reference writes them, with
+                                     transposed indices (warehouse.py:552, 558); worlds where numpy raises IndexError for that
+                                     are counted in rw_error_count once per observation pass */
     const uint8_t *highways;      /* [grid_h*grid_w], row-major [y][x], 1 = highway (warehouse.py:308-326) */
     const int32_t *goals_xy;      /* [n_goals][2] = (x, y) in the reference's order (warehouse.py:303-306, 344-345) */
 } rw_config;
@@ -150,7 +151,7 @@ int rw_get_state(rw_handle *h, const rw_state_view *dev, void *stream);
 int rw_set_state(rw_handle *h, const rw_state_view *dev, void *stream);
 
 /* Count of invalid action values seen so far (the reference raises ValueError from Action(a), warehouse.py:811-814;
- * the batched kernel treats them as NOOP and counts them), plus the worlds whose transposed global-image layers would have
+ * the batched kernel treats them as NOOP and counts them), plus the worlds whose transposed image layers (local or global) would have
  * raised IndexError (see rw_global_image).  Synchronises `stream`. */
 int rw_error_count(rw_handle *h, int64_t *out, void *stream);
 

@@ -87,9 +87,6 @@ int rw_create(const rw_config *cfg, int64_t num_envs, int device, rw_handle **ou
         for (int i = 0; i < cfg->n_image_layers; i++) {
             int ly = cfg->image_layers[i];
             if (ly < 0 || ly > 6) return fail(h, RW_EINVAL, "bad image layer");
-            if (ly == RW_LAYER_AGENT_DIRECTION || ly == RW_LAYER_AGENT_LOAD)
-                return fail(h, RW_EINVAL, "image layers AGENT_DIRECTION / AGENT_LOAD are not supported: the reference writes them with "
-                                          "transposed indices (warehouse.py:552, 558) and raises IndexError off the diagonal");
         }
     }
     const int H = cfg->grid_h, W = cfg->grid_w, cells = H * W, n = cfg->n_agents;

@@ -58,7 +58,9 @@ struct RwParams {
     int32_t goal_cell[RW_MAX_GOALS];
     int32_t obs_kind;             // 0 flattened vector, 2 image, 3 image + features (ObservationType values)
     int32_t img_directional, n_layers, img_layers[8];
-    uint32_t img_mask[8];         // per image layer: test mask over (grid byte | table byte << 8 | outside-the-map << 16), bit 31 = invert
+    uint32_t img_mask[8];         // per image layer: test mask over (grid byte | table byte << 8 | outside-the-map << 16), bit 31 = invert;
+                                  // bit 30: transposed agent layer (AGENT_DIRECTION / AGENT_LOAD), low bits = the layer id
+    int32_t img_transposed;       // bit 0: AGENT_DIRECTION configured, bit 1: AGENT_LOAD configured
     // tile layout
     int32_t nw, w_agent, w_msg, w_shelf, w_queue, w_steps, w_inact;
     // static device tables

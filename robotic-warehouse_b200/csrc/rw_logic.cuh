@@ -904,8 +904,39 @@ RW_HD void rw_obs_image_agent(const RwParams &p, const RwLane &l, int i, float *
             for (int li = 0; li < 8; li++)
                 if (li < p.n_layers) {
                     const uint32_t m = p.img_mask[li];
-                    out[li * KK + o] = (((word & m & 0x1ffffu) != 0) != ((m >> 31) != 0)) ? 1.0f : 0.0f;
+                    float v;
+                    if (m & (1u << 30)) {
+                        // AGENT_DIRECTION / AGENT_LOAD: the reference writes layer[ag.x, ag.y] (sic, ref:552, 558), so
+                        // window cell [yy][xx] shows the agent that stands at column yy, row xx
+                        v = 0.0f;
+                        if (in && xx < H && yy < W) {
+                            const uint32_t id = (uint32_t)l.g[xx * W + yy] & RW_G_AGENT;
+                            if (id) {
+                                const uint32_t ow = rw_agent(l, (int)id - 1);
+                                v = (m & 7u) == 3u ? (float)(rw_adir(ow) + 1) : (rw_acarry(ow) ? 1.0f : 0.0f);
+                            }
+                        }
+                    } else {
+                        v = (((word & m & 0x1ffffu) != 0) != ((m >> 31) != 0)) ? 1.0f : 0.0f;
+                    }
+                    out[li * KK + o] = v;
                 }
+        }
+    }
+    // where numpy raises IndexError for the transposed writes (an agent with x >= H or y >= W) the world is counted once
+    // per observation pass (by the lane of its first agent) and the offending entries are simply absent
+    if (p.img_transposed && i == 0 && part == 0) {
+        int bad = 0;
+        for (int a = 0; a < C::n(p); a++) {
+            const uint32_t ow = rw_agent(l, a);
+            if ((rw_ax(ow) >= H || rw_ay(ow) >= W) && ((p.img_transposed & 1) || rw_acarry(ow))) bad = 1;
+        }
+        if (bad) {
+#if defined(__CUDA_ARCH__)
+            atomicAdd(p.err_count, 1ULL);
+#else
+            *p.err_count += 1;
+#endif
         }
     }
     if (part == 0 && p.obs_kind == 3) {

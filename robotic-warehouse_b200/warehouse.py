@@ -271,6 +271,13 @@ class Warehouse:
         if self.observation_type == ObservationType.DICT:
             return tuple(self._unflatten(o[i], a) for i, a in enumerate(self.agents))
         K, C = 1 + 2 * self.sensor_range, len(self.image_observation_layers)
+        for layer in self.image_observation_layers:  # layer[ag.x, ag.y] (sic, 552 / 558): numpy's IndexError, raised like there
+            if layer in (ImageLayer.AGENT_DIRECTION, ImageLayer.AGENT_LOAD):
+                for ag in self.agents:
+                    if (layer == ImageLayer.AGENT_DIRECTION or ag.carrying_shelf is not None) and (
+                            ag.x >= self.grid_size[0] or ag.y >= self.grid_size[1]):
+                        axis, bad = (0, ag.x) if ag.x >= self.grid_size[0] else (1, ag.y)
+                        raise IndexError(f"index {bad} is out of bounds for axis {axis} with size {self.grid_size[axis]}")
         imgs = [o[i, : C * K * K].reshape(C, K, K).copy() for i in range(self.n_agents)]
         if self.observation_type == ObservationType.IMAGE:
             return tuple(imgs)

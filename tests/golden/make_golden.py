@@ -256,6 +256,67 @@ def record_global_images(wh):
         json.dump(meta, f)
 
 
+def record_image_transposed(wh):
+    """IMAGE observations with the AGENT_DIRECTION / AGENT_LOAD layers (warehouse.py:548-558: `layer[ag.x, ag.y]`, sic): a
+    square map where the transposed writes always land inside the layer, and rware-tiny (11 x 10) where numpy raises IndexError
+    as soon as an agent reaches the bottom row."""
+    OT, IL = wh.ObservationType, wh.ImageLayer
+    cases = {
+        "square_directional": dict(kw=dict(shelf_columns=1, column_height=1, shelf_rows=1,
+                                           layout="..x..x.\n.xx.xx.\n.......\nx..g..x\n.x...x.\n..xgx..\n......."), n=6, r=1,
+                                   directional=True, layers=[IL.AGENT_DIRECTION, IL.SHELVES, IL.AGENT_LOAD, IL.AGENTS]),
+        "square_r2_plain": dict(kw=dict(shelf_columns=1, column_height=1, shelf_rows=1,
+                                        layout="..x..x.\n.xx.xx.\n.......\nx..g..x\n.x...x.\n..xgx..\n......."), n=4, r=2,
+                                directional=False, layers=[IL.AGENT_LOAD, IL.AGENT_DIRECTION]),
+        "tiny_raises": dict(kw=dict(shelf_columns=3, column_height=8, shelf_rows=1), n=5, r=1, directional=True,
+                            layers=[IL.AGENTS, IL.AGENT_DIRECTION, IL.AGENT_LOAD]),
+    }
+    out, meta = {}, {}
+    for name, cs in cases.items():
+        n = cs["n"]
+        kwargs = dict(n_agents=n, msg_bits=0, sensor_range=cs["r"], request_queue_size=3, max_inactivity_steps=None, max_steps=70,
+                      reward_type=wh.RewardType.INDIVIDUAL, observation_type=OT.IMAGE, image_observation_layers=cs["layers"],
+                      image_observation_directional=cs["directional"], **cs["kw"])
+        env = wh.Warehouse(**kwargs)
+        rs = np.random.default_rng(40 + len(name))
+        T = 140
+        acts = rs.choice(5, size=(T, n), p=[.05, .5, .1, .1, .25]).astype(np.int8)
+        K = 2 * cs["r"] + 1
+        imgs, raised = [], []
+
+        def keep(fn):
+            try:
+                obs = fn()
+                imgs.append(np.stack(obs).astype(np.float32))
+                raised.append(0)
+            except IndexError:
+                imgs.append(np.zeros((n, len(cs["layers"]), K, K), np.float32))
+                raised.append(1)
+        keep(lambda: env.reset(seed=9)[0])
+        for t in range(T):
+            done_box = []
+
+            def one():
+                o, _, d, _, _ = env.step([int(a) for a in acts[t]])
+                done_box.append(d)
+                return o
+            keep(one)
+            # a raising step has still advanced the state (the exception comes from the observation code at the end of step)
+            if (done_box and done_box[0]) or (not done_box and env._cur_steps >= env.max_steps):
+                keep(lambda: env.reset()[0])
+                imgs.pop(-2)
+                raised.pop(-2)
+        out[name + "_images"] = np.stack(imgs)
+        out[name + "_raised"] = np.asarray(raised, np.uint8)
+        out[name + "_actions"] = acts
+        meta[name] = dict(kwargs={k: (v.value if hasattr(v, "value") else ([x.value for x in v] if isinstance(v, list) else v))
+                                  for k, v in kwargs.items()}, seed=9)
+        print("transposed-image fixture", name, out[name + "_images"].shape, "raised", int(sum(raised)))
+    np.savez_compressed(os.path.join(HERE, "image_transposed.npz"), **out)
+    with open(os.path.join(HERE, "image_transposed.json"), "w") as f:
+        json.dump(meta, f)
+
+
 def record_registry_ids(gym):
     """id -> kwargs of the reference's optional registrations (rware/__init__.py:42-172): every image id and a random sample
     of the 5.25 million full_registration ids (enumerating them takes ~30 s)."""
@@ -281,6 +342,9 @@ def record_registry_ids(gym):
 
 def main():
     gym, wh = refenv.load_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "image_transposed":
+        record_image_transposed(wh)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "registry":
         record_registry_ids(gym)
         return
@@ -306,6 +370,7 @@ def main():
     layouts(wh)
     record_obs_types(wh)
     record_global_images(wh)
+    record_image_transposed(wh)
     record_registry_ids(gym)
 
 

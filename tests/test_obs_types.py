@@ -120,14 +120,108 @@ def test_batched_image_observations_match_the_oracle(otype, layers, directional,
                 o.reset()
 
 
-def test_transposed_layers_are_rejected_by_the_cuda_abi():
-    """AGENT_DIRECTION / AGENT_LOAD: the reference indexes them [x, y] (warehouse.py:552, 558) and raises IndexError
-    off the diagonal; the C ABI refuses them instead of reproducing that."""
-    import ctypes
-    from rware_b200 import _capi
-    lib = _capi.load_library()
-    cfg = _capi.EnvConfig(np.zeros((4, 4), np.uint8), [(0, 0)], n_agents=1, observation_type=2, image_layers=(0, 3))
-    h = ctypes.c_void_p()
-    s = cfg.to_struct()
-    assert lib.rw_create(ctypes.byref(s), 4, 0, ctypes.byref(h)) == -1
-    assert b"transposed" in lib.rw_last_error(None)
+TX = np.load(os.path.join(HERE, "golden", "image_transposed.npz"))
+with open(os.path.join(HERE, "golden", "image_transposed.json")) as f:
+    TXMETA = json.load(f)
+
+
+def _tx_layout(k):
+    if k.get("layout"):
+        return rware_b200.layout_from_str(k["layout"])
+    return rware_b200.layout_from_params(k["shelf_columns"], k["shelf_rows"], k["column_height"])
+
+
+@pytest.mark.parametrize("name", sorted(TXMETA))
+def test_oracle_transposed_image_layers_match_the_reference(name):
+    """AGENT_DIRECTION / AGENT_LOAD in the local IMAGE observations: `layer[ag.x, ag.y]` (sic, warehouse.py:552, 558), including
+    the steps where numpy raises IndexError in the reference (tests/golden/image_transposed.*)."""
+    k = TXMETA[name]["kwargs"]
+    _, hw, goals = _tx_layout(k)
+    orc = oracle_py.OracleEnv(hw, goals, k["n_agents"], 0, k["sensor_range"], k["request_queue_size"], None, k["max_steps"],
+                              k["reward_type"])
+    imgs, raised, acts = TX[name + "_images"], TX[name + "_raised"], TX[name + "_actions"]
+    layers, directional = k["image_observation_layers"], k["image_observation_directional"]
+
+    def check(t):
+        if raised[t]:
+            with pytest.raises(IndexError):
+                orc.obs_image(layers, directional)
+        else:
+            assert np.array_equal(orc.obs_image(layers, directional), imgs[t]), (name, t)
+    orc.reset(TXMETA[name]["seed"])
+    check(0)
+    for t, a in enumerate(acts):
+        _, _, done = orc.step(a.astype(np.int32))
+        if done:
+            orc.reset()
+        check(t + 1)
+
+
+@pytest.mark.parametrize("backend", backend_params())
+@pytest.mark.parametrize("name", sorted(TXMETA))
+def test_facade_transposed_image_layers_match_the_reference(name, backend):
+    k = dict(TXMETA[name]["kwargs"])
+    k["reward_type"] = RewardType(k["reward_type"])
+    k["observation_type"] = ObservationType(k["observation_type"])
+    k["image_observation_layers"] = [ImageLayer(v) for v in k["image_observation_layers"]]
+    env = Warehouse(_backend_factory=backend_factory(backend), **k)
+    imgs, raised, acts = TX[name + "_images"], TX[name + "_raised"], TX[name + "_actions"]
+
+    if raised[0]:
+        with pytest.raises(IndexError):
+            env.reset(seed=TXMETA[name]["seed"])
+    else:
+        obs, _ = env.reset(seed=TXMETA[name]["seed"])
+        assert np.array_equal(np.stack(obs), imgs[0])
+    for t, a in enumerate(acts):
+        # imgs[t + 1] / raised[t + 1]: what the caller continues from after step t (the reset observation when it ended the episode)
+        steps_before = int(env._vec.get_state()["cur_steps"][0].item())
+        try:
+            obs, _, done, _, _ = env.step([int(v) for v in a])
+            step_raised = False
+        except IndexError:
+            step_raised, done = True, steps_before + 1 >= k["max_steps"]  # a raising step has still advanced the state
+        if done:
+            try:
+                obs, _ = env.reset()
+                step_raised = False
+            except IndexError:
+                step_raised = True
+        assert step_raised == bool(raised[t + 1]), (name, t)
+        if not step_raised:
+            assert np.array_equal(np.stack(obs), imgs[t + 1]), (name, t)
+    assert raised.sum() > 0 or name != "tiny_raises"
+
+
+@pytest.mark.parametrize("backend", backend_params())
+def test_batched_transposed_image_layers_match_the_oracle_and_count_index_errors(backend):
+    E, n, r = 33, 5, 1
+    layers = (3, 2, 4)
+    kw = dict(shelf_columns=3, column_height=8, shelf_rows=1, n_agents=n, request_queue_size=4, sensor_range=r, max_steps=40)
+    vec = rware_b200.VecWarehouse(E, auto_reset=True, observation_type=2, image_observation_layers=layers,
+                                  image_observation_directional=True, _backend_factory=backend_factory(backend), **kw)
+    orcs = [oracle_py.OracleEnv(vec.highways, vec.goals, n, 0, r, 4, None, 40, 1) for _ in range(E)]
+    before = vec.error_count()
+    obs = vec.reset(seed=3)
+    for e, o in enumerate(orcs):
+        o.reset(3 + e)
+    rs = np.random.default_rng(2)
+    n_bad = 0
+    for t in range(50):
+        img, _ = vec.split_image_obs(obs)
+        img = img.cpu().numpy()
+        for e, o in enumerate(orcs):
+            try:
+                want = o.obs_image(layers, True)
+            except IndexError:
+                n_bad += 1
+                continue
+            assert np.array_equal(want, img[e]), (t, e)
+        assert vec.error_count() - before == n_bad, t
+        acts = rs.choice(5, size=(E, n), p=[.05, .55, .15, .15, .1]).astype(np.int32)
+        obs, rew, done = vec.step(torch.from_numpy(acts))
+        for e, o in enumerate(orcs):
+            _, _, od = o.step(acts[e])
+            if od:
+                o.reset()
+    assert n_bad > 0
