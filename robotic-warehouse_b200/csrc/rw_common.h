@@ -59,7 +59,7 @@ struct RwParams {
     int32_t obs_kind;             // 0 flattened vector, 2 image, 3 image + features (ObservationType values)
     int32_t img_directional, n_layers, img_layers[8];
     uint32_t img_mask[8];         // per image layer: test mask over (grid byte | table byte << 8 | outside-the-map << 16), bit 31 = invert;
-                                  // bit 30: transposed agent layer (AGENT_DIRECTION / AGENT_LOAD), low bits = the layer id
+                                  // 0 for the transposed agent layers (AGENT_DIRECTION / AGENT_LOAD), which a second pass fills in
     int32_t img_transposed;       // bit 0: AGENT_DIRECTION configured, bit 1: AGENT_LOAD configured
     // tile layout
     int32_t nw, w_agent, w_msg, w_shelf, w_queue, w_steps, w_inact;

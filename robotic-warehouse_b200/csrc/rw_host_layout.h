@@ -85,8 +85,8 @@ static inline void rw_fill_params(RwParams &p, const rw_config &c, int64_t num_e
                 case 1: p.img_mask[i] = RW_G_REQ; break;
                 case 2: p.img_mask[i] = RW_G_AGENT; break;
                 case 5: p.img_mask[i] = 2u << 8; break;                        // goal flag of the static table byte
-                case 3: p.img_mask[i] = (1u << 30) | 3u; if (i < cfg->n_image_layers) p.img_transposed |= 1; break;
-                case 4: p.img_mask[i] = (1u << 30) | 4u; if (i < cfg->n_image_layers) p.img_transposed |= 2; break;
+                case 3: p.img_mask[i] = 0; if (i < cfg->n_image_layers) p.img_transposed |= 1; break;  // second pass,
+                case 4: p.img_mask[i] = 0; if (i < cfg->n_image_layers) p.img_transposed |= 2; break;  // rw_obs_image_transposed
                 default: p.img_mask[i] = RW_G_AGENT | (1u << 16) | (1u << 31);  // ACCESSIBLE: inside the map and no agent
             }
         }

@@ -870,6 +870,9 @@ RW_HD void rw_obs_agent(const RwParams &p, const RwLane &l, int i, float *out, i
 }
 
 // ------------------------------------------------------------------------------------------------
+template <class C, int nparts>
+RW_HD_NOINLINE void rw_obs_image_transposed(const RwParams &p, const RwLane l, int i, float *out, int part);
+
 // Image observation of agent i (ref:527-596): out = [n_layers][K][K] float32, K = 2r+1, the window centred on the agent,
 // rotated towards its heading when `img_directional` (np.rot90, ref:584-595); IMAGE_DICT appends 6 feature floats
 // (one-hot direction, on_highway, carrying; ref:726-742).  Layers (ImageLayer values, ref:59-70): 0 SHELVES,
@@ -903,29 +906,58 @@ RW_HD void rw_obs_image_agent(const RwParams &p, const RwLane &l, int i, float *
 #pragma unroll
             for (int li = 0; li < 8; li++)
                 if (li < p.n_layers) {
-                    const uint32_t m = p.img_mask[li];
-                    float v;
-                    if (m & (1u << 30)) {
-                        // AGENT_DIRECTION / AGENT_LOAD: the reference writes layer[ag.x, ag.y] (sic, ref:552, 558), so
-                        // window cell [yy][xx] shows the agent that stands at column yy, row xx
-                        v = 0.0f;
-                        if (in && xx < H && yy < W) {
-                            const uint32_t id = (uint32_t)l.g[xx * W + yy] & RW_G_AGENT;
-                            if (id) {
-                                const uint32_t ow = rw_agent(l, (int)id - 1);
-                                v = (m & 7u) == 3u ? (float)(rw_adir(ow) + 1) : (rw_acarry(ow) ? 1.0f : 0.0f);
-                            }
-                        }
-                    } else {
-                        v = (((word & m & 0x1ffffu) != 0) != ((m >> 31) != 0)) ? 1.0f : 0.0f;
-                    }
-                    out[li * KK + o] = v;
+                    const uint32_t m = p.img_mask[li];  // 0 for the transposed agent layers: zero here, filled in below
+                    out[li * KK + o] = (((word & m & 0x1ffffu) != 0) != ((m >> 31) != 0)) ? 1.0f : 0.0f;
                 }
+        }
+    }
+    if (part == 0 && p.obs_kind == 3) {
+        float *f = out + p.n_layers * KK;
+        f[0] = d == 0 ? 1.0f : 0.0f;
+        f[1] = d == 1 ? 1.0f : 0.0f;
+        f[2] = d == 2 ? 1.0f : 0.0f;
+        f[3] = d == 3 ? 1.0f : 0.0f;
+        f[4] = (l.highway[y * W + x] & 1) ? 1.0f : 0.0f;
+        f[5] = rw_acarry(aw) ? 1.0f : 0.0f;
+    }
+    if (p.img_transposed) rw_obs_image_transposed<C, nparts>(p, l, i, out, part);
+}
+
+// AGENT_DIRECTION / AGENT_LOAD layers of the image observation, a second pass taken only by configurations that ask for them:
+// the reference writes layer[ag.x, ag.y] (sic, ref:552, 558), so window cell [yy][xx] shows the agent that stands at column yy,
+// row xx of the map.
+template <class C, int nparts>
+RW_HD_NOINLINE void rw_obs_image_transposed(const RwParams &p, const RwLane l, int i, float *out, int part) {
+    const uint32_t aw = rw_agent(l, i);
+    const int x = rw_ax(aw), y = rw_ay(aw), d = rw_adir(aw);
+    const int W = C::W(p), H = C::H(p), r = C::r(p), K = 2 * r + 1, KK = K * K;
+    const int rot = p.img_directional ? (d == 1 ? 2 : d == 2 ? 3 : d == 3 ? 1 : 0) : 0;
+    const int Kp = (KK + nparts - 1) / nparts;
+    for (int o = part * Kp; o < (part + 1) * Kp && o < KK; o++) {
+        const int oi = o / K, oj = o - oi * K;
+        int si, sj;
+        if (rot == 0) { si = oi; sj = oj; }
+        else if (rot == 1) { si = oj; sj = K - 1 - oi; }
+        else if (rot == 2) { si = K - 1 - oi; sj = K - 1 - oj; }
+        else { si = K - 1 - oj; sj = oi; }
+        const int yy = y - r + si, xx = x - r + sj;
+        // inside the (H, W) layer, and the transposed position (row xx, column yy) inside the map
+        const bool ok = (unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W && xx < H && yy < W;
+        uint32_t ow = 0;
+        bool have = false;
+        if (ok) {
+            const uint32_t id = (uint32_t)l.g[xx * W + yy] & RW_G_AGENT;
+            if (id) { ow = rw_agent(l, (int)id - 1); have = true; }
+        }
+        for (int li = 0; li < p.n_layers; li++) {
+            const int ly = p.img_layers[li];
+            if (ly == 3) out[li * KK + o] = have ? (float)(rw_adir(ow) + 1) : 0.0f;
+            else if (ly == 4) out[li * KK + o] = (have && rw_acarry(ow)) ? 1.0f : 0.0f;
         }
     }
     // where numpy raises IndexError for the transposed writes (an agent with x >= H or y >= W) the world is counted once
     // per observation pass (by the lane of its first agent) and the offending entries are simply absent
-    if (p.img_transposed && i == 0 && part == 0) {
+    if (i == 0 && part == 0) {
         int bad = 0;
         for (int a = 0; a < C::n(p); a++) {
             const uint32_t ow = rw_agent(l, a);
@@ -938,15 +970,6 @@ RW_HD void rw_obs_image_agent(const RwParams &p, const RwLane &l, int i, float *
             *p.err_count += 1;
 #endif
         }
-    }
-    if (part == 0 && p.obs_kind == 3) {
-        float *f = out + p.n_layers * KK;
-        f[0] = d == 0 ? 1.0f : 0.0f;
-        f[1] = d == 1 ? 1.0f : 0.0f;
-        f[2] = d == 2 ? 1.0f : 0.0f;
-        f[3] = d == 3 ? 1.0f : 0.0f;
-        f[4] = (l.highway[y * W + x] & 1) ? 1.0f : 0.0f;
-        f[5] = rw_acarry(aw) ? 1.0f : 0.0f;
     }
 }
 
