@@ -160,3 +160,74 @@ except Exception:  # gymnasium absent
 
         def __repr__(self):
             return "Tuple(" + ", ".join(map(repr, self.spaces)) + ")"
+
+
+def flatdim(space):
+    """gymnasium.spaces.flatdim for the spaces this package uses."""
+    if HAVE_GYMNASIUM:
+        return _gym.spaces.flatdim(space)
+    if isinstance(space, Discrete):
+        return int(space.n)
+    if isinstance(space, MultiDiscrete):
+        return int(np.sum(space.nvec))
+    if isinstance(space, (Box, MultiBinary)):
+        return int(np.prod(space.shape))
+    if isinstance(space, Tuple):
+        return sum(flatdim(s) for s in space.spaces)
+    if isinstance(space, Dict):
+        return sum(flatdim(s) for s in space.spaces.values())
+    raise NotImplementedError(type(space))
+
+
+def flatten(space, x):
+    """gymnasium.spaces.flatten: Discrete / MultiDiscrete become one-hot vectors, Box and MultiBinary are raveled, Tuple and
+    Dict concatenate their members (Dict in the key order of the space)."""
+    if HAVE_GYMNASIUM:
+        return _gym.spaces.flatten(space, x)
+    if isinstance(space, Discrete):
+        out = np.zeros(space.n, dtype=np.int64)
+        out[int(x)] = 1
+        return out
+    if isinstance(space, MultiDiscrete):
+        nvec = np.asarray(space.nvec).ravel()
+        offsets = np.concatenate([[0], np.cumsum(nvec)])
+        out = np.zeros(int(offsets[-1]), dtype=np.int64)
+        out[offsets[:-1] + np.asarray(x).ravel()] = 1
+        return out
+    if isinstance(space, (Box, MultiBinary)):
+        return np.asarray(x, dtype=space.dtype).ravel()
+    if isinstance(space, Tuple):
+        parts = [flatten(s, p) for s, p in zip(space.spaces, x)]
+        return np.concatenate(parts) if parts else np.zeros(0)
+    if isinstance(space, Dict):
+        parts = [flatten(s, x[k]) for k, s in space.spaces.items()]
+        return np.concatenate(parts) if parts else np.zeros(0)
+    raise NotImplementedError(type(space))
+
+
+class MultiAgentObservationSpace(list):
+    """rware/utils/spaces.py:4-21: a list of per-agent spaces with sample() / contains()."""
+
+    def __init__(self, ma_space):
+        for x in ma_space:
+            assert hasattr(x, "sample") and hasattr(x, "contains")
+        super().__init__(ma_space)
+
+    def sample(self):
+        return [sa.sample() for sa in self]
+
+    def contains(self, obs):
+        return all(space.contains(ob) for space, ob in zip(self, obs))
+
+
+class MultiAgentActionSpace(list):
+    """rware/utils/spaces.py:24-32."""
+
+    def __init__(self, ma_space):
+        for x in ma_space:
+            assert hasattr(x, "sample") and hasattr(x, "contains")
+        super().__init__(ma_space)
+
+    def sample(self):
+        return [sa.sample() for sa in self]
+

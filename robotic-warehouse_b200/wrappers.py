@@ -1,5 +1,5 @@
 """Host/device-side reshapes on top of the step outputs, mirroring
-rware/utils/wrappers.py: `FlattenAgents` (9-48) and `DictAgents` (51-80) for the single-world facade, plus
+rware/utils/wrappers.py: `FlattenAgents` (9-48), `DictAgents` (51-80) and `FlattenSAObservation` (83-108) for the single-world facade, plus
 `VecFlattenAgents`, the batched form (a view of the observation tensor and a row sum of the rewards -- no copy, no
 kernel).  They work without gymnasium; they only need an object with the Warehouse / VecWarehouse surface."""
 import math
@@ -65,6 +65,29 @@ class DictAgents(_Wrapper):
         assert keys == sorted(action.keys())
         obs, reward, done, truncated, info = self.env.step([action[k] for k in keys])
         return (dict(zip(keys, obs)), dict(zip(keys, reward)), {k: done for k in keys}, {k: truncated for k in keys}, info)
+
+
+class FlattenSAObservation(_Wrapper):
+    """Flattens every agent's observation with the space's own flatten rule (wrappers.py:83-108): DICT and IMAGE_DICT
+    observations become one vector per agent (Discrete members one-hot, Box / MultiBinary raveled, in the key order of the
+    space)."""
+
+    def __init__(self, env):
+        super().__init__(env)
+        inf = float("inf")
+        self.observation_space = spaces.Tuple(tuple(
+            spaces.Box(low=-inf, high=inf, shape=(spaces.flatdim(sa),), dtype=np.float32) for sa in env.observation_space))
+
+    def observation(self, observation):
+        return [spaces.flatten(sa, obs) for sa, obs in zip(self.env.observation_space, observation)]
+
+    def reset(self, **kwargs):
+        obs, info = self.env.reset(**kwargs)
+        return self.observation(obs), info
+
+    def step(self, action):
+        obs, reward, done, truncated, info = self.env.step(action)
+        return self.observation(obs), reward, done, truncated, info
 
 
 class VecFlattenAgents(_Wrapper):

@@ -317,6 +317,34 @@ def record_image_transposed(wh):
         json.dump(meta, f)
 
 
+def record_flatten_sa(wh):
+    """rware.utils.wrappers.FlattenSAObservation (wrappers.py:83-108) over DICT and IMAGE_DICT observations.  Note: the flatten
+    rule itself is gymnasium's; in this container it is the stand-in's restatement of it (oracle/refharness/gymnasium_standin)."""
+    from rware.utils import wrappers as W
+    OT = wh.ObservationType
+    out = {}
+    for name, kw in (("dict_msg2", dict(n_agents=3, msg_bits=2, observation_type=OT.DICT)),
+                     ("imagedict", dict(n_agents=2, msg_bits=0, observation_type=OT.IMAGE_DICT))):
+        env = W.FlattenSAObservation(wh.Warehouse(shelf_columns=3, column_height=8, shelf_rows=1, sensor_range=1, request_queue_size=2,
+                                                  max_inactivity_steps=None, max_steps=30, reward_type=wh.RewardType.INDIVIDUAL, **kw))
+        rs = np.random.default_rng(len(name))
+        n, mb = kw["n_agents"], kw["msg_bits"]
+        obs, _ = env.reset(seed=21)
+        seq = [[np.asarray(o, np.float64).tolist() for o in obs]]
+        acts = []
+        for t in range(25):
+            a = [[int(rs.integers(5))] + [int(b) for b in rs.integers(0, 2, size=mb)] for _ in range(n)] if mb else \
+                [int(rs.integers(5)) for _ in range(n)]
+            acts.append(a)
+            obs, _, done, _, _ = env.step(a)
+            seq.append([np.asarray(o, np.float64).tolist() for o in obs])
+        out[name] = dict(kwargs={k: (v.value if hasattr(v, "value") else v) for k, v in kw.items()}, actions=acts, obs=seq,
+                         flatdim=[int(s.shape[0]) for s in env.observation_space])
+        print("flatten-sa fixture", name, len(seq), out[name]["flatdim"])
+    with open(os.path.join(HERE, "flatten_sa.json"), "w") as f:
+        json.dump(out, f)
+
+
 def record_registry_ids(gym):
     """id -> kwargs of the reference's optional registrations (rware/__init__.py:42-172): every image id and a random sample
     of the 5.25 million full_registration ids (enumerating them takes ~30 s)."""
@@ -345,6 +373,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "image_transposed":
         record_image_transposed(wh)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "flatten_sa":
+        record_flatten_sa(wh)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "registry":
         record_registry_ids(gym)
         return
@@ -371,6 +402,7 @@ def main():
     record_obs_types(wh)
     record_global_images(wh)
     record_image_transposed(wh)
+    record_flatten_sa(wh)
     record_registry_ids(gym)
 
 
