@@ -115,3 +115,68 @@ def test_host_buffer_entry_points_match_the_device_ones(E, packed, kw):
         obs_d, rew_d, done_d = a.step(acts.cuda())
         b.backend.step_host(acts, h_obs, h_rew, h_done)
         assert torch.equal(h_obs, obs_d.cpu()) and torch.equal(h_rew, rew_d.cpu()) and torch.equal(h_done, done_d.cpu())
+
+
+def _full_size_cases():
+    from conftest import backend_params
+    cases = []
+    for bp in backend_params():
+        backend = bp.values[0]
+        for env_id, over, E_full, L_self in (("rware-small-4ag-v1", {}, 32768, 8), ("rware-medium-8ag-hard-v1", {}, 32768, 8),
+                                            ("rware-large-16ag-v1", {"sensor_range": 2}, 16384, 8)):
+            E = E_full if backend == "cuda" else 70  # the host twin runs the same test body on a few tiles
+            cases.append(pytest.param(env_id, over, E, backend, marks=bp.marks, id=f"{env_id.split('-')[1]}-{E}-{backend}"))
+    return cases
+
+
+@pytest.mark.parametrize("env_id,over,E,backend", _full_size_cases())
+def test_other_baseline_configs_at_full_size(env_id, over, E, backend):
+    """BASELINE.json configs[2..4] at their per-GPU sizes (small-4ag x 32 768, medium-8ag-hard x 32 768, large-16ag r=2 x 16 384):
+    determinism across two instances, structural invariants of every observation row and of the state, and oracle parity on a
+    sample of worlds from the first, a middle and the last tile."""
+    import oracle_py
+    from conftest import backend_factory
+    T = 25
+    kw = rware_b200.env_kwargs(env_id, **over)
+    n, r = kw["n_agents"], kw["sensor_range"]
+    make = lambda: rware_b200.make_vec(env_id, E, auto_reset=True, _backend_factory=backend_factory(backend), **over)  # noqa: E731
+    vec, twin = make(), make()
+    dev = vec.device
+    obs0 = vec.reset(seed=7).clone()
+    twin.reset(seed=7)
+    sample = np.unique(np.r_[0:20, E // 2:E // 2 + 8, E - 20:E])
+    orcs = {int(e): oracle_py.OracleEnv(vec.highways, vec.goals, n, 0, r, kw["request_queue_size"], None, kw["max_steps"],
+                                        kw["reward_type"].value) for e in sample}
+    for e, o in orcs.items():
+        assert np.array_equal(o.reset(7 + e), obs0[e].cpu().numpy())
+    g = torch.Generator(device=dev).manual_seed(11)
+    K = (2 * r + 1) ** 2
+    for t in range(T):
+        a = torch.randint(0, 5, (E, n), generator=g, device=dev, dtype=torch.int32)
+        obs, rew, done = vec.step(a)
+        obs2, rew2, done2 = twin.step(a)
+        assert torch.equal(obs, obs2) and torch.equal(rew, rew2) and torch.equal(done, done2)
+        o = obs.view(E * n, -1)
+        assert bool(((o[:, 3:7].sum(1) == 1) & (o[:, 2] <= 1) & (o[:, 7] <= 1)).all())         # App. C: self block
+        cells = o[:, 8:].view(E * n, K, 7)
+        assert bool((cells[:, :, 1:5].sum(2) == 1).all()) and bool((cells[:, K // 2, 0] == 1).all())  # one-hot dirs; self in the centre
+        assert bool(((cells == 0) | (cells == 1)).all()) and bool((cells[:, :, 6] <= cells[:, :, 5]).all())
+        assert bool(((rew == 0) | (rew == 1)).all())                                           # INDIVIDUAL rewards
+        ah = a.cpu().numpy()
+        oh, rh, dh = obs[sample].cpu().numpy(), rew[sample].cpu().numpy(), done[sample].cpu().numpy()
+        for k, e in enumerate(sample):
+            oo, orw, od = orcs[int(e)].step(ah[e])
+            if od:
+                oo = orcs[int(e)].reset()
+            assert np.array_equal(oo, oh[k]) and np.array_equal(orw.astype(np.float32), rh[k]) and od == bool(dh[k]), (t, e)
+    st = vec.get_state()
+    cell = st["agent_y"] * vec.grid_size[1] + st["agent_x"]
+    assert bool((torch.sort(cell, dim=1).values.diff(dim=1) != 0).all())                        # no two agents share a cell
+    carry = st["agent_carry"].long()
+    has = carry > 0
+    sx = torch.gather(st["shelf_x"], 1, (carry - 1).clamp(min=0))
+    sy = torch.gather(st["shelf_y"], 1, (carry - 1).clamp(min=0))
+    assert bool(((sx == st["agent_x"]) | ~has).all()) and bool(((sy == st["agent_y"]) | ~has).all())
+    q = torch.sort(st["queue"], dim=1).values
+    assert bool((q.diff(dim=1) != 0).all()) and bool((q >= 1).all()) and bool((q <= vec.n_shelves).all())  # queue: distinct shelf ids
+    assert bool((st["cur_steps"] == T).all())
