@@ -50,8 +50,8 @@ typedef struct rw_config {
     int32_t grid_h, grid_w;       /* grid_size, warehouse.py:297-300 / 337 */
     int32_t n_agents;             /* 1..32 */
     int32_t msg_bits;             /* 0..16 */
-    int32_t sensor_range;         /* >= 1 */
-    int32_t request_queue_size;   /* 1..n_shelves */
+    int32_t sensor_range;         /* 0..8 */
+    int32_t request_queue_size;   /* 0..n_shelves (equal to n_shelves: the reference raises on the first delivery) */
     int32_t max_inactivity_steps; /* 0 == None */
     int32_t max_steps;            /* 0 == None */
     int32_t reward_type;          /* RW_REWARD_* */
