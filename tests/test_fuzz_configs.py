@@ -79,3 +79,14 @@ def test_random_configuration_matches_oracle(seed, coop, backend, monkeypatch):
             assert np.array_equal(so["agent_x"], st["agent_x"][e]) and np.array_equal(so["agent_y"], st["agent_y"][e])
             assert np.array_equal(so["queue"], st["queue"][e]) and np.array_equal(so["agent_carry"], st["agent_carry"][e])
             assert np.array_equal(so["rng"], st["rng"][e].astype(np.int64) & 0xFFFFFFFF)
+        if t % 9 == 4:  # whole-warehouse view of the same states: random layer subset, random padding
+            H, W = vec.grid_size
+            layers = [int(v) for v in rs.choice(7, size=int(rs.integers(1, 6)))]
+            pad = None if rs.random() < 0.5 else (len(layers) + int(rs.integers(0, 3)), H + int(rs.integers(0, 4)), W + int(rs.integers(0, 4)))
+            got = vec.global_image(layers, pad).cpu().numpy()
+            for e, o in enumerate(orcs):
+                try:
+                    want = o.global_image(layers, pad)
+                except IndexError:  # transposed layer off the map: the reference raises, the batched call counts the world
+                    continue
+                assert np.array_equal(got[e], want), (kw, t, e, layers, pad)
