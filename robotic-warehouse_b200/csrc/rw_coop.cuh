@@ -18,7 +18,7 @@
 #if defined(__CUDA_ARCH__)
 template <class T>
 using RwV = T;
-#define RW_EACH_LANE for (int lane_ = (int)(threadIdx.x & 31u), once_ = 1; once_; once_ = 0)
+#define RW_EACH_LANE for ([[maybe_unused]] int lane_ = (int)(threadIdx.x & 31u), once_ = 1; once_; once_ = 0)
 #define LV(x) (x)
 __device__ __forceinline__ void rw_shfl(uint32_t &dst, const uint32_t &src, const int &srclane) {
     dst = __shfl_sync(0xffffffffu, src, srclane);
