@@ -124,7 +124,12 @@ struct Pool {
 
     void start(int threads) {
         T = threads < 1 ? 1 : threads;
-        for (int t = 1; t < T; t++) workers.emplace_back([this, t] { worker(t); });
+        try {
+            for (int t = 1; t < T; t++) workers.emplace_back([this, t] { worker(t); });
+        } catch (...) {  // thread limit reached: work with the threads that exist (slices are dealt by T, so fix it first)
+        }
+        // workers read T only after the first wake(), which happens after this assignment
+        T = (int)workers.size() + 1;
     }
 
     void place(const void *dst) {
