@@ -159,6 +159,12 @@ int rw_error_count(rw_handle *h, int64_t *out, void *stream);
  * to the device, runs rw_step, copies obs/reward/done back and synchronises.  Any output pointer may be NULL. */
 int rw_step_host(rw_handle *h, const int32_t *actions_host, float *obs_host, float *reward_host, uint8_t *done_host);
 int rw_reset_host(rw_handle *h, const uint64_t *seeds_host, float *obs_host);
+/* Byte image of an observation tensor: out_dev[i] = (uint8_t)obs_dev[i] for the E*n*L values of obs_dev (a tensor written by
+ * rw_step / rw_reset / rw_obs).  Exact, because every observation value is an integer in 0..255 unless normalised_coordinates
+ * is set (then RW_EINVAL): a 4x smaller observation for consumers that embed or cast on the device.  (new; the reference's
+ * observations are float32 arrays, warehouse.py:17-28) */
+int rw_obs_bytes(rw_handle *h, const float *obs_dev, uint8_t *out_dev, void *stream);
+
 /* Transport of rw_step_host.  The call is bound by PCIe (74 MB of float32 observations per step of 65 536 tiny-4ag worlds), and
  * every observation value is an exact integer < 256 unless normalised_coordinates is set.  With the packed transport (default
  * for batches of >= 2^20 values) the device sends one byte per value in chunks and a pool of host threads widens each chunk to

@@ -97,12 +97,13 @@ def load_library():
     L.rw_render_shape.argtypes = [vp, vp, vp]
     L.rw_render_rgb.argtypes = [vp, i64, i64, vp, vp]
     L.rw_set_host_transport.argtypes = [vp, ci]
+    L.rw_obs_bytes.argtypes = [vp, vp, vp, vp]
     L.rw_host_widen_u8.argtypes = [vp, vp, i64]
     for name in ("rw_create", "rw_destroy", "rw_get_info", "rw_seed", "rw_reset", "rw_step", "rw_obs", "rw_set_auto_reset",
                  "rw_get_state", "rw_set_state", "rw_error_count", "rw_step_host", "rw_reset_host", "rw_host_alloc",
                  "rw_host_free", "rw_random_actions", "rw_debug_set_clock_buffer", "rw_flush_l2", "rw_gather_create", "rw_gather_open", "rw_step_gather",
                  "rw_global_image_shape", "rw_global_image", "rw_render_shape", "rw_render_rgb", "rw_set_host_transport",
-                 "rw_host_widen_u8"):
+                 "rw_host_widen_u8", "rw_obs_bytes"):
         getattr(L, name).restype = ci
     _lib = L
     return L
@@ -281,6 +282,9 @@ class CudaBackend:
     # end-to-end entry points with host (pinned) buffers
     def step_host(self, actions, obs, reward, done):
         self._check(self.lib.rw_step_host(self._h, _ptr(actions), _ptr(obs), _ptr(reward), _ptr(done)))
+
+    def obs_bytes(self, obs, out):
+        self._check(self.lib.rw_obs_bytes(self._h, _ptr(obs), _ptr(out), self._stream()))
 
     def set_host_transport(self, packed):
         """Packed (one byte per observation value over PCIe, widened on the host) or plain float32 copies in step_host."""

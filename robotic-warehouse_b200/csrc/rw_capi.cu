@@ -558,6 +558,14 @@ int rw_step_host(rw_handle *h, const int32_t *actions_host, float *obs_host, flo
     return RW_OK;
 }
 
+int rw_obs_bytes(rw_handle *h, const float *obs_dev, uint8_t *out_dev, void *stream) {
+    if (!h || !obs_dev || !out_dev) return fail(h, RW_EINVAL, "rw_obs_bytes: null argument");
+    if (h->p.norm_coords) return fail(h, RW_EINVAL, "rw_obs_bytes: normalised coordinates are not integers");
+    CK(cudaSetDevice(h->device));
+    CK(rw_launch_pack_u8(obs_dev, out_dev, (size_t)h->p.E * h->p.n * h->p.L, (cudaStream_t)stream));
+    return RW_OK;
+}
+
 int rw_set_host_transport(rw_handle *h, int packed) {
     if (!h) return RW_EINVAL;
     h->host_pack = packed ? 1 : 0;

@@ -89,6 +89,16 @@ class VecWarehouse:
         self.backend.obs(self._obs)
         return self._obs
 
+    def observation_bytes(self, obs=None, out=None):
+        """uint8 image of an observation tensor (default: the last one returned): the same values, one byte each.  Exact because
+        observation values are integers in 0..255 unless `normalised_coordinates` is set (then this raises)."""
+        obs = self._obs if obs is None else obs
+        if out is None:
+            out = torch.empty(obs.shape, dtype=torch.uint8, device=self.device)
+        assert obs.is_contiguous() and out.is_contiguous() and obs.numel() == self._obs.numel() == out.numel()
+        self.backend.obs_bytes(obs, out)
+        return out
+
     # ------------------------------------------------------------------ whole-warehouse views
     def global_image(self, image_layers=(0, 5), pad_to_shape=None, out=None):
         """Warehouse.get_global_image(image_layers, recompute=True, pad_to_shape) (rware/warehouse.py:966-1040) of every world:

@@ -128,3 +128,8 @@ class HostSimBackend:
     def render_rgb(self, first_env, n_envs, out):
         if self.lib.sim_render_rgb(self._h, int(first_env), int(n_envs), _ptr(out)):
             raise RuntimeError("render_rgb: world range out of bounds")
+
+    def obs_bytes(self, obs, out):
+        if self.cfg.normalised_coordinates:
+            raise RuntimeError("rw_obs_bytes: normalised coordinates are not integers")
+        out.copy_(obs.to(torch.uint8))

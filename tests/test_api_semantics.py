@@ -124,3 +124,25 @@ def test_optional_registrations_resolve_like_the_reference():
     finally:
         reg._enabled.clear()
         reg._enabled.update(saved)
+
+
+@pytest.mark.parametrize("backend", backend_params())
+def test_observation_bytes_are_the_same_values(backend):
+    """rw_obs_bytes / VecWarehouse.observation_bytes: the uint8 image of the float32 observations (exact integers 0..255)."""
+    E = 77
+    vec = rware_b200.VecWarehouse(E, shelf_columns=3, column_height=8, shelf_rows=1, n_agents=3, msg_bits=2, sensor_range=2,
+                                  request_queue_size=3, max_steps=20, auto_reset=True, _backend_factory=backend_factory(backend))
+    obs = vec.reset(seed=1)
+    g = torch.Generator().manual_seed(0)
+    for _ in range(12):
+        b = vec.observation_bytes()
+        assert b.dtype == torch.uint8 and b.shape == obs.shape and torch.equal(b.to(torch.float32), obs)
+        acts = torch.cat([torch.randint(0, 5, (E, 3, 1), generator=g), torch.randint(0, 2, (E, 3, 2), generator=g)], dim=2).to(torch.int32)
+        obs, _, _ = vec.step(acts.to(vec.device))
+    out = torch.zeros_like(obs, dtype=torch.uint8)
+    assert vec.observation_bytes(obs, out) is out and torch.equal(out.to(torch.float32), obs)
+    norm = rware_b200.VecWarehouse(4, shelf_columns=3, column_height=8, shelf_rows=1, n_agents=2, normalised_coordinates=True,
+                                   _backend_factory=backend_factory(backend))
+    norm.reset(seed=0)
+    with pytest.raises(RuntimeError):
+        norm.observation_bytes()
