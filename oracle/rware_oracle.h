@@ -9,7 +9,10 @@
  * Parity status: PINNED.  The oracle is checked (tests/test_oracle_golden.py) against golden
  * trajectories generated in the build container from the *unmodified* reference
  * (tests/golden/make_golden.py), against the reference's own behavioural tests restated as fixtures,
- * and against the SHA-256 known-answer vectors of SURVEY.md App. E.  The collision resolver lives in a
+ * against the SHA-256 known-answer vectors of SURVEY.md App. E, and lock-step against the unmodified
+ * reference in the build container (oracle/refharness/diff_reference.py: 9 configurations x 30 000 steps
+ * and 4 800 random configurations x 300 steps, every field and the full PCG64 state, 0 mismatches; logs
+ * next to the script).  The collision resolver lives in a
  * third-party dependency of the reference that is not vendored (networkx, unpinned in setup.py:28,
  * 3.6.1 in this image) and its tie order depends on CPython 3.12 set iteration order; both are
  * restated here from their published sources and pinned by the same golden trajectories.
