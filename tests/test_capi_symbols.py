@@ -98,3 +98,15 @@ def test_host_widening_from_several_threads_and_after_fork():
         os._exit(0 if np.array_equal(out, srcs[0].astype(np.float32)) else 1)
     _, status = os.waitpid(pid, 0)
     assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0
+
+
+@pytest.mark.gpu
+def test_c_abi_against_the_oracle_without_python():
+    """tests/ctest/gpu_quickcheck: a plain CUDA host program that links librware_b200.so and the C oracle and compares IMAGE
+    observations with the transposed agent layers, the index-error count, rewards, done flags and rw_obs_bytes over 46 steps."""
+    import subprocess
+    exe = os.path.join(ROOT, "tests", "ctest", "_build", "gpu_quickcheck")
+    if not os.path.exists(exe):
+        pytest.skip("tests/ctest/_build/gpu_quickcheck not built (__graft_entry__.build() builds it)")
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0 and "gpu_quickcheck OK" in res.stdout, res.stdout + res.stderr
