@@ -142,6 +142,41 @@ def run_reference_arm(args):
         "gpu_launches": 0}))
 
 
+def e2e_record(world, E, n, A, L, steps, e2e_s, plain_s, d2h_ms, dma_share, compressed, bit_rows, host_gbs, host_threads, numa):
+    """The `e2e` object of the bench line: throughput through rw_step_host with host buffers, its transport and its roofline."""
+    rows = E * n
+    obs_bytes = rows * L * 4
+    small = E * n * 4 + E
+    if compressed:
+        rows_cpu = min(rows, int((1.0 - dma_share) * rows) & ~63)
+        per_row = (L / 8.0 + 2) if bit_rows else L
+        d2h = int(rows_cpu * per_row + (rows - rows_cpu) * L * 4) + small
+        transport = (("bits: every 0/1 flag of a row crosses PCIe as one bit and each coordinate as one byte"
+                      if bit_rows else "bytes: every value crosses PCIe as one byte")
+                     + f"; the library's host threads ({host_threads}) rebuild the float32 rows in the caller's buffer with streaming "
+                       f"stores while the GPU's copy engine delivers {dma_share:.2f} of the rows as plain float32 (share follows the "
+                       "measured rates); results bit-identical to the plain copy")
+    else:
+        d2h, transport = obs_bytes + small, "plain float32 copy"
+    pcie_gbs = (obs_bytes + small) / (d2h_ms * 1e-3) / 1e9
+    ms = e2e_s / steps * 1e3
+    # both writers (host pool, copy engine) end in this rank's host DRAM: the call cannot beat obs_bytes / (their summed rates)
+    bound_ms = obs_bytes / ((host_gbs + pcie_gbs) * 1e9) * 1e3
+    return {"value": world * E * steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": E * n * A * 4,
+            "d2h_bytes_per_step": d2h, "steps": steps,
+            "api": "rw_step_host: page-locked host buffers in and out (int32 actions, float32 observations / rewards, uint8 done); "
+                   "copies, kernel, host expansion and synchronisation inside the timed region",
+            "transport": transport, "ms_per_step": ms, "copy_engine_share": dma_share if compressed else 1.0,
+            "roofline": {"bound": "host DRAM writes of the float32 rows (host pool + copy engine)",
+                         "float32_bytes_to_host_per_step_per_rank": obs_bytes,
+                         "host_pool_stream_gbs": host_gbs, "host_pool_threads": host_threads, "pcie_d2h_gbs": pcie_gbs,
+                         "bound_ms_per_step": bound_ms, "frac": bound_ms / ms,
+                         "achieved_host_write_gbs_per_rank": obs_bytes / (ms * 1e-3) / 1e9, "numa": numa},
+            "plain_float32_transport": {"value": world * E * steps / plain_s, "ms_per_step": plain_s / steps * 1e3,
+                                        "d2h_bytes_per_step": obs_bytes + small, "bare_d2h_copy_ms": d2h_ms,
+                                        "pcie_d2h_gbs": pcie_gbs, "frac_of_transport": d2h_ms / (plain_s / steps * 1e3)}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -154,6 +189,7 @@ def main():
                     help="action distribution: P(FORWARD) = p, the other four actions share the rest (default: uniform); "
                          "0.68 is the dense-collision stress of SURVEY.md section 8(d)")
     ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--e2e-warmup", type=int, default=8)
     ap.add_argument("--ref-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", nargs="?", const="nccl", default=None, choices=["nccl", "fused"],
@@ -345,29 +381,34 @@ def main():
         torch.cuda.synchronize()
         obs_kernel_ms = a.elapsed_time(b) / n_obs
 
-    # end to end through the host-buffer C-ABI entry point
+    # end to end through the host-buffer C-ABI entry point: page-locked host buffers in and out (allocated next to the GPU
+    # with the library's own allocator), H2D actions + kernel + D2H observations / rewards / done + sync inside the timed region
     e2e_steps = args.e2e_steps
-    h_act = torch.empty((E, n, A), dtype=torch.int32).pin_memory()
+    be = vec.backend
+    h_act = be.host_alloc((E, n, A), torch.int32)
     h_act.copy_(actions[0].cpu())
-    h_obs = torch.empty((E, n, L), dtype=torch.float32).pin_memory()
-    h_rew = torch.empty((E, n), dtype=torch.float32).pin_memory()
-    h_done = torch.empty((E,), dtype=torch.uint8).pin_memory()
-    def time_e2e(packed):
-        vec.backend.set_host_transport(packed)
-        for _ in range(3):
-            vec.backend.step_host(h_act, h_obs, h_rew, h_done)
+    h_obs = be.host_alloc((E, n, L), torch.float32)
+    h_rew = be.host_alloc((E, n), torch.float32)
+    h_done = be.host_alloc((E,), torch.uint8)
+    def time_e2e(mode):
+        be.set_host_transport(mode)
+        for _ in range(max(3, args.e2e_warmup)):  # also lets the copy-engine share settle
+            be.step_host(h_act, h_obs, h_rew, h_done)
         torch.cuda.synchronize()
         if dist:
             dist.barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            vec.backend.step_host(h_act, h_obs, h_rew, h_done)  # synchronises internally
+            be.step_host(h_act, h_obs, h_rew, h_done)  # synchronises internally
         return time.perf_counter() - t0
-    e2e_plain_s = time_e2e(False)   # float32 observations over PCIe
-    e2e_s = time_e2e(True)          # default transport: one byte per value over PCIe, widened to float32 by host threads
-    packed_used = (not overrides.get("normalised_coordinates")) and E * n * L >= (1 << 20)
+    e2e_plain_s = time_e2e(0)   # float32 observations over PCIe
+    e2e_s = time_e2e(1)         # default transport: bits / bytes over PCIe, expanded by host threads, copy engine sharing the rows
+    dma_share = be.host_dma_share()
+    compressed = (not overrides.get("normalised_coordinates")) and E * n * L >= (1 << 20)
+    bit_rows = compressed and (overrides.get("observation_type", 1) < 2)
 
-    # transport roofline of the end-to-end call: the same device->host bytes moved by a bare pinned-memory copy
+    # transport rooflines of the end-to-end call: the same device->host bytes moved by a bare pinned-memory copy, and the rate at
+    # which the library's host pool streams into the caller's buffer when there is nothing to decode
     d2h_ms = []
     for _ in range(5):
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -379,6 +420,10 @@ def main():
         torch.cuda.synchronize()
         d2h_ms.append(c0.elapsed_time(c1))
     d2h_ms = min(d2h_ms)
+    if dist:
+        dist.barrier()
+    host_stream_gbs, host_threads = be.host_stream_probe(h_obs, repeats=3)  # every rank at once, like the e2e loop
+    numa = {"gpu_node": be.gpu_numa_node(), "obs_buffer_node": be.host_numa_node(h_obs)}
 
     tot = torch.tensor([total_ms, warm_ms, e2e_s, obs_kernel_ms, e2e_plain_s], dtype=torch.float64, device=dev)
     if dist:
@@ -431,19 +476,8 @@ def main():
                        "achieved_gbs": int(info["algorithmic_bytes_obs"]) * E / (obs_kernel_ms * 1e-3) / 1e9,
                        "frac_of_hbm_peak": int(info["algorithmic_bytes_obs"]) * E / (obs_kernel_ms * 1e-3) / 1e9 / peak,
                        "layout_bytes_per_env": int(info["packed_bytes_obs"])},
-        "e2e": {"value": world * E * e2e_steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": E * n * A * 4,
-                "d2h_bytes_per_step": E * n * L * (1 if packed_used else 4) + E * n * 4 + E, "steps": e2e_steps,
-                "api": "rw_step_host: pinned host buffers in and out (int32 actions, float32 observations / rewards, uint8 done); "
-                       "copies, kernel and synchronisation inside the timed region",
-                "transport": ("packed: observation values (exact integers < 256) cross PCIe as one byte each in 8 chunks and are "
-                              "widened to float32 into the caller's buffer by the library's host threads while the next chunk is "
-                              "in flight; results bit-identical to the plain copy") if packed_used else "plain float32 copy",
-                "ms_per_step": e2e_s / e2e_steps * 1e3,
-                "plain_float32_transport": {"value": world * E * e2e_steps / e2e_plain_s, "ms_per_step": e2e_plain_s / e2e_steps * 1e3,
-                                            "d2h_bytes_per_step": E * n * L * 4 + E * n * 4 + E,
-                                            "bare_d2h_copy_ms": d2h_ms,
-                                            "pcie_d2h_gbs": (E * n * L * 4 + E * n * 4 + E) / (d2h_ms * 1e-3) / 1e9,
-                                            "frac_of_transport": d2h_ms / (e2e_plain_s / e2e_steps * 1e3)}},
+        "e2e": e2e_record(world, E, n, A, L, e2e_steps, e2e_s, e2e_plain_s, d2h_ms, dma_share, compressed, bit_rows,
+                          host_stream_gbs, host_threads, numa),
         "gpu_launches": args.steps,
         "clocks": clocks,
         "wall_s_timed_region": t_wall,

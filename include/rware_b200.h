@@ -165,19 +165,40 @@ int rw_reset_host(rw_handle *h, const uint64_t *seeds_host, float *obs_host);
  * observations are float32 arrays, warehouse.py:17-28) */
 int rw_obs_bytes(rw_handle *h, const float *obs_dev, uint8_t *out_dev, void *stream);
 
-/* Transport of rw_step_host.  The call is bound by PCIe (74 MB of float32 observations per step of 65 536 tiny-4ag worlds), and
- * every observation value is an exact integer < 256 unless normalised_coordinates is set.  With the packed transport (default
- * for batches of >= 2^20 values) the device sends one byte per value in chunks and a pool of host threads widens each chunk to
- * float32 into obs_host while the next one is in flight; the buffers the caller gets back are bit-identical either way.
- * Host threads and host memory bandwidth are shared resources, so the call times itself: it samples the plain copy on its
- * third call and every 64 calls, and serves 64 calls with plain copies whenever two packed calls in a row were 25 % slower
- * than the plain estimate.  rw_set_host_transport(h, 0) selects the plain float32 copy for good, (h, 1) the adaptive default.  Environment: RWARE_B200_HOST_PACK=0|1, RWARE_B200_HOST_THREADS. */
-int rw_set_host_transport(rw_handle *h, int packed);
-/* The widening step alone (dst[i] = (float)src[i] with the same thread pool); returns the number of threads used.  Needs no GPU:
- * exposed so that the host half of the transport can be tested where there is none. */
+/* Transport of rw_step_host.  The caller receives float32 rows in host memory (74 MB per step of 65 536 tiny-4ag worlds); a
+ * plain device-to-host copy of them is PCIe bound.  Unless normalised_coordinates is set every value is a small integer, and
+ * for batches of >= 2^20 values the rows travel compressed and a pool of host threads expands them into obs_host with
+ * streaming stores: one BIT per value plus one byte per coordinate where everything else is a 0/1 flag (FLATTENED rows; image
+ * rows without the AGENT_DIRECTION layer; obs_host must be 64-byte aligned), one BYTE per value otherwise.  The expansion is
+ * bound by the host's DRAM write bandwidth, so the GPU's copy engine delivers a share of the rows as plain float32 at the same
+ * time; the share follows the rates the call measures for the two, i.e. a host whose cores or memory bandwidth are taken by
+ * other tenants drifts towards the plain copy by itself.  The buffers the caller gets back are bit-identical in every mode.
+ *   rw_set_host_transport(h, mode)   0 = plain float32 copy, 1 = compressed (default), 2 = compressed, bytes only
+ *   rw_set_host_dma_share(h, share)  fix the copy engine's share of the rows (0..1), negative = follow the measured rates
+ * Environment: RWARE_B200_HOST_PACK=0|1|2, RWARE_B200_HOST_DMA_SHARE, RWARE_B200_HOST_THREADS, RWARE_B200_HOST_CHUNKS,
+ * RWARE_B200_HOST_NUMA=0 (no placement), RWARE_B200_HOST_TRACE=1 (per-call timeline on stderr). */
+int rw_set_host_transport(rw_handle *h, int mode);
+int rw_set_host_dma_share(rw_handle *h, double share);
+int rw_get_host_dma_share(const rw_handle *h, double *share);
+/* The host half of the transport alone, with the same thread pool; each returns the number of threads used.  They need no GPU
+ * and are exposed so that the expansion can be tested, and the host's write bandwidth measured, where there is none.
+ *   rw_host_widen_u8      dst[i] = (float)src[i]
+ *   rw_host_expand_bits   dst[row * row_len + k] = (float)wide[row * n_wide + k] for k < n_wide, else bit (row * row_len + k) of
+ *                         `bits` (little-endian bytes) as 0.0f / 1.0f
+ *   rw_host_stream_probe  streams `n` floats of a constant into dst `repeats` times; *gb_per_s = the best pass: what this
+ *                         host's memory system takes from the pool when nothing has to be decoded (the transport's roofline) */
 int rw_host_widen_u8(const uint8_t *src, float *dst, int64_t n);
-int rw_host_alloc(void **out, int64_t bytes); /* cudaHostAlloc */
+int rw_host_expand_bits(const uint8_t *bits, const uint8_t *wide, float *dst, int64_t n_rows, int32_t row_len, int32_t n_wide);
+int rw_host_stream_probe(float *dst, int64_t n, int32_t repeats, double *gb_per_s);
+/* Page-locked host memory.  rw_host_alloc_near places the pages on the NUMA node the handle's GPU is attached to (first touch
+ * by a thread confined to that node, then cudaHostRegister), so that neither the copy engine's writes nor the expansion cross
+ * the socket interconnect; without NUMA information it is rw_host_alloc (= cudaHostAlloc).  rw_host_free takes either.
+ * rw_host_numa_node / rw_gpu_numa_node report where a buffer / the GPU sits (-1 = unknown). */
+int rw_host_alloc(void **out, int64_t bytes);
+int rw_host_alloc_near(rw_handle *h, void **out, int64_t bytes);
 int rw_host_free(void *p);
+int rw_host_numa_node(const void *p);
+int rw_gpu_numa_node(const rw_handle *h);
 
 /* ---- Fused push all-gather (one process per GPU, NVLink / NVSwitch peers).  SURVEY.md section 8(e): the single optional
  * exchange of the path is an all-gather of obs / reward / done.  Instead of a separate collective, the step kernel's TMA

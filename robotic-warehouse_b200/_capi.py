@@ -99,11 +99,19 @@ def load_library():
     L.rw_set_host_transport.argtypes = [vp, ci]
     L.rw_obs_bytes.argtypes = [vp, vp, vp, vp]
     L.rw_host_widen_u8.argtypes = [vp, vp, i64]
+    L.rw_host_expand_bits.argtypes = [vp, vp, vp, i64, ctypes.c_int32, ctypes.c_int32]
+    L.rw_host_stream_probe.argtypes = [vp, i64, ctypes.c_int32, ctypes.POINTER(ctypes.c_double)]
+    L.rw_set_host_dma_share.argtypes = [vp, ctypes.c_double]
+    L.rw_get_host_dma_share.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
+    L.rw_host_alloc_near.argtypes = [vp, ctypes.POINTER(vp), i64]
+    L.rw_host_numa_node.argtypes = [vp]
+    L.rw_gpu_numa_node.argtypes = [vp]
     for name in ("rw_create", "rw_destroy", "rw_get_info", "rw_seed", "rw_reset", "rw_step", "rw_obs", "rw_set_auto_reset",
                  "rw_get_state", "rw_set_state", "rw_error_count", "rw_step_host", "rw_reset_host", "rw_host_alloc",
                  "rw_host_free", "rw_random_actions", "rw_debug_set_clock_buffer", "rw_flush_l2", "rw_gather_create", "rw_gather_open", "rw_step_gather",
                  "rw_global_image_shape", "rw_global_image", "rw_render_shape", "rw_render_rgb", "rw_set_host_transport",
-                 "rw_host_widen_u8", "rw_obs_bytes"):
+                 "rw_host_widen_u8", "rw_obs_bytes", "rw_host_expand_bits", "rw_host_stream_probe", "rw_set_host_dma_share",
+                 "rw_get_host_dma_share", "rw_host_alloc_near", "rw_host_numa_node", "rw_gpu_numa_node"):
         getattr(L, name).restype = ci
     _lib = L
     return L
@@ -158,7 +166,11 @@ class CudaBackend:
         if not torch.cuda.is_available():
             raise RuntimeError("rware_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = load_library()
-        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else torch.device(device).index or 0)
+        dev = torch.device("cuda") if device is None else torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError(f"rware_b200 runs on CUDA devices only (got {dev}); there is no CPU fallback")
+        # 'cuda' without an index means the current device (under torchrun: the one set from LOCAL_RANK), not GPU 0
+        self.device = torch.device("cuda", torch.cuda.current_device() if dev.index is None else dev.index)
         self.cfg = cfg
         self.num_envs = int(num_envs)
         self._struct = cfg.to_struct()
@@ -180,6 +192,9 @@ class CudaBackend:
 
     def close(self):
         if getattr(self, "_h", None):
+            for ptr in getattr(self, "_host_blocks", []):  # tensors handed out by host_alloc() die with the backend
+                self.lib.rw_host_free(ctypes.c_void_p(ptr))
+            self._host_blocks = []
             self.lib.rw_destroy(self._h)
             self._h = None
 
@@ -286,9 +301,47 @@ class CudaBackend:
     def obs_bytes(self, obs, out):
         self._check(self.lib.rw_obs_bytes(self._h, _ptr(obs), _ptr(out), self._stream()))
 
-    def set_host_transport(self, packed):
-        """Packed (one byte per observation value over PCIe, widened on the host) or plain float32 copies in step_host."""
-        self._check(self.lib.rw_set_host_transport(self._h, int(bool(packed))))
+    def set_host_transport(self, mode):
+        """Transport of step_host: 0 / False = plain float32 copy, 1 / True = compressed (one bit per flag and one byte per
+        coordinate over PCIe where the rows allow it, else one byte per value; expanded by the library's host threads while the
+        copy engine delivers a share of the rows as plain float32), 2 = compressed, bytes only."""
+        self._check(self.lib.rw_set_host_transport(self._h, int(mode)))
+
+    def set_host_dma_share(self, share):
+        """Fixes the share of the rows the copy engine delivers as float32 (0..1); None = follow the measured rates."""
+        self._check(self.lib.rw_set_host_dma_share(self._h, -1.0 if share is None else float(share)))
+
+    def host_dma_share(self):
+        out = ctypes.c_double()
+        self._check(self.lib.rw_get_host_dma_share(self._h, ctypes.byref(out)))
+        return out.value
+
+    def host_alloc(self, shape, dtype=torch.float32):
+        """Page-locked host tensor on the NUMA node of this GPU (rw_host_alloc_near); freed with the backend."""
+        shape = tuple(int(v) for v in shape)
+        nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        ptr = ctypes.c_void_p()
+        self._check(self.lib.rw_host_alloc_near(self._h, ctypes.byref(ptr), max(nbytes, 1)))
+        if not hasattr(self, "_host_blocks"):
+            self._host_blocks = []
+        self._host_blocks.append(ptr.value)
+        buf = (ctypes.c_uint8 * max(nbytes, 1)).from_address(ptr.value)
+        return torch.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).view(shape)
+
+    def host_numa_node(self, tensor):
+        return int(self.lib.rw_host_numa_node(ctypes.c_void_p(tensor.data_ptr())))
+
+    def gpu_numa_node(self):
+        return int(self.lib.rw_gpu_numa_node(self._h))
+
+    def host_stream_probe(self, tensor, repeats=3):
+        """GB/s the host pool streams into `tensor` (float32, page-locked) with non-temporal stores: the roofline of the
+        compressed transport's expansion.  Overwrites the tensor."""
+        out = ctypes.c_double()
+        threads = self.lib.rw_host_stream_probe(ctypes.c_void_p(tensor.data_ptr()), tensor.numel(), int(repeats), ctypes.byref(out))
+        if threads < 0:
+            raise RuntimeError("rw_host_stream_probe failed")
+        return out.value, threads
 
     def reset_host(self, seeds, obs):
         s = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint64)

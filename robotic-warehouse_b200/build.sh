@@ -15,7 +15,7 @@ $NVCC $FLAGS -c -o build/rw_kernels.o csrc/rw_kernels.cu "$@" > build/rw_kernels
 pids+=($!)
 $NVCC $FLAGS -c -o build/rw_views.o csrc/rw_views.cu "$@" > build/rw_views.log 2>&1 &
 pids+=($!)
-g++ -O3 -std=c++17 -fPIC -pthread -c -o build/rw_hostpack.o csrc/rw_hostpack.cpp > build/rw_hostpack.log 2>&1 &
+g++ -O3 -std=c++17 -fPIC -pthread -Wall -c -o build/rw_hostpack.o csrc/rw_hostpack.cpp > build/rw_hostpack.log 2>&1 &
 pids+=($!)
 $NVCC $FLAGS -c -o build/rw_capi.o csrc/rw_capi.cu "$@" > build/rw_capi.log 2>&1 &
 pids+=($!)

@@ -4,18 +4,28 @@
 // fused kernel, and the numpy-compatible seeding (SeedSequence -> PCG64) that makes reset(seed=k) reproduce the
 // reference's generator stream (rware/warehouse.py:758-760, 962-964; numpy/random/bit_generator.pyx).
 #include <cuda_runtime.h>
+#include <sched.h>
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
+#include <cctype>
 #include <cstdio>
 #include <ctime>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
 #include "../../include/rware_b200.h"
 #include "rw_launch.h"
 #include "rw_host_layout.h"
+#include "rw_hostpack.h"
 #include "rw_views.cuh"
+
+#define RW_DMA_FRAC0 0.25
 
 struct rw_handle {
     RwParams p;
@@ -30,15 +40,16 @@ struct rw_handle {
     float *d_obs = nullptr, *d_reward = nullptr;
     uint8_t *d_done = nullptr;
     cudaStream_t host_stream = nullptr;
-    // packed transport of rw_step_host: byte image of the observations on the device and in pinned host memory
+    // compressed transport of rw_step_host: bit / byte image of the observations on the device and in pinned host memory
     uint8_t *d_pack = nullptr, *h_pack = nullptr;
+    size_t pack_bytes = 0;
     cudaEvent_t pack_ev[8] = {};
-    int host_pack = 1;
-    // the packed transport depends on host threads and host memory bandwidth, which other tenants of the machine can take
-    // away; rw_step_host times its own calls and falls back to the plain copy while that one is measured faster
-    double us_packed = 0, us_plain = 0;  // smoothed call durations, 0 = not measured yet
+    cudaEvent_t dma_ev[2] = {};
+    int host_pack = 1;  // 0 plain float32 copy, 1 compressed (bits where the rows allow it, else bytes), 2 compressed, bytes only
+    // share of the observation rows that the copy engine delivers as plain float32 while the host pool expands the rest;
+    // follows the measured rates of the two unless fixed (rw_set_host_dma_share / RWARE_B200_HOST_DMA_SHARE)
+    double dma_frac = RW_DMA_FRAC0, dma_frac_fixed = -1.0;
     int64_t host_calls = 0;
-    int slow_streak = 0, plain_until = 0;
     // fused push all-gather
     void *d_gather = nullptr;
     void *peer_base[RW_MAX_PEERS] = {};
@@ -62,6 +73,7 @@ static int fail(rw_handle *h, int code, const std::string &msg) {
     } while (0)
 
 static int create_impl(rw_handle *h, const rw_config *cfg, int64_t num_envs, int device, const std::vector<uint16_t> &home);
+static cudaError_t free_pinned(void *p);
 
 extern "C" {
 
@@ -148,10 +160,10 @@ static int create_impl(rw_handle *h, const rw_config *cfg, int64_t num_envs, int
         while (wpc > 1 && p.sm_cta_bytes + wpc * p.sm_warp_bytes > smem_cap) wpc--;
         p.warps_per_cta = wpc;
     }
-    // packed host transport: on by default unless more than 4 ranks share this node's memory controllers (then the plain copy,
-    // which only loads the PCIe links, is the safer choice); RWARE_B200_HOST_PACK overrides
-    if (const char *lw = getenv("LOCAL_WORLD_SIZE")) h->host_pack = atoi(lw) <= 4;
-    if (getenv("RWARE_B200_HOST_PACK")) h->host_pack = atoi(getenv("RWARE_B200_HOST_PACK")) != 0;
+    // host transport of rw_step_host (see there); RWARE_B200_HOST_PACK = 0 | 1 | 2 and RWARE_B200_HOST_DMA_SHARE override
+    if (getenv("RWARE_B200_HOST_PACK")) h->host_pack = atoi(getenv("RWARE_B200_HOST_PACK"));
+    if (h->host_pack < 0 || h->host_pack > 2) h->host_pack = 1;
+    if (getenv("RWARE_B200_HOST_DMA_SHARE")) h->dma_frac_fixed = atof(getenv("RWARE_B200_HOST_DMA_SHARE"));
     if (getenv("RWARE_B200_FORCE_DYNAMIC")) rw_force_dynamic_kernels(atoi(getenv("RWARE_B200_FORCE_DYNAMIC")) != 0);
     CK(rw_configure_kernels(p, p.sm_cta_bytes + p.sm_warp_bytes * p.warps_per_cta));
 
@@ -221,8 +233,9 @@ int rw_destroy(rw_handle *h) {
     cudaSetDevice(h->device);
     if (h->d_pack) {
         cudaFree(h->d_pack);
-        cudaFreeHost(h->h_pack);
+        free_pinned(h->h_pack);
         for (auto &e : h->pack_ev) if (e) cudaEventDestroy(e);
+        for (auto &e : h->dma_ev) if (e) cudaEventDestroy(e);
     }
     cudaFree(h->d_highway); cudaFree(h->d_home); cudaFree(h->d_home_id); cudaFree(h->d_cta_tables); cudaFree(h->d_normx); cudaFree(h->d_normy);
     cudaFree(h->d_state); cudaFree(h->d_rng); cudaFree(h->d_err);
@@ -460,6 +473,68 @@ int rw_render_rgb(rw_handle *h, int64_t first_env, int64_t n_envs, uint8_t *out_
     return RW_OK;
 }
 
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ host-buffer entry points
+// NUMA node the GPU hangs off (sysfs), -1 if unknown
+static int gpu_numa_node(int device) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) return -1;
+    for (char *c = bus; *c; c++) *c = (char)tolower(*c);
+    char path[96];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    int node = -1;
+    if (FILE *f = fopen(path, "r")) {
+        if (fscanf(f, "%d", &node) != 1) node = -1;
+        fclose(f);
+    }
+    return node;
+}
+
+// Page-locked host memory whose pages sit on NUMA node `node` (next to the GPU's PCIe root and to the pool's workers): the
+// pages are first touched by this thread while it is confined to that node's CPUs, then registered with CUDA.  Best effort:
+// without NUMA information this is a plain cudaHostAlloc.
+static std::mutex g_reg_mu;
+static std::map<void *, size_t> g_registered;  // mmap'ed + cudaHostRegister'ed blocks handed out by alloc_pinned_on_node
+
+static cudaError_t alloc_pinned_on_node(void **out, size_t bytes, int node) {
+    cpu_set_t want, old;
+    static const bool numa = !(getenv("RWARE_B200_HOST_NUMA") && atoi(getenv("RWARE_B200_HOST_NUMA")) == 0);
+    if (!numa || node < 0 || !rw_host_cpus_of_node(node, &want) || sched_getaffinity(0, sizeof(old), &old) != 0)
+        return cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    const size_t len = (bytes + 4095) & ~(size_t)4095;
+    void *p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p == MAP_FAILED) return cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    madvise(p, len, MADV_HUGEPAGE);
+    const bool moved = sched_setaffinity(0, sizeof(want), &want) == 0;
+    memset(p, 0, len);  // first touch: the default policy places the pages on the node this thread runs on
+    if (moved) sched_setaffinity(0, sizeof(old), &old);
+    cudaError_t e = cudaHostRegister(p, len, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        munmap(p, len);
+        (void)cudaGetLastError();
+        return cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    }
+    std::lock_guard<std::mutex> g(g_reg_mu);
+    g_registered[p] = len;
+    *out = p;
+    return cudaSuccess;
+}
+
+static cudaError_t free_pinned(void *p) {
+    if (!p) return cudaSuccess;
+    size_t len = 0;
+    {
+        std::lock_guard<std::mutex> g(g_reg_mu);
+        auto it = g_registered.find(p);
+        if (it != g_registered.end()) { len = it->second; g_registered.erase(it); }
+    }
+    if (!len) return cudaFreeHost(p);
+    cudaError_t e = cudaHostUnregister(p);
+    munmap(p, len);
+    return e;
+}
+
 static int ensure_host_staging(rw_handle *h) {
     if (h->host_stream) return RW_OK;
     const RwParams &p = h->p;
@@ -472,89 +547,136 @@ static int ensure_host_staging(rw_handle *h) {
     return RW_OK;
 }
 
+extern "C" {
+
 int rw_step_host(rw_handle *h, const int32_t *actions_host, float *obs_host, float *reward_host, uint8_t *done_host) {
     if (!h || !actions_host) return RW_EINVAL;
     int rc = ensure_host_staging(h);
     if (rc) return rc;
     const RwParams &p = h->p;
     cudaStream_t st = h->host_stream;
-    const size_t n_obs = (size_t)p.E * p.n * p.L;
-    // The call is bound by PCIe.  Observation values are exact integers < 256 unless the coordinates are normalised, so
-    // large batches travel as one byte per value (4x fewer bytes) in 8 chunks and are widened to float32 by the host pool
-    // while the following chunk is in flight.  Small batches and normalised coordinates take the plain float32 copy.
-    bool pack = obs_host && h->host_pack && !p.norm_coords && n_obs >= ((size_t)1 << 20);
-    const bool adaptive = pack;
-    auto wall_us = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
-    const double t_call = wall_us();
-    if (adaptive) {
-        const int64_t k = h->host_calls++;
-        if (k == 2 || (k > 2 && k % 64 == 0)) pack = false;       // sample the plain copy now and then
-        else if (k < (int64_t)h->plain_until) pack = false;       // serving a fallback period
+    const size_t n_rows = (size_t)p.E * p.n, L = (size_t)p.L, n_obs = n_rows * L;
+    // What the caller gets is float32 rows in host memory.  The plain way is one device-to-host copy of them (PCIe bound).
+    // Unless the coordinates are normalised every value is a small integer, and in large batches the rows travel compressed
+    // and are expanded by the host pool (rw_hostpack.cpp): one BIT per value plus one byte per coordinate when everything
+    // else is a 0/1 flag (FLATTENED rows; image rows without the AGENT_DIRECTION layer), one BYTE per value otherwise.  The
+    // expansion is bound by host DRAM writes, so the copy engine delivers a share of the rows as plain float32 at the same
+    // time; the share follows the measured rates of the two (dma_frac).
+    bool has_dir_layer = false;
+    for (int i = 0; i < p.n_layers; i++) has_dir_layer |= (p.obs_kind != 0 && p.img_layers[i] == RW_LAYER_AGENT_DIRECTION);
+    const bool compress = obs_host && h->host_pack != 0 && !p.norm_coords && n_obs >= ((size_t)1 << 20);
+    const bool bits = compress && h->host_pack == 1 && !has_dir_layer && (reinterpret_cast<uintptr_t>(obs_host) & 63u) == 0;
+    const int nwide = p.obs_kind == 0 ? 2 : 0;
+    size_t rows_cpu = 0;
+    if (compress) {
+        const double f = h->dma_frac_fixed >= 0 ? h->dma_frac_fixed : h->dma_frac;
+        rows_cpu = (size_t)((1.0 - f) * (double)n_rows);
+        rows_cpu &= ~(size_t)63;  // rows_cpu * L is then a multiple of 64 floats: whole bit words, whole 64-byte lines
+        if (f <= 0.0 || rows_cpu > n_rows) rows_cpu = n_rows;
+        if (rows_cpu * L < ((size_t)1 << 18)) rows_cpu = 0;
     }
-    struct PoolGuard {  // the pool is woken first, so that its wake-up latency hides behind the copies and the kernel
-        bool on;
-        explicit PoolGuard(bool use, const void *dst) : on(use) { if (on) rw_hostpack_begin(dst); }
-        ~PoolGuard() { if (on) rw_hostpack_end(); }
-    } pool(pack, obs_host);
+    const size_t n_cpu = rows_cpu * L;
+    static const bool trace = getenv("RWARE_B200_HOST_TRACE") != nullptr;  // diagnostics: where the call spends its time
+    auto now_us = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
+    const double t_call = now_us();
+    if (n_cpu) rw_hostpool_prewake(obs_host);  // parked workers wake up while the copies and the kernel are in flight
     CK(cudaMemcpyAsync(h->d_actions, actions_host, (size_t)p.E * p.n * p.A * 4, cudaMemcpyHostToDevice, st));
     rc = rw_step(h, h->d_actions, obs_host ? h->d_obs : nullptr, h->d_reward, h->d_done, st);
     if (rc) return rc;
-    if (pack) {
+    int nch = 0;
+    size_t bpc = 0;
+    const size_t bits_bytes = ((n_obs + 31) / 32) * 4, off_wide = (bits_bytes + 255) & ~(size_t)255;
+    if (n_cpu) {
         if (!h->d_pack) {
-            CK(cudaMalloc(&h->d_pack, n_obs + 64));
-            CK(cudaHostAlloc((void **)&h->h_pack, n_obs + 64, cudaHostAllocDefault));
+            h->pack_bytes = n_obs + 256;  // the byte transport needs n_obs, the bit transport n_obs / 8 + 2 bytes per row
+            if (h->pack_bytes < off_wide + n_rows * 2 + 256) h->pack_bytes = off_wide + n_rows * 2 + 256;
+            CK(cudaMalloc(&h->d_pack, h->pack_bytes));
+            CK(alloc_pinned_on_node((void **)&h->h_pack, h->pack_bytes, gpu_numa_node(h->device)));
             for (auto &e : h->pack_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            CK(cudaEventCreate(&h->dma_ev[0]));
+            CK(cudaEventCreate(&h->dma_ev[1]));
         }
-        CK(rw_launch_pack_u8(h->d_obs, h->d_pack, n_obs, st));
-        const int NCH = 8;
-        const size_t per = ((n_obs + NCH - 1) / NCH + 255) & ~(size_t)255;
-        for (int c = 0; c < NCH; c++) {
-            const size_t a = (size_t)c * per, len = a >= n_obs ? 0 : (a + per > n_obs ? n_obs - a : per);
-            if (len) CK(cudaMemcpyAsync(h->h_pack + a, h->d_pack + a, len, cudaMemcpyDeviceToHost, st));
+        static const int want_chunks = getenv("RWARE_B200_HOST_CHUNKS") ? atoi(getenv("RWARE_B200_HOST_CHUNKS")) : 4;
+        const size_t nblocks = (n_cpu + RW_HOST_BLOCK - 1) / RW_HOST_BLOCK;
+        nch = want_chunks < 1 ? 1 : (want_chunks > 8 ? 8 : want_chunks);
+        if ((size_t)nch > nblocks) nch = (int)nblocks;
+        bpc = (nblocks + nch - 1) / nch;
+        nch = (int)((nblocks + bpc - 1) / bpc);
+        if (bits) CK(rw_launch_pack_bits(h->d_obs, (uint32_t *)h->d_pack, h->d_pack + off_wide, n_cpu, (int)L, nwide, rows_cpu, st));
+        else CK(rw_launch_pack_u8(h->d_obs, h->d_pack, n_cpu, st));
+        for (int c = 0; c < nch; c++) {
+            const size_t a = (size_t)c * bpc * RW_HOST_BLOCK, b = a + bpc * RW_HOST_BLOCK > n_cpu ? n_cpu : a + bpc * RW_HOST_BLOCK;
+            if (bits) {
+                const size_t ba = a / 8, bb = (b + 7) / 8;
+                CK(cudaMemcpyAsync(h->h_pack + ba, h->d_pack + ba, bb - ba, cudaMemcpyDeviceToHost, st));
+                if (nwide) {
+                    const size_t ra = a / L, rb = (b + L - 1) / L > rows_cpu ? rows_cpu : (b + L - 1) / L;
+                    CK(cudaMemcpyAsync(h->h_pack + off_wide + ra * nwide, h->d_pack + off_wide + ra * nwide, (rb - ra) * nwide,
+                                       cudaMemcpyDeviceToHost, st));
+                }
+            } else {
+                CK(cudaMemcpyAsync(h->h_pack + a, h->d_pack + a, b - a, cudaMemcpyDeviceToHost, st));
+            }
             CK(cudaEventRecord(h->pack_ev[c], st));
         }
-    } else if (obs_host) {
-        CK(cudaMemcpyAsync(obs_host, h->d_obs, n_obs * 4, cudaMemcpyDeviceToHost, st));
     }
     if (reward_host) CK(cudaMemcpyAsync(reward_host, h->d_reward, (size_t)p.E * p.n * 4, cudaMemcpyDeviceToHost, st));
     if (done_host) CK(cudaMemcpyAsync(done_host, h->d_done, (size_t)p.E, cudaMemcpyDeviceToHost, st));
-    if (pack) {
-        const int NCH = 8;
-        const size_t per = ((n_obs + NCH - 1) / NCH + 255) & ~(size_t)255;
-        static const bool trace = getenv("RWARE_B200_HOST_TRACE") != nullptr;  // diagnostics: where the call spends its time
-        auto now_us = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
-        double tw[NCH], te[NCH];
-        const double t1 = trace ? now_us() : 0;
+    const bool timed_dma = n_cpu && n_cpu < n_obs;
+    if (obs_host && n_cpu < n_obs) {  // the copy engine's share (everything, for the plain transport)
+        if (timed_dma) CK(cudaEventRecord(h->dma_ev[0], st));
+        CK(cudaMemcpyAsync(obs_host + n_cpu, h->d_obs + n_cpu, (n_obs - n_cpu) * 4, cudaMemcpyDeviceToHost, st));
+        if (timed_dma) CK(cudaEventRecord(h->dma_ev[1], st));
+    }
+    double t_first = 0, t_last = 0, t_done = 0;
+    if (n_cpu) {
+        RwHostJob job;
+        job.kind = bits ? RW_HOSTJOB_BITS : RW_HOSTJOB_WIDEN;
+        job.src = h->h_pack;
+        job.wide = h->h_pack + off_wide;
+        job.dst = obs_host;
+        job.n = n_cpu;
+        job.L = (int)L;
+        job.nwide = nwide;
+        job.n_rows = rows_cpu;
+        job.nchunks = nch;
+        job.blocks_per_chunk = bpc;
+        rw_hostpool_begin(job);
         cudaError_t err = cudaSuccess;
-        for (int c = 0; c < NCH && err == cudaSuccess; c++) {
-            const size_t a = (size_t)c * per, len = a >= n_obs ? 0 : (a + per > n_obs ? n_obs - a : per);
+        for (int c = 0; c < nch && err == cudaSuccess; c++) {
             err = cudaEventSynchronize(h->pack_ev[c]);
-            if (trace) tw[c] = now_us();
-            if (err == cudaSuccess && len) rw_hostpack_widen(h->h_pack + a, obs_host + a, len);
-            if (trace) te[c] = now_us();
+            if (err == cudaSuccess) rw_hostpool_chunk_ready(c + 1);
+            if (c == 0) t_first = now_us();
         }
-        if (trace) {
-            fprintf(stderr, "[rw_step_host]");
-            for (int c = 0; c < NCH; c++) fprintf(stderr, " c%d wait %.0f widen %.0f;", c, tw[c] - (c ? te[c - 1] : t1), te[c] - tw[c]);
-            fprintf(stderr, " threads %d\n", rw_hostpack_threads());
-        }
+        t_last = now_us();
+        if (err != cudaSuccess) rw_hostpool_cancel();
+        rw_hostpool_finish();
+        t_done = now_us();
         CK(err);
     }
     CK(cudaStreamSynchronize(st));
-    if (adaptive) {
-        const double us = wall_us() - t_call;
-        double &avg = pack ? h->us_packed : h->us_plain;
-        avg = avg == 0 ? us : 0.75 * avg + 0.25 * us;
-        if (pack && h->us_plain > 0 && us > 1.25 * h->us_plain) {
-            if (++h->slow_streak >= 2) {  // two slow packed calls in a row: plain copies for the next 64 calls
-                h->plain_until = (int)(h->host_calls + 64);
-                h->slow_streak = 0;
-                h->us_packed = 0;
-            }
-        } else if (pack) {
-            h->slow_streak = 0;
-        }
+    const double t_end = now_us();
+    double dma_ms = 0;
+    if (timed_dma) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, h->dma_ev[0], h->dma_ev[1]));
+        dma_ms = ms;
+        // re-balance: both sides should finish together.  Rates as observed in this call (the expansion's includes its waits
+        // for the chunks; both include whatever the other one took from the memory system).
+        const double cpu_rate = (double)n_cpu * 4 / ((t_done - t_first) > 1 ? (t_done - t_first) : 1);            // bytes / us
+        const double dma_rate = (double)(n_obs - n_cpu) * 4 / ((dma_ms * 1e3) > 1 ? (dma_ms * 1e3) : 1);
+        double target = dma_rate / (dma_rate + cpu_rate);
+        if (target > 0.9) target = 0.9;
+        if (target < 0.02) target = 0.02;
+        h->dma_frac = 0.5 * h->dma_frac + 0.5 * target;
     }
+    h->host_calls++;
+    if (trace)
+        fprintf(stderr, "[rw_step_host] %s rows_cpu %zu/%zu chunks %d | enqueue %.0f first-chunk %.0f last-chunk %.0f expand-done %.0f "
+                        "end %.0f us | dma %.0f us | dma_frac -> %.3f | threads %d isa %d\n",
+                !n_cpu ? "plain" : bits ? "bits" : "bytes", rows_cpu, n_rows, nch, 0.0, n_cpu ? t_first - t_call : 0.0,
+                n_cpu ? t_last - t_call : 0.0, n_cpu ? t_done - t_call : 0.0, t_end - t_call, dma_ms * 1e3, h->dma_frac,
+                n_cpu ? rw_hostpool_threads() : 0, n_cpu ? rw_hostpool_isa() : 0);
     return RW_OK;
 }
 
@@ -566,19 +688,73 @@ int rw_obs_bytes(rw_handle *h, const float *obs_dev, uint8_t *out_dev, void *str
     return RW_OK;
 }
 
-int rw_set_host_transport(rw_handle *h, int packed) {
-    if (!h) return RW_EINVAL;
-    h->host_pack = packed ? 1 : 0;
-    h->host_calls = 0; h->us_packed = h->us_plain = 0; h->slow_streak = 0; h->plain_until = 0;
+int rw_set_host_transport(rw_handle *h, int mode) {
+    if (!h || mode < 0 || mode > 2) return RW_EINVAL;
+    h->host_pack = mode;
+    h->host_calls = 0;
+    h->dma_frac = RW_DMA_FRAC0;
+    return RW_OK;
+}
+
+int rw_set_host_dma_share(rw_handle *h, double share) {
+    if (!h || share > 1.0) return RW_EINVAL;
+    h->dma_frac_fixed = share < 0 ? -1.0 : share;
+    return RW_OK;
+}
+
+int rw_get_host_dma_share(const rw_handle *h, double *share) {
+    if (!h || !share) return RW_EINVAL;
+    *share = h->dma_frac_fixed >= 0 ? h->dma_frac_fixed : h->dma_frac;
     return RW_OK;
 }
 
 int rw_host_widen_u8(const uint8_t *src, float *dst, int64_t n) {
     if (!src || !dst || n < 0) return RW_EINVAL;
-    rw_hostpack_begin(dst);
-    rw_hostpack_widen(src, dst, (size_t)n);
-    rw_hostpack_end();
-    return rw_hostpack_threads();
+    RwHostJob job;
+    job.kind = RW_HOSTJOB_WIDEN;
+    job.src = src;
+    job.dst = dst;
+    job.n = (size_t)n;
+    rw_hostpool_begin(job);
+    rw_hostpool_finish();
+    return rw_hostpool_threads();
+}
+
+int rw_host_expand_bits(const uint8_t *bits, const uint8_t *wide, float *dst, int64_t n_rows, int32_t row_len, int32_t n_wide) {
+    if (!bits || !dst || n_rows < 0 || row_len < 1 || n_wide < 0 || n_wide > row_len || (n_wide && !wide)) return RW_EINVAL;
+    RwHostJob job;
+    job.kind = RW_HOSTJOB_BITS;
+    job.src = bits;
+    job.wide = wide;
+    job.dst = dst;
+    job.n = (size_t)n_rows * (size_t)row_len;
+    job.L = row_len;
+    job.nwide = n_wide;
+    job.n_rows = (size_t)n_rows;
+    rw_hostpool_begin(job);
+    rw_hostpool_finish();
+    return rw_hostpool_threads();
+}
+
+int rw_host_stream_probe(float *dst, int64_t n, int32_t repeats, double *gb_per_s) {
+    if (!dst || n < 1 || repeats < 1 || !gb_per_s) return RW_EINVAL;
+    auto now_us = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
+    RwHostJob job;
+    job.kind = RW_HOSTJOB_FILL;
+    job.dst = dst;
+    job.n = (size_t)n;
+    double best = 0;
+    rw_hostpool_prewake(dst);
+    for (int r = 0; r < repeats + 1; r++) {  // the first pass warms the pool up
+        job.fill_value = (float)r;
+        const double t0 = now_us();
+        rw_hostpool_begin(job);
+        rw_hostpool_finish();
+        const double gbs = (double)n * 4 / ((now_us() - t0) * 1e3);
+        if (r > 0 && gbs > best) best = gbs;
+    }
+    *gb_per_s = best;
+    return rw_hostpool_threads();
 }
 
 int rw_reset_host(rw_handle *h, const uint64_t *seeds_host, float *obs_host) {
@@ -601,14 +777,30 @@ int rw_reset_host(rw_handle *h, const uint64_t *seeds_host, float *obs_host) {
 int rw_host_alloc(void **out, int64_t bytes) {
     rw_handle *h = nullptr;
     if (!out || bytes <= 0) return RW_EINVAL;
-    CK(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault));
+    CK(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable));
+    return RW_OK;
+}
+
+int rw_host_alloc_near(rw_handle *h, void **out, int64_t bytes) {
+    if (!h || !out || bytes <= 0) return RW_EINVAL;
+    CK(cudaSetDevice(h->device));
+    CK(alloc_pinned_on_node(out, (size_t)bytes, gpu_numa_node(h->device)));
     return RW_OK;
 }
 
 int rw_host_free(void *ptr) {
     rw_handle *h = nullptr;
-    CK(cudaFreeHost(ptr));
+    CK(free_pinned(ptr));
     return RW_OK;
 }
+
+int rw_host_numa_node(const void *ptr) {
+    void *page = reinterpret_cast<void *>(reinterpret_cast<uintptr_t>(ptr) & ~(uintptr_t)4095);
+    int status = -1;
+    const long r = syscall(SYS_move_pages, 0, 1UL, &page, nullptr, &status, 0);
+    return r == 0 && status >= 0 ? status : -1;
+}
+
+int rw_gpu_numa_node(const rw_handle *h) { return h ? gpu_numa_node(h->device) : -1; }
 
 }  // extern "C"

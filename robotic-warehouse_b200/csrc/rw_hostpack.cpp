@@ -1,14 +1,18 @@
-// rw_hostpack.cpp -- host half of the packed end-to-end transport (rw_step_host).
+// rw_hostpack.cpp -- host half of the end-to-end transport (rw_step_host).
 //
-// The step's observations are exact small integers stored as float32 (coordinates < 256, 0/1 flags), and the end-to-end call
-// is bound by moving them over PCIe.  rw_step_host therefore ships them as one byte per value and widens them back to float32
-// on the host, chunk by chunk while the next chunk is still in flight.  This file holds the widening: a small pool of worker
-// threads (created on first use, parked on a condition variable between calls, spinning between the chunks of one call) and
-// an AVX2 inner loop with streaming stores.  It is transport code only: no part of the simulation runs on the host.
-#include <immintrin.h>
+// The caller of rw_step_host wants float32 observation rows in HOST memory (the reference's contract,
+// rware/warehouse.py:17-28, 631-674): 75.5 MB per step of 65 536 tiny-4ag worlds.  Every value of such a row is a 0/1 flag
+// except the agent's own coordinates, so the device ships one BIT per flag plus one byte per coordinate (11 B instead of
+// 284 B per row over PCIe) and this file expands them into the caller's buffer: a pool of worker threads, woken once per call,
+// pulls 64 KB output blocks from a shared counter (late or descheduled workers simply take fewer blocks) and writes them with
+// non-temporal stores (one 16-bit mask -> one 64-byte line with AVX-512; a 256-entry table with AVX2).  A second job kind
+// widens one byte per value (image observations with the AGENT_DIRECTION layer, whose values reach 4).  The expansion is bound
+// by the host's DRAM write bandwidth; rw_step_host therefore lets the GPU's copy engine write part of the rows as plain
+// float32 at the same time (rw_capi.cu).  Transport code only: no part of the simulation runs on the host.
 #include <pthread.h>
 #include <sched.h>
 #include <sys/syscall.h>
+#include <time.h>
 #include <unistd.h>
 
 #include <atomic>
@@ -19,8 +23,38 @@
 #include <thread>
 #include <vector>
 
+#include "rw_hostpack.h"
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+#define RW_X86 1
+static inline void cpu_relax() { _mm_pause(); }
+#else
+#define RW_X86 0
+static inline void cpu_relax() {
+#if defined(__aarch64__)
+    asm volatile("yield" ::: "memory");
+#endif
+}
+#endif
+
 namespace {
 
+double now_us() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
+
+// ------------------------------------------------------------------------------------------------ inner loops
+// Every job is cut into blocks of RW_HOST_BLOCK floats (64 KB of output); a block is the unit a thread pulls.
+constexpr size_t BLOCK = RW_HOST_BLOCK;
+
+// ---- one byte per value -> float32
+void widen_scalar(const uint8_t *in, float *out, size_t n) {
+    for (size_t i = 0; i < n; i++) out[i] = (float)in[i];
+}
+#if RW_X86
 __attribute__((target("avx2"))) void widen_avx2(const uint8_t *in, float *out, size_t n) {
     size_t i = 0;
     while (i < n && (reinterpret_cast<uintptr_t>(out + i) & 31u)) { out[i] = (float)in[i]; i++; }  // align the stores
@@ -35,20 +69,144 @@ __attribute__((target("avx2"))) void widen_avx2(const uint8_t *in, float *out, s
     for (; i < n; i++) out[i] = (float)in[i];
     _mm_sfence();
 }
-
-void widen_scalar(const uint8_t *in, float *out, size_t n) {
-    for (size_t i = 0; i < n; i++) out[i] = (float)in[i];
-}
-
+#endif
 void widen(const uint8_t *in, float *out, size_t n) {
+#if RW_X86
     static const bool avx2 = __builtin_cpu_supports("avx2");
-    if (avx2) widen_avx2(in, out, n);
-    else widen_scalar(in, out, n);
+    if (avx2) return widen_avx2(in, out, n);
+#endif
+    widen_scalar(in, out, n);
 }
 
-// NUMA placement: the widening is a pure memory stream, and on a two-socket host half of it crosses the socket interconnect
-// unless the workers run next to the memory.  The node of the destination buffer is looked up (move_pages with a NULL target
-// only queries) and the workers are confined to that node's CPUs.  Every step is best effort: failures leave the scheduler free.
+// ---- one bit per value (+ one byte for each of the first `nwide` values of a row) -> float32
+// Float j of the output is 1.0f iff bit j of `bits` is set, except the "wide" positions (row * L + k, k < nwide), which take
+// (float)wide[row * nwide + k] whatever their bit says.  [a, b) is a range of floats; a is a multiple of 16 and out + a is
+// 64-byte aligned for the vector forms.
+struct WideCursor {  // the next wide position at or after a float index
+    size_t w, pos;
+    int k;
+};
+inline WideCursor wide_from(size_t a, int L, int nwide, size_t n_rows) {
+    WideCursor c{(size_t)-1, (size_t)-1, 0};
+    if (nwide <= 0) return c;
+    size_t row = a / (size_t)L;
+    int rem = (int)(a - row * (size_t)L);
+    if (rem >= nwide) { row++; rem = 0; }
+    if (row >= n_rows) return c;
+    c.w = row * (size_t)nwide + (size_t)rem;
+    c.pos = row * (size_t)L + (size_t)rem;
+    c.k = rem;
+    return c;
+}
+inline void wide_next(WideCursor &c, int L, int nwide, size_t n_rows) {
+    c.w++;
+    if (++c.k == nwide) { c.k = 0; c.pos += (size_t)(L - nwide + 1); }
+    else c.pos++;
+    if (c.w >= n_rows * (size_t)nwide) c.pos = (size_t)-1;
+}
+
+void expand_scalar(const uint8_t *bits, const uint8_t *wide, float *out, size_t a, size_t b, int L, int nwide, size_t n_rows) {
+    for (size_t i = a; i < b; i++) out[i] = ((bits[i >> 3] >> (i & 7)) & 1) ? 1.0f : 0.0f;
+    for (WideCursor c = wide_from(a, L, nwide, n_rows); c.pos < b; wide_next(c, L, nwide, n_rows)) out[c.pos] = (float)wide[c.w];
+}
+
+#if RW_X86
+__attribute__((target("avx512f"))) void expand_avx512(const uint8_t *bits, const uint8_t *wide, float *out, size_t a, size_t b,
+                                                      int L, int nwide, size_t n_rows) {
+    const uint16_t *m16 = reinterpret_cast<const uint16_t *>(bits);
+    const __m512 ones = _mm512_set1_ps(1.0f);
+    WideCursor c = wide_from(a, L, nwide, n_rows);
+    size_t i = a;
+    for (; i + 16 <= b; i += 16) {
+        __m512 v = _mm512_maskz_mov_ps((__mmask16)m16[i >> 4], ones);
+        while (c.pos < i + 16) {
+            v = _mm512_mask_mov_ps(v, (__mmask16)(1u << (c.pos - i)), _mm512_set1_ps((float)wide[c.w]));
+            wide_next(c, L, nwide, n_rows);
+        }
+        _mm512_stream_ps(out + i, v);
+    }
+    _mm_sfence();
+    if (i < b) expand_scalar(bits, wide, out, i, b, L, nwide, n_rows);
+}
+
+alignas(64) float g_lut8[256][8];  // byte of flags -> eight floats
+void build_lut() {
+    for (int m = 0; m < 256; m++)
+        for (int k = 0; k < 8; k++) g_lut8[m][k] = ((m >> k) & 1) ? 1.0f : 0.0f;
+}
+__attribute__((target("avx2"))) void expand_avx2(const uint8_t *bits, const uint8_t *wide, float *out, size_t a, size_t b, int L,
+                                                 int nwide, size_t n_rows) {
+    WideCursor c = wide_from(a, L, nwide, n_rows);
+    size_t i = a;
+    for (; i + 8 <= b; i += 8) {
+        __m256 v = _mm256_load_ps(g_lut8[bits[i >> 3]]);
+        if (c.pos < i + 8) {
+            alignas(32) float tmp[8];
+            _mm256_store_ps(tmp, v);
+            while (c.pos < i + 8) { tmp[c.pos - i] = (float)wide[c.w]; wide_next(c, L, nwide, n_rows); }
+            v = _mm256_load_ps(tmp);
+        }
+        _mm256_stream_ps(out + i, v);
+    }
+    _mm_sfence();
+    if (i < b) expand_scalar(bits, wide, out, i, b, L, nwide, n_rows);
+}
+#endif
+
+int g_isa = -1;  // 0 scalar, 1 avx2, 2 avx512
+int detect_isa() {
+    int isa = 0;
+#if RW_X86
+    if (__builtin_cpu_supports("avx2")) isa = 1;
+    if (__builtin_cpu_supports("avx512f")) isa = 2;
+    build_lut();
+#endif
+    if (const char *ev = getenv("RWARE_B200_HOST_ISA")) {  // diagnostics: cap the instruction set (0 scalar, 1 avx2, 2 avx512)
+        const int cap = atoi(ev);
+        if (cap < isa) isa = cap < 0 ? 0 : cap;
+    }
+    return isa;
+}
+
+void expand(const uint8_t *bits, const uint8_t *wide, float *out, size_t a, size_t b, int L, int nwide, size_t n_rows) {
+#if RW_X86
+    const bool aligned = ((reinterpret_cast<uintptr_t>(out) & 63u) == 0) && (a % 16 == 0);
+    if (aligned && g_isa == 2) return expand_avx512(bits, wide, out, a, b, L, nwide, n_rows);
+    if (aligned && g_isa >= 1) return expand_avx2(bits, wide, out, a, b, L, nwide, n_rows);
+#endif
+    expand_scalar(bits, wide, out, a, b, L, nwide, n_rows);
+}
+
+// ---- streaming fill (bandwidth probe: what the host's memory system takes from this pool when nothing has to be decoded)
+#if RW_X86
+__attribute__((target("avx512f"))) void fill_avx512(float *out, size_t a, size_t b, float value) {
+    const __m512 v = _mm512_set1_ps(value);
+    size_t i = a;
+    for (; i + 16 <= b; i += 16) _mm512_stream_ps(out + i, v);
+    for (; i < b; i++) out[i] = value;
+    _mm_sfence();
+}
+__attribute__((target("avx2"))) void fill_avx2(float *out, size_t a, size_t b, float value) {
+    const __m256 v = _mm256_set1_ps(value);
+    size_t i = a;
+    for (; i + 8 <= b; i += 8) _mm256_stream_ps(out + i, v);
+    for (; i < b; i++) out[i] = value;
+    _mm_sfence();
+}
+#endif
+void fill(float *out, size_t a, size_t b, float value) {
+#if RW_X86
+    const bool aligned = ((reinterpret_cast<uintptr_t>(out) & 63u) == 0) && (a % 16 == 0);
+    if (aligned && g_isa == 2) return fill_avx512(out, a, b, value);
+    if (aligned && g_isa >= 1) return fill_avx2(out, a, b, value);
+#endif
+    for (size_t i = a; i < b; i++) out[i] = value;
+}
+
+// ------------------------------------------------------------------------------------------------ NUMA helpers
+// The expansion is a pure memory stream; on a two-socket host half of it crosses the socket interconnect unless the workers
+// run next to the memory.  The node of the destination buffer is looked up (move_pages with a NULL target only queries) and
+// the workers are confined to that node's CPUs.  Every step is best effort: failures leave the scheduler free.
 int node_of(const void *p) {
     void *page = reinterpret_cast<void *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)4095);
     int status = -1;
@@ -56,7 +214,9 @@ int node_of(const void *p) {
     return rc == 0 && status >= 0 ? status : -1;
 }
 
-bool cpus_of_node(int node, cpu_set_t *set) {
+}  // namespace
+
+bool rw_host_cpus_of_node(int node, cpu_set_t *set) {
     char path[96], buf[1024];
     snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
     FILE *f = fopen(path, "r");
@@ -66,7 +226,8 @@ bool cpus_of_node(int node, cpu_set_t *set) {
     if (!ok) return false;
     CPU_ZERO(set);
     int count = 0;
-    for (char *tok = strtok(buf, ",\n"); tok; tok = strtok(nullptr, ",\n")) {  // "0-31,64-95"
+    char *save = nullptr;
+    for (char *tok = strtok_r(buf, ",\n", &save); tok; tok = strtok_r(nullptr, ",\n", &save)) {  // "0-31,64-95"
         int a = 0, b = 0;
         const int k = sscanf(tok, "%d-%d", &a, &b);
         if (k < 1) continue;
@@ -76,113 +237,10 @@ bool cpus_of_node(int node, cpu_set_t *set) {
     return count > 0;
 }
 
-struct Pool {
-    std::vector<std::thread> workers;
-    int node = -2;  // NUMA node the workers are currently confined to (-2: never placed)
-    pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
-    pthread_cond_t cv = PTHREAD_COND_INITIALIZER;
-    bool awake = false, quit = false;      // under mu: workers leave the condition variable while `awake`
-    std::atomic<uint64_t> generation{0};   // bumped once per job
-    std::atomic<int> done{0};              // workers that finished the current job
-    std::atomic<int> ready{0};             // workers that are spinning on `generation` (0 = all parked)
-    const uint8_t *in = nullptr;
-    float *out = nullptr;
-    size_t n = 0;
-    int T = 1;  // participants of a job, caller included
+namespace {
 
-    void slice(int t) const {
-        const size_t per = ((n + T - 1) / T + 31) & ~(size_t)31;
-        const size_t a = (size_t)t * per;
-        if (a < n) widen(in + a, out + a, (a + per > n ? n : a + per) - a);
-    }
-
-    void worker(int t) {
-        for (;;) {
-            pthread_mutex_lock(&mu);
-            while (!awake && !quit) pthread_cond_wait(&cv, &mu);
-            const bool stop = quit;
-            pthread_mutex_unlock(&mu);
-            if (stop) return;
-            // the caller posts its first job only after every worker has announced itself, so `seen` is the value before it
-            uint64_t seen = generation.load(std::memory_order_acquire);
-            ready.fetch_add(1, std::memory_order_release);
-            for (;;) {  // between the chunks of one call: spin
-                uint64_t g;
-                bool asleep = false;
-                while ((g = generation.load(std::memory_order_acquire)) == seen) {
-                    if (!__atomic_load_n(&awake, __ATOMIC_ACQUIRE)) { asleep = true; break; }
-                    _mm_pause();
-                }
-                if (asleep) break;
-                seen = g;
-                slice(t);
-                done.fetch_add(1, std::memory_order_release);
-            }
-            ready.fetch_sub(1, std::memory_order_release);  // back to the condition variable
-        }
-    }
-
-    void start(int threads) {
-        T = threads < 1 ? 1 : threads;
-        try {
-            for (int t = 1; t < T; t++) workers.emplace_back([this, t] { worker(t); });
-        } catch (...) {  // thread limit reached: work with the threads that exist (slices are dealt by T, so fix it first)
-        }
-        // workers read T only after the first wake(), which happens after this assignment
-        T = (int)workers.size() + 1;
-    }
-
-    void place(const void *dst) {
-        const int want = node_of(dst);
-        if (want < 0 || want == node) return;
-        cpu_set_t set;
-        if (!cpus_of_node(want, &set)) return;
-        for (auto &w : workers) pthread_setaffinity_np(w.native_handle(), sizeof(set), &set);
-        node = want;
-    }
-
-    void wake() {
-        if (T == 1) return;
-        pthread_mutex_lock(&mu);
-        __atomic_store_n(&awake, true, __ATOMIC_RELEASE);
-        pthread_cond_broadcast(&cv);
-        pthread_mutex_unlock(&mu);
-        while (ready.load(std::memory_order_acquire) != T - 1) _mm_pause();
-    }
-
-    void sleep() {  // returns once every worker has left the spin loop, so the next wake() starts from a clean state
-        if (T == 1) return;
-        pthread_mutex_lock(&mu);
-        __atomic_store_n(&awake, false, __ATOMIC_RELEASE);
-        pthread_mutex_unlock(&mu);
-        while (ready.load(std::memory_order_acquire) != 0) _mm_pause();
-    }
-
-    void run(const uint8_t *src, float *dst, size_t count) {
-        in = src; out = dst; n = count;
-        if (T == 1) { slice(0); return; }
-        done.store(0, std::memory_order_relaxed);
-        generation.fetch_add(1, std::memory_order_release);
-        slice(0);
-        while (done.load(std::memory_order_acquire) != T - 1) _mm_pause();
-    }
-
-    ~Pool() {
-        if (T > 1) {
-            pthread_mutex_lock(&mu);
-            quit = true;
-            pthread_cond_broadcast(&cv);
-            pthread_mutex_unlock(&mu);
-            for (auto &w : workers) w.join();
-        }
-    }
-};
-
-Pool *g_pool = nullptr;
-pthread_mutex_t g_pool_mu = PTHREAD_MUTEX_INITIALIZER;  // one widening at a time per process
-
-// CPUs this process may use on average: the cgroup v2 / v1 CFS quota if there is one (a spinning pool larger than the quota
-// gets the whole process throttled for the rest of the 100 ms period), else 0
+// CPUs this process may use on average: the cgroup v2 / v1 CFS quota if there is one (a pool that keeps more threads busy
+// than the quota gets the whole process throttled for the rest of the 100 ms period), else 0
 double cgroup_cpu_quota() {
     double quota = 0;
     if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {  // "max 100000" or "<quota> <period>"
@@ -198,6 +256,13 @@ double cgroup_cpu_quota() {
     return q > 0 && period > 0 ? (double)q / (double)period : 0;
 }
 
+int count_nodes() {
+    int n = 0;
+    cpu_set_t s;
+    while (n < 64 && rw_host_cpus_of_node(n, &s)) n++;
+    return n < 1 ? 1 : n;
+}
+
 int default_threads() {
     const char *ev = getenv("RWARE_B200_HOST_THREADS");
     if (ev && atoi(ev) > 0) return atoi(ev);
@@ -205,37 +270,204 @@ int default_threads() {
     if (hw == 0) hw = 1;
     unsigned ranks = 1;  // one process per GPU under torchrun: share the cores between the ranks of this node
     if (const char *lw = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(lw) > 0 ? (unsigned)atoi(lw) : 1;
-    double budget = hw >= 4 ? hw / 2.0 : hw;  // one thread per physical core at most; streaming stores saturate the
-    const double quota = cgroup_cpu_quota();  // memory controllers long before all of them are busy
-    if (quota > 0 && 0.75 * quota < budget) budget = 0.75 * quota;  // leave a quarter of it to the caller, CUDA and the framework
+    // one thread per physical core at most.  A single rank stays on the socket of its buffer; streaming stores saturate that
+    // socket's memory controllers well before all of its cores are busy.
+    double budget = hw >= 4 ? hw / 2.0 : hw;
+    const int nodes = count_nodes();
+    if (ranks < (unsigned)nodes) budget = budget * ranks / nodes;
+    const double quota = cgroup_cpu_quota();
+    if (quota > 0 && quota < budget) budget = quota;  // workers block between calls, so the pool may use the whole quota
     int t = (int)(budget / ranks);
     return t < 1 ? 1 : (t > 32 ? 32 : t);
 }
 
-}  // namespace
+// ------------------------------------------------------------------------------------------------ the pool
+struct Slot {  // parameters of one job; slot (generation & 1) is stable from publication until every block is done
+    RwHostJob job;
+    size_t nblocks = 0;
+    std::atomic<int> chunks_ready{0};
+    std::atomic<int> cancelled{0};
+    std::atomic<size_t> blocks_done{0};
+    char pad[64];
+};
+
+struct Pool {
+    std::vector<std::thread> workers;
+    int T = 1;      // participants of a job, caller included
+    int node = -2;  // NUMA node the workers are currently confined to (-2: never placed)
+    pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+    pthread_cond_t cv = PTHREAD_COND_INITIALIZER;
+    uint64_t wake_seq = 0;  // under mu
+    bool quit = false;      // under mu
+    // (generation << 32) | blocks still to hand out.  A thread takes a block by CAS-decrementing the low half; a successful
+    // CAS on generation g proves that job g is still incomplete, so reading slot[g & 1] afterwards is safe.
+    std::atomic<uint64_t> ctr{0};
+    Slot slot[2];
+    double spin_us = 250;  // a worker without work spins this long (the copies and the kernel of a call are in flight) before it parks
+
+    void run_block(const Slot &s, size_t blk) {
+        const RwHostJob &j = s.job;
+        const size_t a = blk * BLOCK, b = a + BLOCK > j.n ? j.n : a + BLOCK;
+        if (j.nchunks > 1) {  // the bytes this block decodes arrive with chunk (blk / blocks_per_chunk)
+            const int need = (int)(blk / j.blocks_per_chunk) + 1;
+            while (s.chunks_ready.load(std::memory_order_acquire) < need) cpu_relax();
+        }
+        if (s.cancelled.load(std::memory_order_relaxed)) return;
+        switch (j.kind) {
+            case RW_HOSTJOB_WIDEN: widen(j.src + a, j.dst + a, b - a); break;
+            case RW_HOSTJOB_BITS: expand(j.src, j.wide, j.dst, a, b, j.L, j.nwide, j.n_rows); break;
+            default: fill(j.dst, a, b, j.fill_value); break;
+        }
+    }
+
+    // pulls blocks until the current job has none left; returns true if it did any work
+    bool drain() {
+        bool any = false;
+        uint64_t v = ctr.load(std::memory_order_acquire);
+        for (;;) {
+            const uint32_t left = (uint32_t)v;
+            if (left == 0) return any;
+            if (!ctr.compare_exchange_weak(v, v - 1, std::memory_order_acq_rel, std::memory_order_acquire)) continue;
+            Slot &s = slot[(v >> 32) & 1];
+            run_block(s, s.nblocks - left);
+            s.blocks_done.fetch_add(1, std::memory_order_release);
+            any = true;
+            v = ctr.load(std::memory_order_acquire);
+        }
+    }
+
+    void worker() {
+        uint64_t seen = 0;
+        double idle_since = now_us();
+        for (;;) {
+            if (drain()) { idle_since = now_us(); continue; }
+            if (now_us() - idle_since < spin_us) { cpu_relax(); continue; }
+            pthread_mutex_lock(&mu);
+            while (!quit && wake_seq == seen) pthread_cond_wait(&cv, &mu);
+            seen = wake_seq;
+            const bool stop = quit;
+            pthread_mutex_unlock(&mu);
+            if (stop) return;
+            idle_since = now_us();
+        }
+    }
+
+    void start(int threads) {
+        T = threads < 1 ? 1 : threads;
+        try {
+            for (int t = 1; t < T; t++) workers.emplace_back([this] { worker(); });
+        } catch (...) {  // thread limit reached: work with the threads that exist
+        }
+        T = (int)workers.size() + 1;
+    }
+
+    void place(const void *dst) {
+        const int want = node_of(dst);
+        if (want < 0 || want == node) return;
+        cpu_set_t set;
+        if (!rw_host_cpus_of_node(want, &set)) return;
+        for (auto &w : workers) pthread_setaffinity_np(w.native_handle(), sizeof(set), &set);
+        node = want;
+    }
+
+    void wake() {
+        if (T == 1) return;
+        pthread_mutex_lock(&mu);
+        wake_seq++;
+        pthread_cond_broadcast(&cv);
+        pthread_mutex_unlock(&mu);
+    }
+
+    ~Pool() {
+        if (T > 1) {
+            pthread_mutex_lock(&mu);
+            quit = true;
+            wake_seq++;
+            pthread_cond_broadcast(&cv);
+            pthread_mutex_unlock(&mu);
+            for (auto &w : workers) w.join();
+        }
+    }
+};
+
+Pool *g_pool = nullptr;
+pthread_mutex_t g_create_mu = PTHREAD_MUTEX_INITIALIZER;
+pthread_mutex_t g_job_mu = PTHREAD_MUTEX_INITIALIZER;  // one job at a time per process
+Slot *g_cur = nullptr;                                 // under g_job_mu: the slot of the job in flight
 
 // a forked child inherits the pool object but none of its threads: start over there (the parent's pool is simply abandoned)
-static void rw_hostpack_after_fork_in_child() {
+void after_fork_in_child() {
     g_pool = nullptr;
-    pthread_mutex_init(&g_pool_mu, nullptr);
+    g_cur = nullptr;
+    pthread_mutex_init(&g_create_mu, nullptr);
+    pthread_mutex_init(&g_job_mu, nullptr);
 }
 
-// internal interface used by rw_capi.cu
-void rw_hostpack_begin(const void *dst) {
-    pthread_mutex_lock(&g_pool_mu);
+Pool *pool() {
+    Pool *p = __atomic_load_n(&g_pool, __ATOMIC_ACQUIRE);
+    if (p) return p;
+    pthread_mutex_lock(&g_create_mu);
     if (!g_pool) {
-        static const int registered = pthread_atfork(nullptr, nullptr, rw_hostpack_after_fork_in_child);
+        static const int registered = pthread_atfork(nullptr, nullptr, after_fork_in_child);
         (void)registered;
-        g_pool = new Pool();
-        g_pool->start(default_threads());
+        if (g_isa < 0) g_isa = detect_isa();
+        Pool *np = new Pool();
+        if (const char *ev = getenv("RWARE_B200_HOST_SPIN_US")) np->spin_us = atof(ev);
+        np->start(default_threads());
+        __atomic_store_n(&g_pool, np, __ATOMIC_RELEASE);
     }
+    p = g_pool;
+    pthread_mutex_unlock(&g_create_mu);
+    return p;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ internal interface (rw_hostpack.h)
+void rw_hostpool_prewake(const void *dst) {
+    Pool *p = pool();
     static const bool numa = !(getenv("RWARE_B200_HOST_NUMA") && atoi(getenv("RWARE_B200_HOST_NUMA")) == 0);
-    if (numa && dst) g_pool->place(dst);
-    g_pool->wake();
+    if (numa && dst && p->node == -2) p->place(dst);  // first placement; later moves happen under the job lock
+    p->wake();
 }
-void rw_hostpack_widen(const uint8_t *src, float *dst, size_t n) { g_pool->run(src, dst, n); }
-void rw_hostpack_end() {
-    g_pool->sleep();
-    pthread_mutex_unlock(&g_pool_mu);
+
+void rw_hostpool_begin(const RwHostJob &job) {
+    Pool *p = pool();
+    pthread_mutex_lock(&g_job_mu);
+    static const bool numa = !(getenv("RWARE_B200_HOST_NUMA") && atoi(getenv("RWARE_B200_HOST_NUMA")) == 0);
+    if (numa && job.dst) p->place(job.dst);
+    const uint64_t gen = (p->ctr.load(std::memory_order_acquire) >> 32) + 1;
+    Slot &s = p->slot[gen & 1];
+    s.job = job;
+    s.nblocks = (job.n + BLOCK - 1) / BLOCK;
+    if (s.job.nchunks < 1) s.job.nchunks = 1;
+    if (s.job.blocks_per_chunk < 1) s.job.blocks_per_chunk = s.nblocks ? s.nblocks : 1;
+    s.chunks_ready.store(0, std::memory_order_relaxed);
+    s.cancelled.store(0, std::memory_order_relaxed);
+    s.blocks_done.store(0, std::memory_order_relaxed);
+    g_cur = &s;
+    p->ctr.store((gen << 32) | (uint64_t)(uint32_t)s.nblocks, std::memory_order_release);
+    p->wake();
 }
-int rw_hostpack_threads() { return g_pool ? g_pool->T : default_threads(); }
+
+void rw_hostpool_chunk_ready(int chunks) { g_cur->chunks_ready.store(chunks, std::memory_order_release); }
+
+void rw_hostpool_cancel() {
+    g_cur->cancelled.store(1, std::memory_order_release);
+    g_cur->chunks_ready.store(1 << 30, std::memory_order_release);
+}
+
+void rw_hostpool_finish() {
+    Pool *p = g_pool;
+    Slot &s = *g_cur;
+    p->drain();  // the caller works too
+    while (s.blocks_done.load(std::memory_order_acquire) != s.nblocks) cpu_relax();
+    g_cur = nullptr;
+    pthread_mutex_unlock(&g_job_mu);
+}
+
+int rw_hostpool_threads() { return pool()->T; }
+int rw_hostpool_isa() {
+    pool();
+    return g_isa;
+}

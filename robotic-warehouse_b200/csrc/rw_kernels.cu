@@ -112,6 +112,41 @@ cudaError_t rw_launch_pack_u8(const float *in, uint8_t *out, size_t n, cudaStrea
     return cudaGetLastError();
 }
 
+// Bit transport for rw_step_host: every value of a FLATTENED observation row is a 0/1 flag except the agent's own
+// coordinates (rware/warehouse.py:636-674), so the host only needs one bit per value plus one byte per coordinate to rebuild
+// the float32 rows (rw_hostpack.cpp).  bits word w, bit i <- in[32 w + i] != 0 (the bits of the "wide" positions are ignored by
+// the host); wide[row * nwide + k] <- (uint8_t)in[row * L + k].  A warp turns 1024 consecutive floats into 32 words: 32
+// coalesced 128-byte loads in flight, one ballot each, one coalesced 128-byte store.
+__global__ void rw_pack_bits_kernel(const float *__restrict__ in, uint32_t *__restrict__ bits, uint8_t *__restrict__ wide, size_t n,
+                                    int L, int nwide, size_t n_rows) {
+    const int lane = threadIdx.x & 31;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (size_t)gridDim.x * blockDim.x;
+    const size_t nwords = (n + 31) / 32;
+    for (size_t g = tid >> 5; g * 32 < nwords; g += nthreads >> 5) {
+        const size_t f0 = g * 1024;
+        uint32_t mine = 0;
+#pragma unroll 8
+        for (int j = 0; j < 32; j++) {
+            const size_t idx = f0 + (size_t)j * 32 + lane;
+            const float v = idx < n ? __ldcs(in + idx) : 0.0f;
+            const uint32_t b = __ballot_sync(0xffffffffu, v != 0.0f);
+            if (lane == j) mine = b;
+        }
+        if (g * 32 + lane < nwords) bits[g * 32 + lane] = mine;
+    }
+    const size_t nw = n_rows * (size_t)nwide;
+    for (size_t i = tid; i < nw; i += nthreads) {
+        const size_t row = i / (size_t)nwide;
+        wide[i] = (uint8_t)in[row * (size_t)L + (i - row * (size_t)nwide)];
+    }
+}
+
+cudaError_t rw_launch_pack_bits(const float *in, uint32_t *bits, uint8_t *wide, size_t n, int L, int nwide, size_t n_rows,
+                                cudaStream_t stream) {
+    rw_pack_bits_kernel<<<148 * 8, 256, 0, stream>>>(in, bits, wide, n, L, nwide, n_rows);
+    return cudaGetLastError();
+}
+
 // L2 flush for benchmarks: streams `bytes` of writes through the L2 with the SAME shared-memory carve-out as the step
 // kernel (a flush kernel with a different carve-out makes the next launch pay an SM reconfiguration).
 __global__ void rw_flush_l2_kernel(int4 *buf, size_t n16, int value) {

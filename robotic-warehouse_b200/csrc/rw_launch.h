@@ -23,9 +23,7 @@ struct RwViewSpec;
 cudaError_t rw_launch_global_image(const RwParams &p, const RwViewSpec &spec, float *out, cudaStream_t stream);
 cudaError_t rw_launch_render(const RwParams &p, uint8_t *out, int64_t env0, int64_t count, cudaStream_t stream);
 
-// packed end-to-end transport (rw_step_host): device side (rw_kernels.cu) and host side (rw_hostpack.cpp)
+// end-to-end transport (rw_step_host): device side (rw_kernels.cu); the host side is rw_hostpack.h
 cudaError_t rw_launch_pack_u8(const float *in, uint8_t *out, size_t n, cudaStream_t stream);
-void rw_hostpack_begin(const void *dst);                              // wakes the worker pool (created on first use), next to dst's NUMA node
-void rw_hostpack_widen(const uint8_t *src, float *dst, size_t n);     // dst[i] = (float)src[i], all workers + the caller
-void rw_hostpack_end();                                               // parks the pool
-int rw_hostpack_threads();
+cudaError_t rw_launch_pack_bits(const float *in, uint32_t *bits, uint8_t *wide, size_t n, int L, int nwide, size_t n_rows,
+                                cudaStream_t stream);

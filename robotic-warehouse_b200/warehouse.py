@@ -153,7 +153,7 @@ class Warehouse:
         self._obs_sensor_locations = (1 + 2 * sensor_range) ** 2
         self._obs_length = (self._obs_bits_for_self + self._obs_sensor_locations * self._obs_bits_per_agent
                             + self._obs_sensor_locations * self._obs_bits_per_shelf)
-        self.observation_space = self._make_observation_space()
+        self.observation_space = self._make_observation_space(self.observation_type)
         self.global_image = None
         self.renderer = None
         self.render_mode = render_mode
@@ -213,20 +213,32 @@ class Warehouse:
         self._cur_inactive_steps = int(st["cur_inactive"])
         self._recalc_grid()
 
-    def _make_observation_space(self):
+    def _use_slow_obs(self):
+        """rware/warehouse.py:429-503: switch the non-image observations to the nested DICT form; returns its space."""
+        self.fast_obs = False
+        return self._make_observation_space(ObservationType.DICT)
+
+    def _use_fast_obs(self):
+        """rware/warehouse.py:505-522: switch the non-image observations to the flattened vectors; returns their space."""
+        if self.fast_obs:
+            return self.observation_space
+        self.fast_obs = True
+        return self._make_observation_space(ObservationType.FLATTENED)
+
+    def _make_observation_space(self, observation_type):
         n, K = self.n_agents, 1 + 2 * self.sensor_range
         inf = float("inf")
-        if self.observation_type == ObservationType.FLATTENED:  # warehouse.py:505-522
+        if observation_type == ObservationType.FLATTENED:  # warehouse.py:505-522
             return spaces.Tuple(tuple(spaces.Box(low=-inf, high=inf, shape=(self._obs_length,), dtype=np.float32)
                                       for _ in range(n)))
-        if self.observation_type in (ObservationType.IMAGE, ObservationType.IMAGE_DICT):  # warehouse.py:352-427
+        if observation_type in (ObservationType.IMAGE, ObservationType.IMAGE_DICT):  # warehouse.py:352-427
             C = len(self.image_observation_layers)
             hi = np.ones((C, K, K), np.float32)
             for i, layer in enumerate(self.image_observation_layers):
                 if layer == ImageLayer.AGENT_DIRECTION:
                     hi[i] *= 4
             image = spaces.Box(np.zeros((C, K, K), np.float32), hi, dtype=np.float32)
-            if self.observation_type == ObservationType.IMAGE:
+            if observation_type == ObservationType.IMAGE:
                 return spaces.Tuple(tuple([image] * n))
             feats = spaces.Box(low=-inf, high=inf, shape=(6,), dtype=np.float32)
             return spaces.Tuple(tuple(spaces.Dict({"image": image, "features": feats}) for _ in range(n)))
@@ -266,9 +278,9 @@ class Warehouse:
 
     def _obs_tuple(self, obs_tensor):
         o = obs_tensor[0].cpu().numpy()
-        if self.observation_type == ObservationType.FLATTENED:
-            return tuple(o[i].copy() for i in range(self.n_agents))
-        if self.observation_type == ObservationType.DICT:
+        if not (self.image_obs or self.image_dict_obs):  # warehouse.py:722-744: `fast_obs` picks the form (598-674 / 676-720)
+            if self.fast_obs:
+                return tuple(o[i].copy() for i in range(self.n_agents))
             return tuple(self._unflatten(o[i], a) for i, a in enumerate(self.agents))
         K, C = 1 + 2 * self.sensor_range, len(self.image_observation_layers)
         for layer in self.image_observation_layers:  # layer[ag.x, ag.y] (sic, 552 / 558): numpy's IndexError, raised like there
@@ -279,7 +291,7 @@ class Warehouse:
                         axis, bad = (0, ag.x) if ag.x >= self.grid_size[0] else (1, ag.y)
                         raise IndexError(f"index {bad} is out of bounds for axis {axis} with size {self.grid_size[axis]}")
         imgs = [o[i, : C * K * K].reshape(C, K, K).copy() for i in range(self.n_agents)]
-        if self.observation_type == ObservationType.IMAGE:
+        if self.image_obs:
             return tuple(imgs)
         return tuple({"image": imgs[i], "features": o[i, C * K * K:].copy()} for i in range(self.n_agents))
 

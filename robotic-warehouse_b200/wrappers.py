@@ -34,9 +34,14 @@ class FlattenAgents(_Wrapper):
         self.action_space = spaces.Discrete(sa[0]) if (len(sa) == 1 and n == 1) else spaces.MultiDiscrete(n * sa)
         self.observation_space = spaces.Tuple(tuple(s for s in env.observation_space))
 
+    def _flat(self, obs):
+        # every agent's observation goes through its space's flatten rule first (wrappers.py:26-32, 41-46), so DICT /
+        # IMAGE / IMAGE_DICT observations become vectors too
+        return np.concatenate([spaces.flatten(s, o) for s, o in zip(self.observation_space, obs)])
+
     def reset(self, **kwargs):
         obs, info = self.env.reset(**kwargs)
-        return np.concatenate(obs), info
+        return self._flat(obs), info
 
     def step(self, action):
         try:
@@ -45,7 +50,7 @@ class FlattenAgents(_Wrapper):
         except (AttributeError, IndexError, ValueError):
             action = [action]
         obs, reward, done, truncated, info = self.env.step(action)
-        return np.concatenate(obs), np.sum(reward), done, truncated, info
+        return self._flat(obs), np.sum(reward), done, truncated, info
 
 
 class DictAgents(_Wrapper):

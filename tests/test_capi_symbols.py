@@ -100,6 +100,80 @@ def test_host_widening_from_several_threads_and_after_fork():
     assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0
 
 
+def _expand_bits_reference(rows, L, nwide, rs):
+    """Random rows of the shape the bit transport carries: `nwide` leading byte values, then 0/1 flags."""
+    import numpy as np
+    obs = rs.integers(0, 2, size=(rows, L)).astype(np.float32)
+    wide = rs.integers(0, 256, size=(rows, max(nwide, 1)), dtype=np.uint8)[:, :nwide]
+    obs[:, :nwide] = wide
+    flat = obs.reshape(-1)
+    bits = np.packbits((flat != 0).astype(np.uint8), bitorder="little")
+    bits = np.concatenate([bits, np.zeros(8, np.uint8)])  # the vector forms read whole 16-bit masks
+    return flat, bits, np.ascontiguousarray(wide)
+
+
+_EXPAND_CASES = "((1, 71, 2), (3, 15, 2), (64, 71, 2), (1000, 71, 2), (257, 183, 2), (5000, 16, 0), (4099, 45, 0), (20000, 71, 2), (70000, 8, 2))"
+
+
+def test_host_expansion_of_the_bit_transport():
+    """rw_host_expand_bits: the host half of rw_step_host's bit transport (one bit per 0/1 flag, one byte per coordinate over
+    PCIe; float32 rows rebuilt by the thread pool).  Needs no GPU: exact for ragged sizes, row lengths that straddle the
+    64-byte lines in every phase, aligned and unaligned destinations, repeated calls."""
+    import numpy as np
+    from rware_b200 import _capi
+    lib = _capi.load_library()
+    rs = np.random.default_rng(1)
+    for rows, L, nwide in eval(_EXPAND_CASES):
+        flat, bits, wide = _expand_bits_reference(rows, L, nwide, rs)
+        for shift in (0, 16, 3):  # 64-byte aligned (vector form), 64-byte aligned at another line, unaligned (scalar form)
+            raw = np.full(flat.size + 64, -1.0, np.float32)
+            base = (-raw.ctypes.data // 4) % 16  # first 64-byte aligned float
+            dst = raw[base + shift: base + shift + flat.size]
+            threads = lib.rw_host_expand_bits(bits.ctypes.data, wide.ctypes.data if nwide else None, dst.ctypes.data, rows, L, nwide)
+            assert threads >= 1
+            assert np.array_equal(dst, flat), (rows, L, nwide, shift)
+            assert np.all(raw[:base + shift] == -1.0) and np.all(raw[base + shift + flat.size:] == -1.0)
+
+
+@pytest.mark.parametrize("isa", [0, 1])
+def test_host_expansion_scalar_and_avx2_forms(isa):
+    """The same check with the instruction set capped (RWARE_B200_HOST_ISA): the forms a host without AVX-512 / AVX2 runs."""
+    import subprocess
+    import sys
+    code = f"""
+import sys, numpy as np
+sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})
+from rware_b200 import _capi
+from test_capi_symbols import _expand_bits_reference, _EXPAND_CASES
+lib = _capi.load_library()
+rs = np.random.default_rng(2)
+for rows, L, nwide in eval(_EXPAND_CASES):
+    flat, bits, wide = _expand_bits_reference(rows, L, nwide, rs)
+    raw = np.full(flat.size + 64, -1.0, np.float32)
+    base = (-raw.ctypes.data // 4) % 16
+    dst = raw[base: base + flat.size]
+    lib.rw_host_expand_bits(bits.ctypes.data, wide.ctypes.data if nwide else None, dst.ctypes.data, rows, L, nwide)
+    assert np.array_equal(dst, flat), (rows, L, nwide)
+    src = rs.integers(0, 256, size=flat.size, dtype=np.uint8)
+    lib.rw_host_widen_u8(src.ctypes.data, dst.ctypes.data, src.size)
+    assert np.array_equal(dst, src.astype(np.float32))
+print("ok")
+"""
+    env = dict(os.environ, RWARE_B200_HOST_ISA=str(isa), RWARE_B200_HOST_THREADS="3")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert res.returncode == 0 and "ok" in res.stdout, res.stdout + res.stderr
+
+
+def test_host_stream_probe_reports_a_bandwidth():
+    import numpy as np
+    from rware_b200 import _capi
+    lib = _capi.load_library()
+    buf = np.zeros(1 << 22, np.float32)
+    gbs = ctypes.c_double()
+    threads = lib.rw_host_stream_probe(buf.ctypes.data, buf.size, 2, ctypes.byref(gbs))
+    assert threads >= 1 and gbs.value > 0.05 and np.all(buf == 2.0)
+
+
 @pytest.mark.gpu
 def test_c_abi_against_the_oracle_without_python():
     """tests/ctest/gpu_quickcheck: a plain CUDA host program that links librware_b200.so and the C oracle and compares IMAGE

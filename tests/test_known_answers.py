@@ -92,18 +92,25 @@ def test_full_size_batch_properties_and_sampled_oracle_parity():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("E,packed,kw", [(1000, True, {}), (6000, True, {}), (6000, False, {}), (5000, True, {"normalised_coordinates": True}),
-                                         (4099, True, {"msg_bits": 2})],
-                         ids=["small-batch-plain-copy", "packed-transport", "plain-transport", "normalised-falls-back", "packed-ragged-msg"])
-def test_host_buffer_entry_points_match_the_device_ones(E, packed, kw):
-    """rw_reset_host / rw_step_host (pinned host buffers, the end-to-end path of bench.py) against rw_reset / rw_step, with the
-    packed transport (one byte per value over PCIe, widened on the host; batches of >= 2^20 values) and the plain float32 copy."""
+@pytest.mark.parametrize("E,mode,share,kw", [
+    (1000, 1, None, {}), (6000, 1, None, {}), (6000, 1, 0.0, {}), (6000, 1, 0.5, {}), (6000, 2, None, {}), (6000, 2, 0.3, {}),
+    (6000, 0, None, {}), (5000, 1, None, {"normalised_coordinates": True}), (4099, 1, 0.37, {"msg_bits": 2}),
+    (6007, 1, 0.2, {"observation_type": 2}), (6007, 1, 0.2, {"observation_type": 3, "image_observation_layers": (0, 1, 2, 3, 4, 5, 6)}),
+    (3001, 1, None, {"sensor_range": 2})],
+    ids=["small-batch-plain-copy", "bits-adaptive-share", "bits-all-host", "bits-half-dma", "bytes-adaptive-share", "bytes-fixed-share",
+         "plain-transport", "normalised-falls-back", "bits-ragged-msg", "image-bits", "image-direction-layer-bytes", "bits-5x5-window"])
+def test_host_buffer_entry_points_match_the_device_ones(E, mode, share, kw):
+    """rw_reset_host / rw_step_host (page-locked host buffers, the end-to-end path of bench.py) against rw_reset / rw_step, for
+    every transport: plain float32 copy, bits (one bit per flag + one byte per coordinate over PCIe, rows rebuilt by the host
+    pool), bytes (one byte per value), each with the copy engine delivering a fixed or self-adjusting share of the rows as
+    float32 at the same time.  The buffers the caller gets must be bit-identical in all of them."""
     a = rware_b200.make_vec("rware-small-4ag-v1", E, **kw)
     b = rware_b200.make_vec("rware-small-4ag-v1", E, **kw)
-    b.backend.set_host_transport(packed)
+    b.backend.set_host_transport(mode)
+    b.backend.set_host_dma_share(share)
     seeds = np.arange(E, dtype=np.uint64) + 9
     obs_d = a.reset(seed=seeds).cpu()
-    h_obs = torch.empty((E, 4, a.obs_len), dtype=torch.float32).pin_memory()
+    h_obs = b.backend.host_alloc((E, 4, a.obs_len), torch.float32)  # on the GPU's NUMA node, 64-byte aligned
     h_rew = torch.empty((E, 4), dtype=torch.float32).pin_memory()
     h_done = torch.empty((E,), dtype=torch.uint8).pin_memory()
     b.backend.reset_host(seeds, h_obs)
@@ -113,8 +120,12 @@ def test_host_buffer_entry_points_match_the_device_ones(E, packed, kw):
         acts = torch.cat([torch.randint(0, 5, (E, 4, 1), generator=g, dtype=torch.int32),
                           torch.randint(0, 2, (E, 4, a.msg_bits), generator=g, dtype=torch.int32)], dim=2).contiguous().pin_memory()
         obs_d, rew_d, done_d = a.step(acts.cuda())
+        h_obs.fill_(-7.0)
         b.backend.step_host(acts, h_obs, h_rew, h_done)
         assert torch.equal(h_obs, obs_d.cpu()) and torch.equal(h_rew, rew_d.cpu()) and torch.equal(h_done, done_d.cpu())
+    if share is None and mode and not kw.get("normalised_coordinates") and E >= 3000:
+        assert 0.0 < b.backend.host_dma_share() <= 0.9
+    b.close()
 
 
 def _full_size_cases():
