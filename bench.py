@@ -177,6 +177,149 @@ def e2e_record(world, E, n, A, L, steps, e2e_s, plain_s, d2h_ms, dma_share, comp
                                         "pcie_d2h_gbs": pcie_gbs, "frac_of_transport": d2h_ms / (plain_s / steps * 1e3)}}
 
 
+def time_rotating(step_fn, steps, warmup, dist, dev):
+    """K back-to-back calls inside one CUDA event pair after W warm-up calls; max over ranks; returns ms per call."""
+    import torch
+    for i in range(warmup):
+        step_fn(i)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step_fn(warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if dist:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def make_actions(vec, E, n, A, dev, rank, p_forward, ring=8, seed=4242):
+    import torch
+    acts = [torch.empty((E, n, A), dtype=torch.int32, device=dev) for _ in range(ring)]
+    for i, a in enumerate(acts):
+        vec.backend.random_actions(a, seed + rank, i)
+        if p_forward is not None:
+            g = torch.Generator(device=dev).manual_seed(seed + 16 * rank + i)
+            u = torch.rand((E, n), device=dev, generator=g)
+            other = torch.tensor([0, 2, 3, 4], device=dev, dtype=torch.int32)[torch.randint(0, 4, (E, n), device=dev, generator=g)]
+            a[..., 0] = torch.where(u < p_forward, torch.ones_like(other), other)
+    return acts
+
+
+def other_workloads_records(dev, rank, peak, steps, warmup):
+    """N=1 sub-records: BASELINE config 4 (medium-8ag-hard x 32 768, the dense-collision stress) under uniform actions and under
+    P(FORWARD)=0.68, and config 5's per-GPU shard, same rotate-over-world-sets protocol as the headline."""
+    import rware_b200
+    out = []
+    for name, pf in (("medium-8ag-hard", None), ("medium-8ag-hard", 0.68), ("large-16ag-r2", None)):
+        env_id, overrides, E = WORKLOADS[name]
+        nsets = 8
+        sets = [rware_b200.make_vec(env_id, E, auto_reset=True, device=dev, **overrides) for _ in range(nsets)]
+        for k, v in enumerate(sets):
+            v.reset(seed=(1000 + k) * E)
+        v0 = sets[0]
+        acts = make_actions(v0, E, v0.n_agents, 1 + v0.msg_bits, dev, rank, pf)
+        ms = time_rotating(lambda i: sets[i % nsets].step(acts[i % len(acts)]), steps, max(3, warmup), None, dev)
+        b_step = int(v0.info["algorithmic_bytes_step"])
+        out.append({"workload": f"{env_id} {overrides or ''}".strip(), "worlds": E, "actions": "uniform" if pf is None else f"P(FORWARD)={pf}",
+                    "kernel_us": ms * 1e3, "env_steps_per_s": E / (ms * 1e-3), "algorithmic_bytes_per_env_step": b_step,
+                    "roofline_frac": b_step * E / (ms * 1e-3) / 1e9 / peak, "l2": f"rotating over {nsets} world sets"})
+        for v in sets:
+            v.close()
+        del sets
+    return out
+
+
+def peer_copy_gbs(dev, local_rank, world):
+    """GB/s of a plain device-to-device copy into the next GPU of the box (the NVLink path the fused push uses); None if unavailable."""
+    import torch
+    try:
+        peer = torch.device("cuda", (local_rank + 1) % world)
+        src = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        dst = torch.empty(256 << 20, dtype=torch.uint8, device=peer)
+        best = 0.0
+        for _ in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dst.copy_(src, non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            torch.cuda.synchronize(peer)
+            best = max(best, src.numel() / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+        del src, dst
+        return best
+    except Exception:
+        return None
+
+
+def gathered_records(dist, dev, rank, local_rank, world, steps, warmup):
+    """N>1 sub-records: the ONE collective of the path on BASELINE configs 3 and 5 -- worlds sharded over
+    the ranks, obs / reward / done all-gathered every step -- as kernel + NCCL all_gather_into_tensor and as the fused push
+    (the step kernel's TMA stores write every chunk into all ranks' gathered tensors over NVLink; one 4-byte all-reduce as barrier)."""
+    import torch
+    import rware_b200
+    peer = peer_copy_gbs(dev, local_rank, world)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    out = []
+    for name, label in (("small-4ag", "BASELINE config 3"), ("large-16ag-r2", "BASELINE config 5")):
+        env_id, overrides, E = WORKLOADS[name]
+        nsets = 2
+        rec = {"config": f"{label}: {env_id} {overrides or ''}".strip() + f", {E * world} worlds over {world} GPUs, obs/reward/done all-gathered",
+               "worlds_per_gpu": E}
+        for mode in ("nccl", "fused"):
+            sets = [rware_b200.make_vec(env_id, E, auto_reset=True, device=dev, **overrides) for _ in range(nsets)]
+            for k, v in enumerate(sets):
+                v.reset(seed=((7 + k) * world + rank) * E)
+            v0 = sets[0]
+            n, L = v0.n_agents, v0.obs_len
+            acts = make_actions(v0, E, n, 1 + v0.msg_bits, dev, rank, None)
+            if mode == "nccl":
+                g = (torch.empty((world * E, n, L), dtype=torch.float32, device=dev),
+                     torch.empty((world * E, n), dtype=torch.float32, device=dev),
+                     torch.empty((world * E,), dtype=torch.uint8, device=dev))
+
+                def step_fn(i):
+                    obs, rew, done = sets[i % nsets].step(acts[i % len(acts)])
+                    dist.all_gather_into_tensor(g[0], obs)
+                    dist.all_gather_into_tensor(g[1], rew)
+                    dist.all_gather_into_tensor(g[2], done)
+            else:
+                for v in sets:
+                    _, handle = v.backend.gather_create(world, rank)
+                    handles = [None] * world
+                    dist.all_gather_object(handles, handle)
+                    v.backend.gather_open(b"".join(handles))
+                dist.barrier()
+
+                def step_fn(i):
+                    sets[i % nsets].backend.step_gather(acts[i % len(acts)])
+                    dist.all_reduce(flag)
+            ms = time_rotating(step_fn, steps, max(3, warmup), dist, dev)
+            rec[f"{mode}_ms"] = ms
+            torch.cuda.synchronize()
+            dist.barrier()
+            for v in sets:
+                v.close()
+            del sets
+            if mode == "nccl":
+                del g
+            torch.cuda.empty_cache()
+        shard = E * (n * L * 4 + n * 4 + 1)
+        rec.update({"env_steps_per_s": world * E / (rec["fused_ms"] * 1e-3), "env_steps_per_s_nccl": world * E / (rec["nccl_ms"] * 1e-3),
+                    "gathered_bytes_per_rank": world * shard, "nvlink_egress_bytes_per_gpu": (world - 1) * shard,
+                    "nvlink_gbs": (world - 1) * shard / (rec["fused_ms"] * 1e-3) / 1e9,
+                    "peer_copy_peak_gbs": peer, "peer_copy_peak_source": "measured: 256 MiB torch copy into the next GPU" if peer else None,
+                    "frac_of_peer_copy_peak": ((world - 1) * shard / (rec["fused_ms"] * 1e-3) / 1e9 / peer) if peer else None})
+        out.append(rec)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -192,6 +335,8 @@ def main():
     ap.add_argument("--e2e-warmup", type=int, default=8)
     ap.add_argument("--ref-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the sub-records (other_workloads at N=1, gathered configs 3 and 5 at N>1)")
     ap.add_argument("--gather", nargs="?", const="nccl", default=None, choices=["nccl", "fused"],
                     help="all-gather obs/reward/done across ranks every step: NCCL all_gather_into_tensor, or the fused "
                          "push (the step kernel's TMA stores write into every rank's gathered tensor over NVLink)")
@@ -267,7 +412,7 @@ def main():
 
     def one_step(i):
         if fused is not None:
-            sets[i % NSETS].backend.step_gather(actions[i % RING])
+            sets[i % NSETS].backend.step_gather(actions[i % RING])  # lands in slot (call count & 1) of every rank's tensors
             dist.all_reduce(flag)  # the barrier: all ranks' pushes have landed
             return
         obs, rew, done = sets[i % NSETS].step(actions[i % RING])
@@ -425,6 +570,20 @@ def main():
     host_stream_gbs, host_threads = be.host_stream_probe(h_obs, repeats=3)  # every rank at once, like the e2e loop
     numa = {"gpu_node": be.gpu_numa_node(), "obs_buffer_node": be.host_numa_node(h_obs)}
 
+    # sub-records: free the headline's world sets first
+    extras = {}
+    if not args.no_extras and args.workload == "tiny-4ag" and args.gather is None:
+        be.close()
+        for v in sets[1:]:
+            v.close()
+        del actions, flush
+        torch.cuda.empty_cache()
+        peak_gbs, _ = load_peaks()
+        if world == 1:
+            extras["other_workloads"] = other_workloads_records(dev, rank, peak_gbs, min(args.steps, 100), args.warmup)
+        else:
+            extras["gathered"] = gathered_records(dist, dev, rank, local_rank, world, min(args.steps, 40), args.warmup)
+
     tot = torch.tensor([total_ms, warm_ms, e2e_s, obs_kernel_ms, e2e_plain_s], dtype=torch.float64, device=dev)
     if dist:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
@@ -486,6 +645,7 @@ def main():
         out["cpu_baseline"] = cb
     if multi:
         out["concurrent_streams"] = multi
+    out.update(extras)
     print(json.dumps(out))
     if dist:
         dist.destroy_process_group()

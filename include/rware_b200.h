@@ -203,16 +203,25 @@ int rw_gpu_numa_node(const rw_handle *h);
 /* ---- Fused push all-gather (one process per GPU, NVLink / NVSwitch peers).  SURVEY.md section 8(e): the single optional
  * exchange of the path is an all-gather of obs / reward / done.  Instead of a separate collective, the step kernel's TMA
  * bulk stores write every observation chunk straight into this rank's slot of EVERY rank's gathered tensor.
- *   rw_gather_create    allocates this rank's gathered buffers (one cudaMalloc: obs [W*E][n][L] f32, reward [W*E][n] f32,
- *                       done [W*E] u8 for W = world_size ranks of E worlds each) and returns their device pointers plus
- *                       a 64-byte CUDA IPC handle to hand to the other ranks (any transport: torch.distributed, MPI...)
+ *   rw_gather_create    allocates this rank's gathered buffers (one cudaMalloc holding TWO slots of: obs [W*E][n][L] f32,
+ *                       reward [W*E][n] f32, done [W*E] u8 for W = world_size ranks of E worlds each), returns the device
+ *                       pointers of slot 0 plus a 64-byte CUDA IPC handle to hand to the other ranks (any transport:
+ *                       torch.distributed, MPI...)
  *   rw_gather_open      maps the peers' buffers from their IPC handles ([W][64] bytes, own slot ignored)
- *   rw_step_gather      rw_step whose outputs land in all gathered tensors; the caller then runs ONE barrier-like
- *                       collective on the same stream (e.g. a 4-byte all-reduce) before reading its gathered tensors */
+ *   rw_step_gather      rw_step whose outputs land in slot (k & 1) of all ranks' gathered tensors, k = number of earlier
+ *                       rw_step_gather calls on this handle (all ranks must call it the same number of times).  Returns the
+ *                       slot index (0 / 1) on success, a negative RW_E* code on failure.  The caller then runs ONE
+ *                       barrier-like collective on the same stream (e.g. a 4-byte all-reduce) and reads slot (k & 1).
+ *   rw_gather_slot      device pointers of a slot of this rank's gathered tensors
+ * Ordering contract (why two slots suffice): a rank that is ahead can at most be pushing step k+1 while this rank still reads
+ * step k -- its step k+2 has to pass barrier k+1 first, which this rank only joins after its own rw_step_gather k+1, which is
+ * stream-ordered after everything this rank enqueued on that stream to consume step k.  So: consume step k on the stream that is
+ * passed to rw_step_gather (or make that stream wait for the consumer) before calling rw_step_gather k+1. */
 int rw_gather_create(rw_handle *h, int world_size, int rank, float **obs_all, float **reward_all, uint8_t **done_all,
                      void *ipc_handle_out /* 64 bytes */);
 int rw_gather_open(rw_handle *h, const void *ipc_handles /* [world_size][64] */);
 int rw_step_gather(rw_handle *h, const int32_t *actions_dev, void *stream);
+int rw_gather_slot(const rw_handle *h, int slot, float **obs_all, float **reward_all, uint8_t **done_all);
 
 /* Diagnostics: when dev_ptr != NULL every warp of every CTA writes phase timestamps (globaltimer, ns) to
  * dev_ptr[(cta*32 + warp)*8 + k] (uint64).  NULL switches it off (default). */

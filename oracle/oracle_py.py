@@ -63,6 +63,11 @@ def lib():
         L.orc_rollout_random.restype = ctypes.c_int64
         L.orc_rollout_random.argtypes = [ctypes.POINTER(_Config), ctypes.c_int, ctypes.c_int, ctypes.c_uint64,
                                          ctypes.c_int, ctypes.c_void_p]
+        L.orc_batch_create.restype = ctypes.c_void_p
+        L.orc_batch_create.argtypes = [ctypes.POINTER(_Config), ctypes.c_int64, ctypes.c_int]
+        L.orc_batch_destroy.argtypes = [ctypes.c_void_p]
+        L.orc_batch_reset.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_batch_step.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         _lib = L
     return _lib
 
@@ -207,3 +212,39 @@ def rollout_random(env: OracleEnv, n_envs, n_steps, seed=0, n_threads=1):
     rs = ctypes.c_double()
     total = lib().orc_rollout_random(ctypes.byref(env.config_struct), n_envs, n_steps, seed, n_threads, ctypes.byref(rs))
     return int(total), rs.value
+
+
+class OracleBatch:
+    """E independent oracle worlds stepped in lock step on `n_threads` host threads (orc_batch_*): the checker of the
+    full-size parity tests, where every world of a BASELINE-sized batch is compared, not a sample."""
+
+    def __init__(self, env: OracleEnv, n_envs, n_threads=None, auto_reset=True):
+        self.proto = env  # keeps the config struct (and the arrays it points to) alive
+        self.E, self.n, self.L = int(n_envs), env.n, env.L
+        self.A = 1 + env.msg_bits
+        self.auto_reset = bool(auto_reset)
+        self._h = lib().orc_batch_create(ctypes.byref(env.config_struct), self.E, int(n_threads or os.cpu_count() or 1))
+        self.obs = np.zeros((self.E, self.n, self.L), np.float32)
+        self.reward = np.zeros((self.E, self.n), np.float32)
+        self.done = np.zeros((self.E,), np.uint8)
+
+    def reset(self, seeds=None):
+        s = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint64)
+        lib().orc_batch_reset(self._h, None if s is None else _p(s), _p(self.obs))
+        return self.obs
+
+    def step(self, actions):
+        a = np.ascontiguousarray(actions, dtype=np.int32).reshape(self.E, self.n, self.A)
+        lib().orc_batch_step(self._h, _p(a), int(self.auto_reset), _p(self.obs), _p(self.reward), _p(self.done))
+        return self.obs, self.reward, self.done
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().orc_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -796,3 +796,96 @@ int64_t orc_rollout_random(const orc_config *cfg, int n_envs, int n_steps, uint6
     free(jobs);
     return total;
 }
+
+/* ---------------------------------------------------------------- batched oracle (test infrastructure)
+ * E independent oracle worlds advanced in lock step with the product's batched step, so that the full-size parity tests can
+ * compare EVERY world of a BASELINE-sized batch (65 536 worlds) instead of a sample.  Same per-world functions as above; the
+ * worlds are split over `n_threads` pthreads per call. */
+struct orc_batch {
+    orc_config cfg;
+    int64_t E;
+    int n_threads;
+    orc_env **env;
+};
+
+typedef struct {
+    orc_batch *b;
+    int64_t lo, hi;
+    int mode;           /* 0 reset, 1 step */
+    const uint64_t *seeds;
+    const int32_t *actions;
+    int auto_reset;
+    float *obs, *reward;
+    uint8_t *done;
+} batch_job;
+
+static void *batch_worker(void *arg) {
+    batch_job *j = (batch_job *)arg;
+    orc_batch *b = j->b;
+    const int n = b->cfg.n_agents, A = 1 + b->cfg.msg_bits;
+    double rew[MAX_AGENTS];
+    for (int64_t e = j->lo; e < j->hi; e++) {
+        orc_env *w = b->env[e];
+        float *obs = j->obs ? j->obs + (size_t)e * n * w->L : NULL;
+        float *scratch = NULL;
+        if (!obs) obs = scratch = (float *)malloc(sizeof(float) * (size_t)n * (size_t)w->L);
+        if (j->mode == 0) {
+            orc_reset(w, j->seeds ? (int64_t)j->seeds[e] : -1, obs);
+        } else {
+            uint8_t d = 0;
+            orc_step(w, j->actions + (size_t)e * n * A, obs, rew, &d);
+            if (j->reward) for (int a = 0; a < n; a++) j->reward[(size_t)e * n + a] = (float)rew[a];
+            if (j->done) j->done[e] = d;
+            if (d && j->auto_reset) orc_reset(w, -1, obs); /* continues the world's generator, as the kernel's auto-reset */
+        }
+        free(scratch);
+    }
+    return NULL;
+}
+
+static void batch_run(orc_batch *b, batch_job proto) {
+    int T = b->n_threads < 1 ? 1 : b->n_threads;
+    if (T > b->E) T = (int)b->E;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)T);
+    batch_job *jobs = (batch_job *)malloc(sizeof(batch_job) * (size_t)T);
+    for (int t = 0; t < T; t++) {
+        jobs[t] = proto;
+        jobs[t].lo = b->E * t / T;
+        jobs[t].hi = b->E * (t + 1) / T;
+        pthread_create(&th[t], NULL, batch_worker, &jobs[t]);
+    }
+    for (int t = 0; t < T; t++) pthread_join(th[t], NULL);
+    free(th);
+    free(jobs);
+}
+
+orc_batch *orc_batch_create(const orc_config *cfg, int64_t n_envs, int n_threads) {
+    orc_batch *b = (orc_batch *)calloc(1, sizeof(orc_batch));
+    b->cfg = *cfg;
+    b->E = n_envs;
+    b->n_threads = n_threads;
+    b->env = (orc_env **)calloc((size_t)n_envs, sizeof(orc_env *));
+    for (int64_t e = 0; e < n_envs; e++) b->env[e] = orc_create(cfg);
+    return b;
+}
+
+void orc_batch_destroy(orc_batch *b) {
+    if (!b) return;
+    for (int64_t e = 0; e < b->E; e++) orc_destroy(b->env[e]);
+    free(b->env);
+    free(b);
+}
+
+void orc_batch_reset(orc_batch *b, const uint64_t *seeds, float *obs) {
+    batch_job j;
+    memset(&j, 0, sizeof(j));
+    j.b = b; j.mode = 0; j.seeds = seeds; j.obs = obs;
+    batch_run(b, j);
+}
+
+void orc_batch_step(orc_batch *b, const int32_t *actions, int auto_reset, float *obs, float *reward, uint8_t *done) {
+    batch_job j;
+    memset(&j, 0, sizeof(j));
+    j.b = b; j.mode = 1; j.actions = actions; j.auto_reset = auto_reset; j.obs = obs; j.reward = reward; j.done = done;
+    batch_run(b, j);
+}

@@ -98,6 +98,16 @@ void orc_py_set_order(const int32_t *xy, int n, int32_t *out_index_order);
 int64_t orc_rollout_random(const orc_config *cfg, int n_envs, int n_steps, uint64_t seed, int n_threads,
                            double *reward_sum);
 
+/* Batched form (test infrastructure): E independent worlds stepped in lock step on n_threads pthreads, so that full-size parity
+ * tests can compare every world of a batch.  seeds [E] or NULL (continue the generators); obs [E][n][L] float32 or NULL;
+ * reward [E][n] float32; done [E].  With auto_reset a world that is done is reset (continuing its generator) and obs holds the
+ * first observation of the new episode, as the product's in-kernel auto-reset does. */
+typedef struct orc_batch orc_batch;
+orc_batch *orc_batch_create(const orc_config *cfg, int64_t n_envs, int n_threads);
+void orc_batch_destroy(orc_batch *b);
+void orc_batch_reset(orc_batch *b, const uint64_t *seeds, float *obs);
+void orc_batch_step(orc_batch *b, const int32_t *actions, int auto_reset, float *obs, float *reward, uint8_t *done);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,6 +92,7 @@ def load_library():
     L.rw_gather_create.argtypes = [vp, ci, ci, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp), vp]
     L.rw_gather_open.argtypes = [vp, vp]
     L.rw_step_gather.argtypes = [vp, vp, vp]
+    L.rw_gather_slot.argtypes = [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)]
     L.rw_global_image_shape.argtypes = [vp, ctypes.c_int32, vp, vp]
     L.rw_global_image.argtypes = [vp, vp, ctypes.c_int32, vp, vp, vp]
     L.rw_render_shape.argtypes = [vp, vp, vp]
@@ -108,7 +109,7 @@ def load_library():
     L.rw_gpu_numa_node.argtypes = [vp]
     for name in ("rw_create", "rw_destroy", "rw_get_info", "rw_seed", "rw_reset", "rw_step", "rw_obs", "rw_set_auto_reset",
                  "rw_get_state", "rw_set_state", "rw_error_count", "rw_step_host", "rw_reset_host", "rw_host_alloc",
-                 "rw_host_free", "rw_random_actions", "rw_debug_set_clock_buffer", "rw_flush_l2", "rw_gather_create", "rw_gather_open", "rw_step_gather",
+                 "rw_host_free", "rw_random_actions", "rw_debug_set_clock_buffer", "rw_flush_l2", "rw_gather_create", "rw_gather_open", "rw_step_gather", "rw_gather_slot",
                  "rw_global_image_shape", "rw_global_image", "rw_render_shape", "rw_render_rgb", "rw_set_host_transport",
                  "rw_host_widen_u8", "rw_obs_bytes", "rw_host_expand_bits", "rw_host_stream_probe", "rw_set_host_dma_share",
                  "rw_get_host_dma_share", "rw_host_alloc_near", "rw_host_numa_node", "rw_gpu_numa_node"):
@@ -263,7 +264,8 @@ class CudaBackend:
 
     # ---- fused push all-gather (multi-GPU)
     def gather_create(self, world_size, rank):
-        """Allocates this rank's gathered obs/reward/done buffers; returns (tensors, 64-byte IPC handle)."""
+        """Allocates this rank's gathered obs/reward/done buffers (two slots, written alternately); returns
+        ([slot 0 tensors, slot 1 tensors], 64-byte IPC handle)."""
         po, pr, pd = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
         handle = ctypes.create_string_buffer(64)
         self._check(self.lib.rw_gather_create(self._h, world_size, rank, ctypes.byref(po), ctypes.byref(pr),
@@ -274,16 +276,24 @@ class CudaBackend:
             class _Raw:  # __cuda_array_interface__ view of library-owned memory
                 __cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
             return torch.as_tensor(_Raw(), device=self.device).view(dtype).view(shape)
-        tensors = (wrap(po.value, (E, n, L), "<f4", torch.float32), wrap(pr.value, (E, n), "<f4", torch.float32),
-                   wrap(pd.value, (E,), "|u1", torch.uint8))
-        return tensors, handle.raw
+        slots = []
+        for slot in range(2):
+            self._check(self.lib.rw_gather_slot(self._h, slot, ctypes.byref(po), ctypes.byref(pr), ctypes.byref(pd)))
+            slots.append((wrap(po.value, (E, n, L), "<f4", torch.float32), wrap(pr.value, (E, n), "<f4", torch.float32),
+                          wrap(pd.value, (E,), "|u1", torch.uint8)))
+        self._gather_slots = slots
+        return slots, handle.raw
 
     def gather_open(self, handles: bytes):
         buf = ctypes.create_string_buffer(handles, len(handles))
         self._check(self.lib.rw_gather_open(self._h, buf))
 
     def step_gather(self, actions):
-        self._check(self.lib.rw_step_gather(self._h, _ptr(actions), self._stream()))
+        """Returns the slot (0 / 1) of the gathered tensors this step is being pushed into."""
+        slot = self.lib.rw_step_gather(self._h, _ptr(actions), self._stream())
+        if slot < 0:
+            self._check(slot)
+        return slot
 
     def flush_l2(self, buf, value=0):
         self._check(self.lib.rw_flush_l2(self._h, _ptr(buf), buf.numel() * buf.element_size(), int(value), self._stream()))

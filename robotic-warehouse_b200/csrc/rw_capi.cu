@@ -25,7 +25,8 @@
 #include "rw_hostpack.h"
 #include "rw_views.cuh"
 
-#define RW_DMA_FRAC0 0.25
+#define RW_DMA_FRAC0 0.15
+#define RW_HOST_LOCAL_TAIL 0.25  // share of a buffer from rw_host_alloc_near that stays on the GPU's NUMA node (the copy engine's rows)
 
 struct rw_handle {
     RwParams p;
@@ -44,7 +45,8 @@ struct rw_handle {
     uint8_t *d_pack = nullptr, *h_pack = nullptr;
     size_t pack_bytes = 0;
     cudaEvent_t pack_ev[8] = {};
-    cudaEvent_t dma_ev[2] = {};
+    cudaEvent_t dma_ev[2] = {}, kernel_ev = nullptr;
+    cudaStream_t dma_stream = nullptr;
     int host_pack = 1;  // 0 plain float32 copy, 1 compressed (bits where the rows allow it, else bytes), 2 compressed, bytes only
     // share of the observation rows that the copy engine delivers as plain float32 while the host pool expands the rest;
     // follows the measured rates of the two unless fixed (rw_set_host_dma_share / RWARE_B200_HOST_DMA_SHARE)
@@ -55,7 +57,8 @@ struct rw_handle {
     void *peer_base[RW_MAX_PEERS] = {};
     int gather_world = 0, gather_rank = 0;
     bool gather_open = false;
-    size_t gather_off_rew = 0, gather_off_done = 0;
+    size_t gather_off_rew = 0, gather_off_done = 0, gather_slot_bytes = 0;
+    int64_t gather_steps = 0;  // rw_step_gather calls so far: call k writes slot k & 1
     rw_info info;
 };
 
@@ -236,6 +239,8 @@ int rw_destroy(rw_handle *h) {
         free_pinned(h->h_pack);
         for (auto &e : h->pack_ev) if (e) cudaEventDestroy(e);
         for (auto &e : h->dma_ev) if (e) cudaEventDestroy(e);
+        if (h->kernel_ev) cudaEventDestroy(h->kernel_ev);
+        if (h->dma_stream) cudaStreamDestroy(h->dma_stream);
     }
     cudaFree(h->d_highway); cudaFree(h->d_home); cudaFree(h->d_home_id); cudaFree(h->d_cta_tables); cudaFree(h->d_normx); cudaFree(h->d_normy);
     cudaFree(h->d_state); cudaFree(h->d_rng); cudaFree(h->d_err);
@@ -354,11 +359,14 @@ int rw_flush_l2(rw_handle *h, void *buf_dev, int64_t bytes, int value, void *str
     return RW_OK;
 }
 
-static void gather_set_peer(rw_handle *h, int r, void *base) {
-    h->peer_base[r] = base;
-    h->p.peer_obs[r] = (float *)base;
-    h->p.peer_rew[r] = (float *)((char *)base + h->gather_off_rew);
-    h->p.peer_done[r] = (uint8_t *)((char *)base + h->gather_off_done);
+static void gather_set_peer(rw_handle *h, int r, void *base) { h->peer_base[r] = base; }
+
+// pointers of slot `slot` of rank r's gathered tensors
+static void gather_slot_ptrs(const rw_handle *h, int r, int slot, float **obs, float **rew, uint8_t **done) {
+    char *base = (char *)h->peer_base[r] + (size_t)slot * h->gather_slot_bytes;
+    *obs = (float *)base;
+    *rew = (float *)(base + h->gather_off_rew);
+    *done = (uint8_t *)(base + h->gather_off_done);
 }
 
 int rw_gather_create(rw_handle *h, int world_size, int rank, float **obs_all, float **reward_all, uint8_t **done_all,
@@ -372,19 +380,24 @@ int rw_gather_create(rw_handle *h, int world_size, int rank, float **obs_all, fl
     auto up = [](size_t x) { return (x + 255) / 256 * 256; };
     h->gather_off_rew = up(W * E * p.n * p.L * 4);
     h->gather_off_done = h->gather_off_rew + up(W * E * p.n * 4);
-    const size_t total = h->gather_off_done + up(W * E);
-    CK(cudaMalloc(&h->d_gather, total));
-    CK(cudaMemset(h->d_gather, 0, total));
+    h->gather_slot_bytes = h->gather_off_done + up(W * E);
+    // TWO slots in one allocation (one IPC handle): step k lands in slot k & 1, so a peer that is already pushing step k+1
+    // cannot touch the tensors this rank's consumer is still reading for step k (see rw_step_gather)
+    CK(cudaMalloc(&h->d_gather, 2 * h->gather_slot_bytes));
+    CK(cudaMemset(h->d_gather, 0, 2 * h->gather_slot_bytes));
     h->gather_world = world_size;
     h->gather_rank = rank;
+    h->gather_steps = 0;
     gather_set_peer(h, rank, h->d_gather);
     cudaIpcMemHandle_t ipc;
     CK(cudaIpcGetMemHandle(&ipc, h->d_gather));
     static_assert(sizeof(ipc) == 64, "cudaIpcMemHandle_t is 64 bytes");
     memcpy(ipc_handle_out, &ipc, 64);
-    if (obs_all) *obs_all = h->p.peer_obs[rank];
-    if (reward_all) *reward_all = h->p.peer_rew[rank];
-    if (done_all) *done_all = h->p.peer_done[rank];
+    float *o; float *r; uint8_t *d;
+    gather_slot_ptrs(h, rank, 0, &o, &r, &d);
+    if (obs_all) *obs_all = o;
+    if (reward_all) *reward_all = r;
+    if (done_all) *done_all = d;
     return RW_OK;
 }
 
@@ -403,6 +416,16 @@ int rw_gather_open(rw_handle *h, const void *ipc_handles) {
     return RW_OK;
 }
 
+int rw_gather_slot(const rw_handle *h, int slot, float **obs_all, float **reward_all, uint8_t **done_all) {
+    if (!h || !h->d_gather || slot < 0 || slot > 1) return RW_EINVAL;
+    float *o; float *r; uint8_t *d;
+    gather_slot_ptrs(h, h->gather_rank, slot, &o, &r, &d);
+    if (obs_all) *obs_all = o;
+    if (reward_all) *reward_all = r;
+    if (done_all) *done_all = d;
+    return RW_OK;
+}
+
 int rw_step_gather(rw_handle *h, const int32_t *actions_dev, void *stream) {
     if (!h || !actions_dev) return RW_EINVAL;
     if (!h->ready) return fail(h, RW_ESTATE, "rw_step_gather before rw_reset / rw_set_state");
@@ -410,14 +433,17 @@ int rw_step_gather(rw_handle *h, const int32_t *actions_dev, void *stream) {
         return fail(h, RW_ESTATE, "rw_step_gather before rw_gather_create / rw_gather_open");
     CK(cudaSetDevice(h->device));
     RwParams p = h->p;  // the plain entry points keep n_peers == 0
+    const int slot = (int)(h->gather_steps & 1);
     p.n_peers = h->gather_world;
     p.my_rank = h->gather_rank;
     p.gather_env0 = (int64_t)h->gather_rank * p.E;
+    for (int r = 0; r < h->gather_world; r++) gather_slot_ptrs(h, r, slot, &p.peer_obs[r], &p.peer_rew[r], &p.peer_done[r]);
     float *obs = p.peer_obs[p.my_rank] + (size_t)p.gather_env0 * p.n * p.L;
     float *rew = p.peer_rew[p.my_rank] + (size_t)p.gather_env0 * p.n;
     uint8_t *done = p.peer_done[p.my_rank] + (size_t)p.gather_env0;
     CK(rw_launch_main(RW_MODE_STEP, p, actions_dev, obs, rew, done, nullptr, (cudaStream_t)stream));
-    return RW_OK;
+    h->gather_steps++;
+    return slot;
 }
 
 int rw_random_actions(rw_handle *h, int32_t *actions_dev, uint64_t seed, uint64_t step, void *stream) {
@@ -491,47 +517,63 @@ static int gpu_numa_node(int device) {
     return node;
 }
 
-// Page-locked host memory whose pages sit on NUMA node `node` (next to the GPU's PCIe root and to the pool's workers): the
-// pages are first touched by this thread while it is confined to that node's CPUs, then registered with CUDA.  Best effort:
-// without NUMA information this is a plain cudaHostAlloc.
+// Page-locked host memory placed for the transport of rw_step_host.  The expansion of the observation rows is bound by the
+// DRAM write bandwidth of the socket(s) holding the pages, so a large buffer is STRIPED over the NUMA nodes (2 MB stripes, the
+// first one on the GPU's node) and the host pool expands every stripe with threads of its own socket; the last `local_tail`
+// of the buffer -- the rows the copy engine delivers -- stays on the node the GPU is attached to, so that the DMA writes do
+// not cross the socket interconnect.  Pages are placed by first touch from this thread while it is confined to the node's
+// CPUs, then registered with CUDA.  Best effort: without NUMA information this is a plain cudaHostAlloc.
 static std::mutex g_reg_mu;
-static std::map<void *, size_t> g_registered;  // mmap'ed + cudaHostRegister'ed blocks handed out by alloc_pinned_on_node
+struct RegBlock { void *base; size_t maplen, reglen; };
+static std::map<void *, RegBlock> g_registered;  // mmap'ed + cudaHostRegister'ed blocks handed out by alloc_pinned_placed
 
-static cudaError_t alloc_pinned_on_node(void **out, size_t bytes, int node) {
-    cpu_set_t want, old;
-    static const bool numa = !(getenv("RWARE_B200_HOST_NUMA") && atoi(getenv("RWARE_B200_HOST_NUMA")) == 0);
-    if (!numa || node < 0 || !rw_host_cpus_of_node(node, &want) || sched_getaffinity(0, sizeof(old), &old) != 0)
+static cudaError_t alloc_pinned_placed(void **out, size_t bytes, int gpu_node, double local_tail) {
+    const int nodes = rw_host_numa_nodes();
+    cpu_set_t old;
+    if (nodes < 2 || gpu_node < 0 || gpu_node >= nodes || sched_getaffinity(0, sizeof(old), &old) != 0)
         return cudaHostAlloc(out, bytes, cudaHostAllocPortable);
-    const size_t len = (bytes + 4095) & ~(size_t)4095;
-    void *p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
-    if (p == MAP_FAILED) return cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    static const size_t stripe = (size_t)(getenv("RWARE_B200_HOST_STRIPE_MB") ? atoi(getenv("RWARE_B200_HOST_STRIPE_MB")) : 2) << 20;
+    if (getenv("RWARE_B200_HOST_LOCAL_TAIL")) local_tail = atof(getenv("RWARE_B200_HOST_LOCAL_TAIL"));
+    const size_t huge = (size_t)2 << 20;
+    const size_t len = (bytes + 4095) & ~(size_t)4095, maplen = len + huge;
+    void *base = mmap(nullptr, maplen, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (base == MAP_FAILED) return cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    char *p = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(base) + huge - 1) & ~(uintptr_t)(huge - 1));
     madvise(p, len, MADV_HUGEPAGE);
-    const bool moved = sched_setaffinity(0, sizeof(want), &want) == 0;
-    memset(p, 0, len);  // first touch: the default policy places the pages on the node this thread runs on
-    if (moved) sched_setaffinity(0, sizeof(old), &old);
+    size_t striped = 0;
+    if (stripe && len >= ((size_t)8 << 20) && local_tail < 1.0) striped = (size_t)((1.0 - local_tail) * (double)len) / stripe * stripe;
+    for (int k = 0; k < nodes; k++) {  // first touch: the default policy places a page on the node of the thread that touches it
+        const int node = (gpu_node + k) % nodes;
+        cpu_set_t want;
+        const bool moved = rw_host_cpus_of_node(node, &want) && sched_setaffinity(0, sizeof(want), &want) == 0;
+        for (size_t off = (size_t)k * stripe; stripe && off < striped; off += (size_t)nodes * stripe) memset(p + off, 0, stripe);
+        if (k == 0) memset(p + striped, 0, len - striped);
+        (void)moved;
+    }
+    sched_setaffinity(0, sizeof(old), &old);
     cudaError_t e = cudaHostRegister(p, len, cudaHostRegisterPortable);
     if (e != cudaSuccess) {
-        munmap(p, len);
+        munmap(base, maplen);
         (void)cudaGetLastError();
         return cudaHostAlloc(out, bytes, cudaHostAllocPortable);
     }
     std::lock_guard<std::mutex> g(g_reg_mu);
-    g_registered[p] = len;
+    g_registered[p] = RegBlock{base, maplen, len};
     *out = p;
     return cudaSuccess;
 }
 
 static cudaError_t free_pinned(void *p) {
     if (!p) return cudaSuccess;
-    size_t len = 0;
+    RegBlock blk{nullptr, 0, 0};
     {
         std::lock_guard<std::mutex> g(g_reg_mu);
         auto it = g_registered.find(p);
-        if (it != g_registered.end()) { len = it->second; g_registered.erase(it); }
+        if (it != g_registered.end()) { blk = it->second; g_registered.erase(it); }
     }
-    if (!len) return cudaFreeHost(p);
+    if (!blk.base) return cudaFreeHost(p);
     cudaError_t e = cudaHostUnregister(p);
-    munmap(p, len);
+    munmap(blk.base, blk.maplen);
     return e;
 }
 
@@ -579,42 +621,53 @@ int rw_step_host(rw_handle *h, const int32_t *actions_host, float *obs_host, flo
     static const bool trace = getenv("RWARE_B200_HOST_TRACE") != nullptr;  // diagnostics: where the call spends its time
     auto now_us = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
     const double t_call = now_us();
-    if (n_cpu) rw_hostpool_prewake(obs_host);  // parked workers wake up while the copies and the kernel are in flight
+    if (n_cpu) rw_hostpool_prewake();  // parked workers wake up while the copies and the kernel are in flight
     CK(cudaMemcpyAsync(h->d_actions, actions_host, (size_t)p.E * p.n * p.A * 4, cudaMemcpyHostToDevice, st));
     rc = rw_step(h, h->d_actions, obs_host ? h->d_obs : nullptr, h->d_reward, h->d_done, st);
     if (rc) return rc;
     int nch = 0;
-    size_t bpc = 0;
+    size_t chunk_end[8] = {0};
     const size_t bits_bytes = ((n_obs + 31) / 32) * 4, off_wide = (bits_bytes + 255) & ~(size_t)255;
+    const bool timed_dma = n_cpu && n_cpu < n_obs;
     if (n_cpu) {
         if (!h->d_pack) {
             h->pack_bytes = n_obs + 256;  // the byte transport needs n_obs, the bit transport n_obs / 8 + 2 bytes per row
             if (h->pack_bytes < off_wide + n_rows * 2 + 256) h->pack_bytes = off_wide + n_rows * 2 + 256;
             CK(cudaMalloc(&h->d_pack, h->pack_bytes));
-            CK(alloc_pinned_on_node((void **)&h->h_pack, h->pack_bytes, gpu_numa_node(h->device)));
-            for (auto &e : h->pack_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            CK(alloc_pinned_placed((void **)&h->h_pack, h->pack_bytes, gpu_numa_node(h->device), 1.0));
+            for (auto &e : h->pack_ev) CK(cudaEventCreate(&e));
             CK(cudaEventCreate(&h->dma_ev[0]));
             CK(cudaEventCreate(&h->dma_ev[1]));
         }
+        // The compressed rows reach the host in a few pieces of growing size (each packed by its own small launch, so the
+        // first copy starts as early as possible); the pool starts expanding when the first piece has landed.
         static const int want_chunks = getenv("RWARE_B200_HOST_CHUNKS") ? atoi(getenv("RWARE_B200_HOST_CHUNKS")) : 4;
         const size_t nblocks = (n_cpu + RW_HOST_BLOCK - 1) / RW_HOST_BLOCK;
         nch = want_chunks < 1 ? 1 : (want_chunks > 8 ? 8 : want_chunks);
         if ((size_t)nch > nblocks) nch = (int)nblocks;
-        bpc = (nblocks + nch - 1) / nch;
-        nch = (int)((nblocks + bpc - 1) / bpc);
-        if (bits) CK(rw_launch_pack_bits(h->d_obs, (uint32_t *)h->d_pack, h->d_pack + off_wide, n_cpu, (int)L, nwide, rows_cpu, st));
-        else CK(rw_launch_pack_u8(h->d_obs, h->d_pack, n_cpu, st));
+        {   // piece c ends at block nblocks * (c + 1) * (c + 2) / (nch * (nch + 1)): sizes 1 : 2 : 3 : ...
+            size_t prev = 0;
+            int k = 0;
+            for (int c = 0; c < nch; c++) {
+                size_t end = c + 1 == nch ? nblocks : nblocks * (size_t)(c + 1) * (c + 2) / ((size_t)nch * (nch + 1));
+                if (end <= prev) continue;
+                chunk_end[k++] = end;
+                prev = end;
+            }
+            nch = k;
+        }
         for (int c = 0; c < nch; c++) {
-            const size_t a = (size_t)c * bpc * RW_HOST_BLOCK, b = a + bpc * RW_HOST_BLOCK > n_cpu ? n_cpu : a + bpc * RW_HOST_BLOCK;
+            const size_t a = (c ? chunk_end[c - 1] : 0) * RW_HOST_BLOCK, b = chunk_end[c] * RW_HOST_BLOCK > n_cpu ? n_cpu : chunk_end[c] * RW_HOST_BLOCK;
             if (bits) {
                 const size_t ba = a / 8, bb = (b + 7) / 8;
+                const size_t ra = a / L, rb = (b + L - 1) / L > rows_cpu ? rows_cpu : (b + L - 1) / L;
+                CK(rw_launch_pack_bits(h->d_obs, (uint32_t *)h->d_pack, h->d_pack + off_wide, a, b, (int)L, nwide, ra, rb, st));
                 CK(cudaMemcpyAsync(h->h_pack + ba, h->d_pack + ba, bb - ba, cudaMemcpyDeviceToHost, st));
-                if (nwide) {
-                    const size_t ra = a / L, rb = (b + L - 1) / L > rows_cpu ? rows_cpu : (b + L - 1) / L;
+                if (nwide)
                     CK(cudaMemcpyAsync(h->h_pack + off_wide + ra * nwide, h->d_pack + off_wide + ra * nwide, (rb - ra) * nwide,
                                        cudaMemcpyDeviceToHost, st));
-                }
             } else {
+                CK(rw_launch_pack_u8(h->d_obs + a, h->d_pack + a, b - a, st));
                 CK(cudaMemcpyAsync(h->h_pack + a, h->d_pack + a, b - a, cudaMemcpyDeviceToHost, st));
             }
             CK(cudaEventRecord(h->pack_ev[c], st));
@@ -622,8 +675,8 @@ int rw_step_host(rw_handle *h, const int32_t *actions_host, float *obs_host, flo
     }
     if (reward_host) CK(cudaMemcpyAsync(reward_host, h->d_reward, (size_t)p.E * p.n * 4, cudaMemcpyDeviceToHost, st));
     if (done_host) CK(cudaMemcpyAsync(done_host, h->d_done, (size_t)p.E, cudaMemcpyDeviceToHost, st));
-    const bool timed_dma = n_cpu && n_cpu < n_obs;
-    if (obs_host && n_cpu < n_obs) {  // the copy engine's share (everything, for the plain transport)
+    if (obs_host && n_cpu < n_obs) {  // the copy engine's share (everything, for the plain transport).  Device-to-host copies of
+        // different streams do not overlap on this hardware, so it simply follows the compressed pieces on the same stream.
         if (timed_dma) CK(cudaEventRecord(h->dma_ev[0], st));
         CK(cudaMemcpyAsync(obs_host + n_cpu, h->d_obs + n_cpu, (n_obs - n_cpu) * 4, cudaMemcpyDeviceToHost, st));
         if (timed_dma) CK(cudaEventRecord(h->dma_ev[1], st));
@@ -640,7 +693,7 @@ int rw_step_host(rw_handle *h, const int32_t *actions_host, float *obs_host, flo
         job.nwide = nwide;
         job.n_rows = rows_cpu;
         job.nchunks = nch;
-        job.blocks_per_chunk = bpc;
+        for (int c = 0; c < nch; c++) job.chunk_end[c] = chunk_end[c];
         rw_hostpool_begin(job);
         cudaError_t err = cudaSuccess;
         for (int c = 0; c < nch && err == cudaSuccess; c++) {
@@ -654,28 +707,37 @@ int rw_step_host(rw_handle *h, const int32_t *actions_host, float *obs_host, flo
         t_done = now_us();
         CK(err);
     }
-    CK(cudaStreamSynchronize(st));
-    const double t_end = now_us();
-    double dma_ms = 0;
+    double dma_us = 0, dma_end = 0;
     if (timed_dma) {
-        float ms = 0;
+        const bool late = cudaEventQuery(h->dma_ev[1]) == cudaErrorNotReady;
+        CK(cudaEventSynchronize(h->dma_ev[1]));
+        const double t_sync = now_us();
+        float ms = 0, ms_end = 0;
         CK(cudaEventElapsedTime(&ms, h->dma_ev[0], h->dma_ev[1]));
-        dma_ms = ms;
-        // re-balance: both sides should finish together.  Rates as observed in this call (the expansion's includes its waits
-        // for the chunks; both include whatever the other one took from the memory system).
-        const double cpu_rate = (double)n_cpu * 4 / ((t_done - t_first) > 1 ? (t_done - t_first) : 1);            // bytes / us
-        const double dma_rate = (double)(n_obs - n_cpu) * 4 / ((dma_ms * 1e3) > 1 ? (dma_ms * 1e3) : 1);
-        double target = dma_rate / (dma_rate + cpu_rate);
+        CK(cudaEventElapsedTime(&ms_end, h->pack_ev[0], h->dma_ev[1]));  // negative when the copy ended before chunk 0 landed
+        dma_us = ms * 1e3;
+        dma_end = late ? t_sync : t_first + ms_end * 1e3;  // on the host clock (chunk 0 was seen at t_first)
+        // re-balance so that the expansion and the copy engine FINISH together.  With the rates observed in this call (each
+        // includes what the other took from the memory system) and the copy's head start d0 over the expansion, the copy
+        // engine's bytes x solve (B - x) / r_cpu = d0 + x / r_dma.
+        const double B = (double)n_obs * 4, x_now = (double)(n_obs - n_cpu) * 4;
+        const double r_cpu = (B - x_now) / ((t_done - t_first) > 1 ? (t_done - t_first) : 1);  // bytes / us
+        const double r_dma = x_now / (dma_us > 1 ? dma_us : 1);
+        const double d0 = (dma_end - dma_us) - t_first;
+        double target = (B / r_cpu - d0) / (1.0 / r_cpu + 1.0 / r_dma) / B;
+        if (!(target > 0.02)) target = 0.02;
         if (target > 0.9) target = 0.9;
-        if (target < 0.02) target = 0.02;
         h->dma_frac = 0.5 * h->dma_frac + 0.5 * target;
     }
+    CK(cudaStreamSynchronize(st));
+    const double t_end = now_us();
     h->host_calls++;
     if (trace)
         fprintf(stderr, "[rw_step_host] %s rows_cpu %zu/%zu chunks %d | enqueue %.0f first-chunk %.0f last-chunk %.0f expand-done %.0f "
-                        "end %.0f us | dma %.0f us | dma_frac -> %.3f | threads %d isa %d\n",
+                        "end %.0f us | dma %.0f us, ends at %.0f | dma_frac -> %.3f | threads %d isa %d\n",
                 !n_cpu ? "plain" : bits ? "bits" : "bytes", rows_cpu, n_rows, nch, 0.0, n_cpu ? t_first - t_call : 0.0,
-                n_cpu ? t_last - t_call : 0.0, n_cpu ? t_done - t_call : 0.0, t_end - t_call, dma_ms * 1e3, h->dma_frac,
+                n_cpu ? t_last - t_call : 0.0, n_cpu ? t_done - t_call : 0.0, t_end - t_call, dma_us, timed_dma ? dma_end - t_call : 0.0,
+                h->dma_frac,
                 n_cpu ? rw_hostpool_threads() : 0, n_cpu ? rw_hostpool_isa() : 0);
     return RW_OK;
 }
@@ -744,7 +806,7 @@ int rw_host_stream_probe(float *dst, int64_t n, int32_t repeats, double *gb_per_
     job.dst = dst;
     job.n = (size_t)n;
     double best = 0;
-    rw_hostpool_prewake(dst);
+    rw_hostpool_prewake();
     for (int r = 0; r < repeats + 1; r++) {  // the first pass warms the pool up
         job.fill_value = (float)r;
         const double t0 = now_us();
@@ -784,7 +846,7 @@ int rw_host_alloc(void **out, int64_t bytes) {
 int rw_host_alloc_near(rw_handle *h, void **out, int64_t bytes) {
     if (!h || !out || bytes <= 0) return RW_EINVAL;
     CK(cudaSetDevice(h->device));
-    CK(alloc_pinned_on_node(out, (size_t)bytes, gpu_numa_node(h->device)));
+    CK(alloc_pinned_placed(out, (size_t)bytes, gpu_numa_node(h->device), RW_HOST_LOCAL_TAIL));
     return RW_OK;
 }
 

@@ -204,16 +204,11 @@ void fill(float *out, size_t a, size_t b, float value) {
 }
 
 // ------------------------------------------------------------------------------------------------ NUMA helpers
-// The expansion is a pure memory stream; on a two-socket host half of it crosses the socket interconnect unless the workers
-// run next to the memory.  The node of the destination buffer is looked up (move_pages with a NULL target only queries) and
-// the workers are confined to that node's CPUs.  Every step is best effort: failures leave the scheduler free.
-int node_of(const void *p) {
-    void *page = reinterpret_cast<void *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)4095);
-    int status = -1;
-    const long rc = syscall(SYS_move_pages, 0, 1UL, &page, nullptr, &status, 0);
-    return rc == 0 && status >= 0 ? status : -1;
-}
-
+// The expansion is a pure memory stream, bound by the DRAM write bandwidth of the socket(s) that hold the destination pages
+// (about 200 GB/s per socket of the 2 x Xeon 8562Y+ hosts this was tuned on, reached by ~10 threads).  Buffers from
+// rw_host_alloc_near are therefore striped over the sockets, the workers are spread over the sockets, and every block is
+// preferably expanded by a worker of the socket that holds its pages (per-socket queues, stealing when a queue runs dry).
+// Every step is best effort: without NUMA information there is one queue and the scheduler is left free.
 }  // namespace
 
 bool rw_host_cpus_of_node(int node, cpu_set_t *set) {
@@ -237,7 +232,45 @@ bool rw_host_cpus_of_node(int node, cpu_set_t *set) {
     return count > 0;
 }
 
+int rw_host_numa_nodes() {
+    static int n = -1;
+    if (n < 0) {
+        int k = 0;
+        cpu_set_t s;
+        while (k < RW_HOST_MAX_NODES && rw_host_cpus_of_node(k, &s)) k++;
+        if (getenv("RWARE_B200_HOST_NUMA") && atoi(getenv("RWARE_B200_HOST_NUMA")) == 0) k = 1;
+        n = k < 1 ? 1 : k;
+    }
+    return n;
+}
+
+// node of every page in `pages` (move_pages with a NULL target only queries); -1 where unknown
+void rw_host_nodes_of(void *const *pages, int count, int *status) {
+    for (int i = 0; i < count; i++) status[i] = -1;
+    for (int a = 0; a < count; a += 512) {
+        const int k = count - a < 512 ? count - a : 512;
+        if (syscall(SYS_move_pages, 0, (unsigned long)k, pages + a, nullptr, status + a, 0) != 0)
+            for (int i = 0; i < k; i++) status[a + i] = -1;
+    }
+}
+
 namespace {
+
+int node_of_cpu(int cpu) {
+    static int table[CPU_SETSIZE];
+    static bool built = false;
+    if (!built) {
+        for (int c = 0; c < CPU_SETSIZE; c++) table[c] = 0;
+        for (int nd = 0; nd < rw_host_numa_nodes(); nd++) {
+            cpu_set_t s;
+            if (!rw_host_cpus_of_node(nd, &s)) continue;
+            for (int c = 0; c < CPU_SETSIZE; c++)
+                if (CPU_ISSET(c, &s)) table[c] = nd;
+        }
+        built = true;
+    }
+    return cpu >= 0 && cpu < CPU_SETSIZE ? table[cpu] : 0;
+}
 
 // CPUs this process may use on average: the cgroup v2 / v1 CFS quota if there is one (a pool that keeps more threads busy
 // than the quota gets the whole process throttled for the rest of the 100 ms period), else 0
@@ -256,13 +289,6 @@ double cgroup_cpu_quota() {
     return q > 0 && period > 0 ? (double)q / (double)period : 0;
 }
 
-int count_nodes() {
-    int n = 0;
-    cpu_set_t s;
-    while (n < 64 && rw_host_cpus_of_node(n, &s)) n++;
-    return n < 1 ? 1 : n;
-}
-
 int default_threads() {
     const char *ev = getenv("RWARE_B200_HOST_THREADS");
     if (ev && atoi(ev) > 0) return atoi(ev);
@@ -270,46 +296,62 @@ int default_threads() {
     if (hw == 0) hw = 1;
     unsigned ranks = 1;  // one process per GPU under torchrun: share the cores between the ranks of this node
     if (const char *lw = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(lw) > 0 ? (unsigned)atoi(lw) : 1;
-    // one thread per physical core at most.  A single rank stays on the socket of its buffer; streaming stores saturate that
-    // socket's memory controllers well before all of its cores are busy.
+    // one thread per physical core at most; ~10 threads per socket saturate its memory controllers
     double budget = hw >= 4 ? hw / 2.0 : hw;
-    const int nodes = count_nodes();
-    if (ranks < (unsigned)nodes) budget = budget * ranks / nodes;
     const double quota = cgroup_cpu_quota();
     if (quota > 0 && quota < budget) budget = quota;  // workers block between calls, so the pool may use the whole quota
     int t = (int)(budget / ranks);
-    return t < 1 ? 1 : (t > 32 ? 32 : t);
+    const int cap = 12 * rw_host_numa_nodes();
+    return t < 1 ? 1 : (t > cap ? cap : t);
 }
 
 // ------------------------------------------------------------------------------------------------ the pool
+constexpr int MAXQ = RW_HOST_MAX_NODES;
+
 struct Slot {  // parameters of one job; slot (generation & 1) is stable from publication until every block is done
     RwHostJob job;
     size_t nblocks = 0;
+    int nq = 1;
+    std::vector<uint32_t> qblocks[MAXQ];  // blocks whose pages sit on node q, ascending
     std::atomic<int> chunks_ready{0};
     std::atomic<int> cancelled{0};
     std::atomic<size_t> blocks_done{0};
     char pad[64];
 };
 
+struct DstInfo {  // node of every block of a destination buffer (looked up once per buffer)
+    const float *dst = nullptr;
+    size_t n = 0;
+    std::vector<uint8_t> node;
+};
+
+struct alignas(64) QueueCtr {
+    // (generation << 32) | blocks still to hand out.  A thread takes a block by CAS-decrementing the low half; a successful
+    // CAS on generation g proves that job g is still incomplete, so reading slot[g & 1] afterwards is safe.
+    std::atomic<uint64_t> v{0};
+};
+
 struct Pool {
     std::vector<std::thread> workers;
-    int T = 1;      // participants of a job, caller included
-    int node = -2;  // NUMA node the workers are currently confined to (-2: never placed)
+    int T = 1;  // participants of a job, caller included
+    int nq = 1;
     pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
     pthread_cond_t cv = PTHREAD_COND_INITIALIZER;
     uint64_t wake_seq = 0;  // under mu
     bool quit = false;      // under mu
-    // (generation << 32) | blocks still to hand out.  A thread takes a block by CAS-decrementing the low half; a successful
-    // CAS on generation g proves that job g is still incomplete, so reading slot[g & 1] afterwards is safe.
-    std::atomic<uint64_t> ctr{0};
+    QueueCtr ctr[MAXQ];
+    uint64_t gen = 0;       // under the job lock
     Slot slot[2];
+    DstInfo known[4];
+    int known_next = 0;
     double spin_us = 250;  // a worker without work spins this long (the copies and the kernel of a call are in flight) before it parks
 
     void run_block(const Slot &s, size_t blk) {
         const RwHostJob &j = s.job;
         const size_t a = blk * BLOCK, b = a + BLOCK > j.n ? j.n : a + BLOCK;
-        if (j.nchunks > 1) {  // the bytes this block decodes arrive with chunk (blk / blocks_per_chunk)
-            const int need = (int)(blk / j.blocks_per_chunk) + 1;
+        if (j.nchunks > 1) {  // the bytes this block decodes arrive with the piece that covers it
+            int need = 1;
+            while (need < j.nchunks && blk >= j.chunk_end[need - 1]) need++;
             while (s.chunks_ready.load(std::memory_order_acquire) < need) cpu_relax();
         }
         if (s.cancelled.load(std::memory_order_relaxed)) return;
@@ -320,27 +362,33 @@ struct Pool {
         }
     }
 
-    // pulls blocks until the current job has none left; returns true if it did any work
-    bool drain() {
+    // pulls blocks -- from the queue of node `home` first, then from the others -- until the current job has none left;
+    // returns true if it did any work
+    bool drain(int home) {
         bool any = false;
-        uint64_t v = ctr.load(std::memory_order_acquire);
-        for (;;) {
-            const uint32_t left = (uint32_t)v;
-            if (left == 0) return any;
-            if (!ctr.compare_exchange_weak(v, v - 1, std::memory_order_acq_rel, std::memory_order_acquire)) continue;
-            Slot &s = slot[(v >> 32) & 1];
-            run_block(s, s.nblocks - left);
-            s.blocks_done.fetch_add(1, std::memory_order_release);
-            any = true;
-            v = ctr.load(std::memory_order_acquire);
+        for (int k = 0; k < nq; k++) {
+            const int q = (home + k) % nq;
+            uint64_t v = ctr[q].v.load(std::memory_order_acquire);
+            for (;;) {
+                const uint32_t left = (uint32_t)v;
+                if (left == 0) break;
+                if (!ctr[q].v.compare_exchange_weak(v, v - 1, std::memory_order_acq_rel, std::memory_order_acquire)) continue;
+                Slot &s = slot[(v >> 32) & 1];
+                run_block(s, s.qblocks[q][s.qblocks[q].size() - left]);
+                s.blocks_done.fetch_add(1, std::memory_order_release);
+                any = true;
+                k = -1;  // after a block, look at the home queue first again
+                break;
+            }
         }
+        return any;
     }
 
-    void worker() {
+    void worker(int home) {
         uint64_t seen = 0;
         double idle_since = now_us();
         for (;;) {
-            if (drain()) { idle_since = now_us(); continue; }
+            if (drain(home)) { idle_since = now_us(); continue; }
             if (now_us() - idle_since < spin_us) { cpu_relax(); continue; }
             pthread_mutex_lock(&mu);
             while (!quit && wake_seq == seen) pthread_cond_wait(&cv, &mu);
@@ -354,20 +402,38 @@ struct Pool {
 
     void start(int threads) {
         T = threads < 1 ? 1 : threads;
+        nq = rw_host_numa_nodes();
+        if (nq > MAXQ) nq = MAXQ;
+        const int home0 = node_of_cpu(sched_getcpu());  // the caller usually runs next to its GPU: the workers start on the other node
         try {
-            for (int t = 1; t < T; t++) workers.emplace_back([this] { worker(); });
+            for (int t = 1; t < T; t++) {
+                const int home = (home0 + t) % nq;
+                workers.emplace_back([this, home] { worker(home); });
+                cpu_set_t set;
+                if (nq > 1 && rw_host_cpus_of_node(home, &set)) pthread_setaffinity_np(workers.back().native_handle(), sizeof(set), &set);
+            }
         } catch (...) {  // thread limit reached: work with the threads that exist
         }
         T = (int)workers.size() + 1;
     }
 
-    void place(const void *dst) {
-        const int want = node_of(dst);
-        if (want < 0 || want == node) return;
-        cpu_set_t set;
-        if (!rw_host_cpus_of_node(want, &set)) return;
-        for (auto &w : workers) pthread_setaffinity_np(w.native_handle(), sizeof(set), &set);
-        node = want;
+    const std::vector<uint8_t> &nodes_of(const float *dst, size_t n) {
+        for (auto &k : known)
+            if (k.dst == dst && k.n >= n) return k.node;
+        DstInfo &k = known[known_next++ & 3];
+        k.dst = dst;
+        k.n = n;
+        const size_t nb = (n + BLOCK - 1) / BLOCK;
+        k.node.assign(nb, 0);
+        if (nq > 1) {
+            std::vector<void *> pages(nb);
+            std::vector<int> st(nb);
+            for (size_t b = 0; b < nb; b++)
+                pages[b] = reinterpret_cast<void *>(reinterpret_cast<uintptr_t>(dst + b * BLOCK + (b + 1 == nb ? 0 : BLOCK / 2)) & ~(uintptr_t)4095);
+            rw_host_nodes_of(pages.data(), (int)nb, st.data());
+            for (size_t b = 0; b < nb; b++) k.node[b] = (uint8_t)(st[b] >= 0 && st[b] < nq ? st[b] : 0);
+        }
+        return k.node;
     }
 
     void wake() {
@@ -424,30 +490,34 @@ Pool *pool() {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ internal interface (rw_hostpack.h)
-void rw_hostpool_prewake(const void *dst) {
-    Pool *p = pool();
-    static const bool numa = !(getenv("RWARE_B200_HOST_NUMA") && atoi(getenv("RWARE_B200_HOST_NUMA")) == 0);
-    if (numa && dst && p->node == -2) p->place(dst);  // first placement; later moves happen under the job lock
-    p->wake();
-}
+void rw_hostpool_prewake() { pool()->wake(); }
 
 void rw_hostpool_begin(const RwHostJob &job) {
     Pool *p = pool();
     pthread_mutex_lock(&g_job_mu);
-    static const bool numa = !(getenv("RWARE_B200_HOST_NUMA") && atoi(getenv("RWARE_B200_HOST_NUMA")) == 0);
-    if (numa && job.dst) p->place(job.dst);
-    const uint64_t gen = (p->ctr.load(std::memory_order_acquire) >> 32) + 1;
+    const uint64_t gen = ++p->gen;
     Slot &s = p->slot[gen & 1];
     s.job = job;
     s.nblocks = (job.n + BLOCK - 1) / BLOCK;
+    s.nq = p->nq;
     if (s.job.nchunks < 1) s.job.nchunks = 1;
-    if (s.job.blocks_per_chunk < 1) s.job.blocks_per_chunk = s.nblocks ? s.nblocks : 1;
+    if (s.job.nchunks > 8) s.job.nchunks = 8;
+    const std::vector<uint8_t> &node = p->nodes_of(job.dst, job.n);
+    for (int q = 0; q < p->nq; q++) s.qblocks[q].clear();
+    for (size_t b = 0; b < s.nblocks; b++) s.qblocks[node[b]].push_back((uint32_t)b);
     s.chunks_ready.store(0, std::memory_order_relaxed);
     s.cancelled.store(0, std::memory_order_relaxed);
     s.blocks_done.store(0, std::memory_order_relaxed);
     g_cur = &s;
-    p->ctr.store((gen << 32) | (uint64_t)(uint32_t)s.nblocks, std::memory_order_release);
+    for (int q = 0; q < p->nq; q++)
+        p->ctr[q].v.store((gen << 32) | (uint64_t)(uint32_t)s.qblocks[q].size(), std::memory_order_release);
     p->wake();
+    static const bool trace = getenv("RWARE_B200_HOST_TRACE") != nullptr;
+    if (trace && (gen % 16) == 1) {
+        fprintf(stderr, "[rw_hostpool] job %llu: %zu blocks, per-node queues:", (unsigned long long)gen, s.nblocks);
+        for (int q = 0; q < p->nq; q++) fprintf(stderr, " node%d=%zu", q, s.qblocks[q].size());
+        fprintf(stderr, " | threads %d, caller on node %d\n", p->T, node_of_cpu(sched_getcpu()));
+    }
 }
 
 void rw_hostpool_chunk_ready(int chunks) { g_cur->chunks_ready.store(chunks, std::memory_order_release); }
@@ -460,7 +530,7 @@ void rw_hostpool_cancel() {
 void rw_hostpool_finish() {
     Pool *p = g_pool;
     Slot &s = *g_cur;
-    p->drain();  // the caller works too
+    p->drain(node_of_cpu(sched_getcpu()));  // the caller works too
     while (s.blocks_done.load(std::memory_order_acquire) != s.nblocks) cpu_relax();
     g_cur = nullptr;
     pthread_mutex_unlock(&g_job_mu);

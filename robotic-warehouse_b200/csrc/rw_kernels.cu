@@ -5,6 +5,7 @@
 #include "rw_launch.h"
 #include "rw_logic.cuh"
 #include "../../include/rware_b200.h"
+#include "rw_state_io.h"
 
 // ---------------------------------------------------------------- cold-path kernels (state views, seeding, synthetic actions)
 __global__ void rw_get_state_kernel(const RwParams p, const rw_state_view v) {
@@ -39,42 +40,10 @@ __global__ void rw_get_state_kernel(const RwParams p, const rw_state_view v) {
         for (int w = 0; w < RW_RNG_WORDS; w++) v.rng[env * RW_RNG_WORDS + w] = p.rng[(size_t)w * p.E_pad + env];
 }
 
-__global__ void rw_set_state_kernel(const RwParams p, const rw_state_view v) {
+__global__ void rw_set_state_kernel(const RwParams p, const rw_state_view v) {  // see rw_state_io.h
     int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= p.E) return;
-    int32_t *t = p.state + (size_t)(env >> 5) * p.nw * RW_TILE + (env & 31);
-    RwLane l{t, nullptr, nullptr, 0, nullptr, nullptr};
-    const RwOff o = rw_off<RwDynamic>(p);
-    for (int i = 0; i < p.n; i++) {
-        uint32_t aw = rw_agent(l, i);
-        int x = v.agent_x ? v.agent_x[env * p.n + i] : rw_ax(aw);
-        int y = v.agent_y ? v.agent_y[env * p.n + i] : rw_ay(aw);
-        int d = v.agent_dir ? v.agent_dir[env * p.n + i] : rw_adir(aw);
-        int c = v.agent_carry ? v.agent_carry[env * p.n + i] : rw_acarry(aw);
-        int hd = v.agent_has_delivered ? (v.agent_has_delivered[env * p.n + i] != 0) : rw_adeliv(aw);
-        rw_set_agent(l, i, rw_apack(x & 0xff, y & 0xff, d & 3, hd, c & 0x1fff));
-        if (v.agent_msg && p.msg_bits) {
-            uint32_t bits = 0;
-            for (int b = 0; b < p.msg_bits; b++) bits |= (uint32_t)(v.agent_msg[(env * p.n + i) * p.msg_bits + b] & 1) << b;
-            t[(p.w_msg + i) * RW_TILE] = (int32_t)bits;
-        }
-    }
-    if (v.shelf_x && v.shelf_y)
-        for (int k = 0; k < p.S; k++) rw_set_shelf_cell(o, l, k, v.shelf_y[env * p.S + k] * p.W + v.shelf_x[env * p.S + k]);
-    if (v.queue)
-        for (int q = 0; q < p.R; q++) rw_set_queue(o, l, q, v.queue[env * p.R + q]);
-    if (v.cur_steps) t[p.w_steps * RW_TILE] = v.cur_steps[env];
-    if (v.cur_inactive) t[p.w_inact * RW_TILE] = v.cur_inactive[env] & 0x7fffffff;
-    // flag worlds where two shelves share a cell (cold path, O(S^2)); see RW_OVERLAP_BIT
-    bool overlap = false;
-    for (int k = 1; k < p.S && !overlap; k++) {
-        int c = rw_shelf_cell(o, l, k);
-        for (int j = 0; j < k; j++) overlap |= (rw_shelf_cell(o, l, j) == c);
-    }
-    uint32_t wi = (uint32_t)t[p.w_inact * RW_TILE] & ~RW_OVERLAP_BIT;
-    t[p.w_inact * RW_TILE] = (int32_t)(wi | (overlap ? RW_OVERLAP_BIT : 0u));
-    if (v.rng)
-        for (int w = 0; w < RW_RNG_WORDS; w++) p.rng[(size_t)w * p.E_pad + env] = v.rng[env * RW_RNG_WORDS + w];
+    if (rw_set_state_world(p, v, env)) atomicAdd(p.err_count, 1ULL);
 }
 
 __global__ void rw_seed_scatter_kernel(const RwParams p, const uint32_t *__restrict__ staging, const uint8_t *__restrict__ mask) {
@@ -117,33 +86,38 @@ cudaError_t rw_launch_pack_u8(const float *in, uint8_t *out, size_t n, cudaStrea
 // the float32 rows (rw_hostpack.cpp).  bits word w, bit i <- in[32 w + i] != 0 (the bits of the "wide" positions are ignored by
 // the host); wide[row * nwide + k] <- (uint8_t)in[row * L + k].  A warp turns 1024 consecutive floats into 32 words: 32
 // coalesced 128-byte loads in flight, one ballot each, one coalesced 128-byte store.
-__global__ void rw_pack_bits_kernel(const float *__restrict__ in, uint32_t *__restrict__ bits, uint8_t *__restrict__ wide, size_t n,
-                                    int L, int nwide, size_t n_rows) {
+__global__ void rw_pack_bits_kernel(const float *__restrict__ in, uint32_t *__restrict__ bits, uint8_t *__restrict__ wide, size_t f_lo,
+                                    size_t f_hi, int L, int nwide, size_t row_lo, size_t row_hi) {
+    // floats [f_lo, f_hi) (f_lo a multiple of 1024) -> bit words; rows [row_lo, row_hi) -> wide bytes
     const int lane = threadIdx.x & 31;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (size_t)gridDim.x * blockDim.x;
-    const size_t nwords = (n + 31) / 32;
-    for (size_t g = tid >> 5; g * 32 < nwords; g += nthreads >> 5) {
+    const size_t w_lo = f_lo / 32, w_hi = (f_hi + 31) / 32;
+    for (size_t g = (w_lo >> 5) + (tid >> 5); g * 32 < w_hi; g += nthreads >> 5) {
         const size_t f0 = g * 1024;
         uint32_t mine = 0;
 #pragma unroll 8
         for (int j = 0; j < 32; j++) {
             const size_t idx = f0 + (size_t)j * 32 + lane;
-            const float v = idx < n ? __ldcs(in + idx) : 0.0f;
+            const float v = idx < f_hi ? __ldcs(in + idx) : 0.0f;
             const uint32_t b = __ballot_sync(0xffffffffu, v != 0.0f);
             if (lane == j) mine = b;
         }
-        if (g * 32 + lane < nwords) bits[g * 32 + lane] = mine;
+        if (g * 32 + lane < w_hi) bits[g * 32 + lane] = mine;
     }
-    const size_t nw = n_rows * (size_t)nwide;
+    const size_t nw = (row_hi - row_lo) * (size_t)nwide;
     for (size_t i = tid; i < nw; i += nthreads) {
-        const size_t row = i / (size_t)nwide;
-        wide[i] = (uint8_t)in[row * (size_t)L + (i - row * (size_t)nwide)];
+        const size_t row = row_lo + i / (size_t)nwide, k = i % (size_t)nwide;
+        wide[row * (size_t)nwide + k] = (uint8_t)in[row * (size_t)L + k];
     }
 }
 
-cudaError_t rw_launch_pack_bits(const float *in, uint32_t *bits, uint8_t *wide, size_t n, int L, int nwide, size_t n_rows,
-                                cudaStream_t stream) {
-    rw_pack_bits_kernel<<<148 * 8, 256, 0, stream>>>(in, bits, wide, n, L, nwide, n_rows);
+cudaError_t rw_launch_pack_bits(const float *in, uint32_t *bits, uint8_t *wide, size_t f_lo, size_t f_hi, int L, int nwide,
+                                size_t row_lo, size_t row_hi, cudaStream_t stream) {
+    const size_t groups = (f_hi - f_lo + 1023) / 1024;
+    int blocks = (int)((groups + 7) / 8);  // 8 warps per block, one 1024-float group per warp and pass
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    rw_pack_bits_kernel<<<blocks, 256, 0, stream>>>(in, bits, wide, f_lo, f_hi, L, nwide, row_lo, row_hi);
     return cudaGetLastError();
 }
 

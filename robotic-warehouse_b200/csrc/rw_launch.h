@@ -25,5 +25,5 @@ cudaError_t rw_launch_render(const RwParams &p, uint8_t *out, int64_t env0, int6
 
 // end-to-end transport (rw_step_host): device side (rw_kernels.cu); the host side is rw_hostpack.h
 cudaError_t rw_launch_pack_u8(const float *in, uint8_t *out, size_t n, cudaStream_t stream);
-cudaError_t rw_launch_pack_bits(const float *in, uint32_t *bits, uint8_t *wide, size_t n, int L, int nwide, size_t n_rows,
-                                cudaStream_t stream);
+cudaError_t rw_launch_pack_bits(const float *in, uint32_t *bits, uint8_t *wide, size_t f_lo, size_t f_hi, int L, int nwide,
+                                size_t row_lo, size_t row_hi, cudaStream_t stream);

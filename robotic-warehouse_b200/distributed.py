@@ -76,7 +76,9 @@ class ShardedVecWarehouse:
     def enable_fused_gather(self):
         """Sets up the fused push all-gather (CUDA IPC peer mappings over NVLink): afterwards `step(..., gather=True)`
         lets the step kernel's TMA stores write every observation chunk into all ranks' gathered tensors, and the only
-        collective left is a 4-byte all-reduce that acts as the barrier.  Needs uniform shards and one process per GPU."""
+        collective left is a 4-byte all-reduce that acts as the barrier.  Needs uniform shards and one process per GPU.
+        The gathered tensors are double-buffered: step k returns slot k & 1, valid until step k+2 is issued; consume them on
+        the current stream before the next step (include/rware_b200.h, rw_step_gather)."""
         if not self.uniform:
             raise ValueError("fused gather needs total_envs divisible by the number of ranks")
         tensors, handle = self.local.backend.gather_create(self.world_size, self.rank)
@@ -92,9 +94,9 @@ class ShardedVecWarehouse:
             a = actions
             if not (isinstance(a, torch.Tensor) and a.dtype == torch.int32 and a.device == self.device and a.is_contiguous()):
                 a = torch.as_tensor(actions, device=self.device).to(torch.int32).contiguous()
-            self.local.backend.step_gather(a)
+            slot = self.local.backend.step_gather(a)
             dist.all_reduce(self._flag, group=self.group)  # stream-ordered barrier: every rank's pushes have landed
-            return self._fused
+            return self._fused[slot]
         obs, rew, done = self.local.step(actions)
         if gather:
             return self.gather(obs, rew, done)

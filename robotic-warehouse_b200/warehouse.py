@@ -178,6 +178,11 @@ class Warehouse:
         """host entity objects -> device world (what the reference keeps in Python objects)."""
         n = self.n_agents
         shelf_ids = {id(s): s.id for s in self.shelfs}
+        H, W = self.grid_size
+        for ent in (*self.agents, *self.shelfs):  # the reference's _recalc_grid (749-755) raises IndexError for these
+            if not (0 <= int(ent.x) < W and 0 <= int(ent.y) < H):
+                axis, bad = (2, int(ent.x)) if not 0 <= int(ent.x) < W else (1, int(ent.y))
+                raise IndexError(f"index {bad} is out of bounds for axis {axis} with size {W if axis == 2 else H}")
         st = dict(
             agent_x=[[int(a.x) for a in self.agents]], agent_y=[[int(a.y) for a in self.agents]],
             agent_dir=[[Direction(a.dir).value for a in self.agents]],

@@ -15,6 +15,7 @@
 #include "../../robotic-warehouse_b200/csrc/rw_logic.cuh"
 #include "../../robotic-warehouse_b200/csrc/rw_coop.cuh"
 #include "../../robotic-warehouse_b200/csrc/rw_views.cuh"
+#include "../../robotic-warehouse_b200/csrc/rw_state_io.h"
 
 struct Sim {
     RwParams p;
@@ -201,42 +202,10 @@ void sim_get_state(Sim *s, const rw_state_view *v) {
     }
 }
 
-void sim_set_state(Sim *s, const rw_state_view *v) {
+void sim_set_state(Sim *s, const rw_state_view *v) {  // the same per-world function as the CUDA kernel (rw_state_io.h)
     const RwParams &p = s->p;
-    for (int64_t env = 0; env < p.E; env++) {
-        int32_t *t = p.state + (size_t)(env >> 5) * p.nw * RW_TILE + (env & 31);
-        RwLane l{t, nullptr, nullptr, 0, nullptr, nullptr};
-        const RwOff o = rw_off<RwDynamic>(p);
-        for (int i = 0; i < p.n; i++) {
-            uint32_t aw = rw_agent(l, i);
-            int x = v->agent_x ? v->agent_x[env * p.n + i] : rw_ax(aw);
-            int y = v->agent_y ? v->agent_y[env * p.n + i] : rw_ay(aw);
-            int d = v->agent_dir ? v->agent_dir[env * p.n + i] : rw_adir(aw);
-            int c = v->agent_carry ? v->agent_carry[env * p.n + i] : rw_acarry(aw);
-            int hd = v->agent_has_delivered ? (v->agent_has_delivered[env * p.n + i] != 0) : rw_adeliv(aw);
-            rw_set_agent(l, i, rw_apack(x & 0xff, y & 0xff, d & 3, hd, c & 0x1fff));
-            if (v->agent_msg && p.msg_bits) {
-                uint32_t bits = 0;
-                for (int b = 0; b < p.msg_bits; b++) bits |= (uint32_t)(v->agent_msg[(env * p.n + i) * p.msg_bits + b] & 1) << b;
-                t[(p.w_msg + i) * RW_TILE] = (int32_t)bits;
-            }
-        }
-        if (v->shelf_x && v->shelf_y)
-            for (int k = 0; k < p.S; k++) rw_set_shelf_cell(o, l, k, v->shelf_y[env * p.S + k] * p.W + v->shelf_x[env * p.S + k]);
-        if (v->queue)
-            for (int q = 0; q < p.R; q++) rw_set_queue(o, l, q, v->queue[env * p.R + q]);
-        if (v->cur_steps) t[p.w_steps * RW_TILE] = v->cur_steps[env];
-        if (v->cur_inactive) t[p.w_inact * RW_TILE] = v->cur_inactive[env] & 0x7fffffff;
-        bool overlap = false;
-        for (int k = 1; k < p.S && !overlap; k++) {
-            int c = rw_shelf_cell(o, l, k);
-            for (int j = 0; j < k; j++) overlap |= (rw_shelf_cell(o, l, j) == c);
-        }
-        uint32_t wi = (uint32_t)t[p.w_inact * RW_TILE] & ~RW_OVERLAP_BIT;
-        t[p.w_inact * RW_TILE] = (int32_t)(wi | (overlap ? RW_OVERLAP_BIT : 0u));
-        if (v->rng)
-            for (int w = 0; w < RW_RNG_WORDS; w++) p.rng[(size_t)w * p.E_pad + env] = v->rng[env * RW_RNG_WORDS + w];
-    }
+    for (int64_t env = 0; env < p.E; env++)
+        if (rw_set_state_world(p, *v, env)) *p.err_count += 1;
 }
 
 // whole-warehouse views (rw_views.cuh), same per-element functions as rw_views.cu

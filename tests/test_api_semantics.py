@@ -7,6 +7,7 @@ import torch
 import oracle_py
 import rware_b200
 from conftest import backend_factory, backend_params
+from rware_b200.warehouse import Action, RewardType, Warehouse
 
 KW = dict(shelf_columns=3, column_height=8, shelf_rows=1, n_agents=3, request_queue_size=3, max_steps=12)
 
@@ -146,3 +147,32 @@ def test_observation_bytes_are_the_same_values(backend):
     norm.reset(seed=0)
     with pytest.raises(RuntimeError):
         norm.observation_bytes()
+
+
+@pytest.mark.parametrize("backend", backend_params())
+def test_out_of_range_state_is_rejected_or_clamped(backend):
+    """A coordinate outside the grid: the facade raises IndexError like the reference's _recalc_grid (rware/warehouse.py:749-755);
+    the batched set_state clamps it into range and counts the world (rw_error_count) instead of letting later kernels index out
+    of bounds."""
+    env = Warehouse(3, 8, 1, 2, 0, 1, 2, None, None, RewardType.GLOBAL, _backend_factory=backend_factory(backend))
+    env.reset(seed=4)
+    env.agents[0].x = env.grid_size[1] + 3
+    with pytest.raises(IndexError):
+        env.step([Action.NOOP, Action.NOOP])
+    vec = rware_b200.VecWarehouse(40, 3, 8, 1, 2, request_queue_size=2, _backend_factory=backend_factory(backend))
+    vec.reset(seed=0)
+    st = {k: v.clone() for k, v in vec.get_state().items()}
+    H, W = vec.grid_size
+    st["agent_x"][3, 0] = 200
+    st["agent_y"][5, 1] = -4
+    st["shelf_x"][7, 2] = W
+    st["queue"][9, 0] = vec.n_shelves + 50
+    st["agent_carry"][11, 1] = 8000
+    before = vec.error_count()
+    vec.set_state(**st)
+    assert vec.error_count() - before == 5
+    back = vec.get_state()
+    assert int(back["agent_x"][3, 0]) == W - 1 and int(back["agent_y"][5, 1]) == 0 and int(back["shelf_x"][7, 2]) == W - 1
+    assert int(back["queue"][9, 0]) == vec.n_shelves and int(back["agent_carry"][11, 1]) == vec.n_shelves
+    obs, rew, done = vec.step(torch.ones((40, 2), dtype=torch.int32))  # and stepping such worlds is safe
+    assert obs.shape == (40, 2, vec.obs_len)

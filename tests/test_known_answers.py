@@ -2,7 +2,7 @@
 ids, `reset(seed=0)`, 500 steps of `default_rng(12345)` actions, SHA-256 over every float32 observation, float64 reward
 and done flag.  No oracle involved: the product path alone has to reproduce the reference's hashes, which covers the
 numpy-compatible reset sampler, the step, and the observation gather in one go.  Also: full-size batches (65 536 worlds)
-checked through size-independent properties and against the oracle on a sample of worlds."""
+checked through size-independent properties and against the oracle on every world."""
 import hashlib
 import json
 import os
@@ -47,17 +47,15 @@ def test_reference_sha256_through_the_product_path(key, backend):
 
 
 @pytest.mark.gpu
-def test_full_size_batch_properties_and_sampled_oracle_parity():
-    """BASELINE.json configs[1]: rware-tiny-4ag x 65 536 worlds on one GPU."""
+def test_full_size_batch_properties_and_full_population_oracle_parity():
+    """BASELINE.json configs[1]: rware-tiny-4ag x 65 536 worlds on one GPU.  EVERY world is compared with the oracle (a batched,
+    multi-threaded instance of it) at every step -- a tile-boundary or CTA-tail bug anywhere in the batch fails this."""
     import oracle_py
     E, T = 65536, 40
-    kw = rware_b200.env_kwargs("rware-tiny-4ag-v1")
     vec = rware_b200.make_vec("rware-tiny-4ag-v1", E, auto_reset=True)
     obs0 = vec.reset(seed=0).clone()
-    sample = np.r_[0:48, 32000:32016, E - 48:E]  # first tile(s), middle, last tile
-    orcs = {int(e): oracle_py.OracleEnv(vec.highways, vec.goals, 4, 0, 1, 4, None, 500, 1) for e in sample}
-    for e, o in orcs.items():
-        assert np.array_equal(o.reset(e), obs0[e].cpu().numpy())
+    orc = oracle_py.OracleBatch(oracle_py.OracleEnv(vec.highways, vec.goals, 4, 0, 1, 4, None, 500, 1), E, auto_reset=True)
+    assert np.array_equal(orc.reset(np.arange(E, dtype=np.uint64)), obs0.cpu().numpy())
     g = torch.Generator(device="cuda").manual_seed(5)
     ref = rware_b200.make_vec("rware-tiny-4ag-v1", E, auto_reset=True)  # second instance: determinism
     ref.reset(seed=0)
@@ -73,13 +71,12 @@ def test_full_size_batch_properties_and_sampled_oracle_parity():
         assert bool((cells[:, :, 1:5].sum(2) == 1).all()) and bool((cells[:, 4, 0] == 1).all())
         assert bool(((cells == 0) | (cells == 1)).all())
         assert bool((cells[:, :, 6] <= cells[:, :, 5]).all())  # requested implies shelf
-        ah = a.cpu().numpy()
-        oh, rh, dh = obs[sample].cpu().numpy(), rew[sample].cpu().numpy(), done[sample].cpu().numpy()
-        for k, e in enumerate(sample):
-            oo, orw, od = orcs[int(e)].step(ah[e])
-            if od:
-                oo = orcs[int(e)].reset()
-            assert np.array_equal(oo, oh[k]) and np.array_equal(orw.astype(np.float32), rh[k]) and od == bool(dh[k])
+        oo, orw, od = orc.step(a.cpu().numpy())
+        oh, rh, dh = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+        if not (np.array_equal(oo, oh) and np.array_equal(orw, rh) and np.array_equal(od, dh)):
+            bad = np.nonzero((oo != oh).reshape(E, -1).any(1) | (orw != rh).any(1) | (od != dh))[0]
+            raise AssertionError(f"step {t}: {bad.size} worlds differ from the oracle, first {bad[:8].tolist()} (tiles {(bad[:8] // 32).tolist()})")
+    orc.close()
     st = vec.get_state()
     # no two agents of a world share a cell; carried shelves sit under their carriers
     cell = st["agent_y"] * vec.grid_size[1] + st["agent_x"]
@@ -143,8 +140,8 @@ def _full_size_cases():
 @pytest.mark.parametrize("env_id,over,E,backend", _full_size_cases())
 def test_other_baseline_configs_at_full_size(env_id, over, E, backend):
     """BASELINE.json configs[2..4] at their per-GPU sizes (small-4ag x 32 768, medium-8ag-hard x 32 768, large-16ag r=2 x 16 384):
-    determinism across two instances, structural invariants of every observation row and of the state, and oracle parity on a
-    sample of worlds from the first, a middle and the last tile."""
+    determinism across two instances, structural invariants of every observation row and of the state, and oracle parity of
+    EVERY world at every step (batched multi-threaded oracle)."""
     import oracle_py
     from conftest import backend_factory
     T = 25
@@ -155,11 +152,9 @@ def test_other_baseline_configs_at_full_size(env_id, over, E, backend):
     dev = vec.device
     obs0 = vec.reset(seed=7).clone()
     twin.reset(seed=7)
-    sample = np.unique(np.r_[0:20, E // 2:E // 2 + 8, E - 20:E])
-    orcs = {int(e): oracle_py.OracleEnv(vec.highways, vec.goals, n, 0, r, kw["request_queue_size"], None, kw["max_steps"],
-                                        kw["reward_type"].value) for e in sample}
-    for e, o in orcs.items():
-        assert np.array_equal(o.reset(7 + e), obs0[e].cpu().numpy())
+    orc = oracle_py.OracleBatch(oracle_py.OracleEnv(vec.highways, vec.goals, n, 0, r, kw["request_queue_size"], None, kw["max_steps"],
+                                                    kw["reward_type"].value), E, auto_reset=True)
+    assert np.array_equal(orc.reset(7 + np.arange(E, dtype=np.uint64)), obs0.cpu().numpy())
     g = torch.Generator(device=dev).manual_seed(11)
     K = (2 * r + 1) ** 2
     for t in range(T):
@@ -173,13 +168,12 @@ def test_other_baseline_configs_at_full_size(env_id, over, E, backend):
         assert bool((cells[:, :, 1:5].sum(2) == 1).all()) and bool((cells[:, K // 2, 0] == 1).all())  # one-hot dirs; self in the centre
         assert bool(((cells == 0) | (cells == 1)).all()) and bool((cells[:, :, 6] <= cells[:, :, 5]).all())
         assert bool(((rew == 0) | (rew == 1)).all())                                           # INDIVIDUAL rewards
-        ah = a.cpu().numpy()
-        oh, rh, dh = obs[sample].cpu().numpy(), rew[sample].cpu().numpy(), done[sample].cpu().numpy()
-        for k, e in enumerate(sample):
-            oo, orw, od = orcs[int(e)].step(ah[e])
-            if od:
-                oo = orcs[int(e)].reset()
-            assert np.array_equal(oo, oh[k]) and np.array_equal(orw.astype(np.float32), rh[k]) and od == bool(dh[k]), (t, e)
+        oo, orw, od = orc.step(a.cpu().numpy())  # every world, not a sample
+        oh, rh, dh = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+        if not (np.array_equal(oo, oh) and np.array_equal(orw, rh) and np.array_equal(od, dh)):
+            bad = np.nonzero((oo != oh).reshape(E, -1).any(1) | (orw != rh).any(1) | (od != dh))[0]
+            raise AssertionError(f"step {t}: {bad.size} worlds differ from the oracle, first {bad[:8].tolist()} (tiles {(bad[:8] // 32).tolist()})")
+    orc.close()
     st = vec.get_state()
     cell = st["agent_y"] * vec.grid_size[1] + st["agent_x"]
     assert bool((torch.sort(cell, dim=1).values.diff(dim=1) != 0).all())                        # no two agents share a cell
