@@ -88,9 +88,15 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_baseline(env_id, overrides, target_seconds=10.0, threads=None):
-    """The oracle port (plain C, oracle/) on the host cores, random-action rollout of the same configuration."""
+def cpu_baseline(env_id, overrides, target_seconds=10.0, threads=None, n_worlds=None):
+    """The oracle port (plain C, oracle/) on the host cores, random-action rollout of the same configuration, timed two ways:
+    * lock step (the headline of this arm, `value`): the same batch of worlds as the GPU arm, every step advances ALL worlds
+      once and rewrites the stacked observation / reward / done arrays of the batch in host memory -- what a vector
+      environment built on the reference does, and exactly what the GPU arm's end-to-end call delivers per step;
+    * independent worlds: every host thread runs its worlds' episodes back to back, one world at a time, nothing stacked
+      (everything stays in that core's cache) -- an upper bound no batched consumer can use, kept for continuity with round 1."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
     import oracle_py
     import rware_b200
     kw = rware_b200.env_kwargs(env_id, **{k: v for k, v in overrides.items() if k != "observation_type"})
@@ -98,24 +104,39 @@ def cpu_baseline(env_id, overrides, target_seconds=10.0, threads=None):
     env = oracle_py.OracleEnv(highways, goals, kw["n_agents"], kw["msg_bits"], kw["sensor_range"], kw["request_queue_size"],
                               kw["max_inactivity_steps"], kw["max_steps"], kw["reward_type"].value)
     threads = threads or os.cpu_count() or 1
-    n_envs = threads * 8
-    t0 = time.perf_counter()
-    done, _ = oracle_py.rollout_random(env, n_envs, 200, seed=1, n_threads=threads)  # calibration
-    rate = done / (time.perf_counter() - t0)
-    steps = max(200, int(rate * target_seconds / n_envs))
-    t0 = time.perf_counter()
-    done, _ = oracle_py.rollout_random(env, n_envs, steps, seed=2, n_threads=threads)
-    dt = time.perf_counter() - t0
     quota = None
     try:  # the container's CFS quota, if any: `threads` host threads run, but only this many CPUs' worth of time is granted
         q, period = open("/sys/fs/cgroup/cpu.max").read().split()
         quota = None if q == "max" else float(q) / float(period)
     except Exception:
         pass
+    # independent worlds (round-1 protocol), a third of the time budget
+    n_envs = threads * 8
+    t0 = time.perf_counter()
+    done, _ = oracle_py.rollout_random(env, n_envs, 200, seed=1, n_threads=threads)  # calibration
+    rate = done / (time.perf_counter() - t0)
+    steps = max(200, int(rate * target_seconds / 3 / n_envs))
+    t0 = time.perf_counter()
+    done, _ = oracle_py.rollout_random(env, n_envs, steps, seed=2, n_threads=threads)
+    dt_ind = time.perf_counter() - t0
+    independent = {"value": done / dt_ind, "sample": f"{n_envs} worlds x {steps} steps, one world at a time per thread, {dt_ind:.1f} s"}
+    # lock step over the GPU arm's batch
+    E = int(n_worlds or 65536)
+    batch = oracle_py.OracleBatch(env, E, n_threads=threads, auto_reset=True)
+    batch.reset(np.arange(E, dtype=np.uint64))
+    t0 = time.perf_counter()
+    done, _ = batch.rollout_lockstep(4, seed=1)  # calibration (also first touch of the stacked arrays)
+    rate = done / (time.perf_counter() - t0)
+    steps = max(4, int(rate * target_seconds * 2 / 3 / E))
+    t0 = time.perf_counter()
+    done, _ = batch.rollout_lockstep(steps, seed=2)
+    dt = time.perf_counter() - t0
+    batch.close()
     return {"value": done / dt, "unit": "env-steps/s", "cores": threads, "cgroup_cpu_quota": quota, "kind": "port",
-            "sample": f"{n_envs} worlds x {steps} random-action steps of {env_id} {overrides or ''} with reset on done, "
-                      f"{dt:.1f} s on {threads} host threads (C oracle port; the Python reference itself cannot travel to the GPU box)",
-            "seconds": dt}
+            "sample": f"{E} worlds x {steps} lock-step random-action steps of {env_id} {overrides or ''} with reset on done, stacked "
+                      f"float32 observations / rewards / done of the whole batch rewritten every step, {dt:.1f} s on {threads} host "
+                      f"threads (C oracle port; the Python reference itself cannot travel to the GPU box)",
+            "independent_worlds": independent, "seconds": dt + dt_ind}
 
 
 def run_reference_arm(args):
@@ -125,7 +146,7 @@ def run_reference_arm(args):
     env_id, overrides, E = WORKLOADS[args.workload]
     vals = []
     for i in range(args.warmup + args.steps):
-        cb = cpu_baseline(env_id, overrides, target_seconds=args.ref_seconds)
+        cb = cpu_baseline(env_id, overrides, target_seconds=args.ref_seconds, n_worlds=(args.envs or E) * max(1, args.gpus))
         if i >= args.warmup:
             vals.append(cb)
     v = sum(c["value"] for c in vals) / len(vals)
@@ -136,8 +157,10 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "env-steps/s", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * secs, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": f"{env_id} {overrides or ''} random-action rollout, CPU (a step = one bounded sample, see cpu_baseline.sample)"},
-        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "config": {"workload": f"{env_id} {overrides or ''}".strip() + f", {(args.envs or E) * max(1, args.gpus)} worlds (the GPU arm's whole batch at {args.gpus} GPU(s)), random-action rollout (uniform actions), "
+                               "reset on done; CPU, lock step (a step of this arm = one bounded sample, see cpu_baseline.sample)",
+                   "worlds_per_gpu": args.envs or E},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "independent_worlds")},
         "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
@@ -605,8 +628,8 @@ def main():
             traffic = json.load(f).get("dram_bytes_per_launch")
     cb = None
     if not args.no_cpu_baseline:
-        cb = cpu_baseline(env_id, overrides, target_seconds=12.0)
-        cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cb = cpu_baseline(env_id, overrides, target_seconds=12.0, n_worlds=E)
+        cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "independent_worlds")}
     out = {
         "metric": "env-steps/s", "value": world * E * args.steps / (total_ms * 1e-3), "unit": "env-steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": kernel_ms,

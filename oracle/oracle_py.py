@@ -68,6 +68,8 @@ def lib():
         L.orc_batch_destroy.argtypes = [ctypes.c_void_p]
         L.orc_batch_reset.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_batch_step.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.orc_batch_rollout_lockstep.restype = ctypes.c_int64
+        L.orc_batch_rollout_lockstep.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64] + [ctypes.c_void_p] * 4
         _lib = L
     return _lib
 
@@ -237,6 +239,14 @@ class OracleBatch:
         a = np.ascontiguousarray(actions, dtype=np.int32).reshape(self.E, self.n, self.A)
         lib().orc_batch_step(self._h, _p(a), int(self.auto_reset), _p(self.obs), _p(self.reward), _p(self.done))
         return self.obs, self.reward, self.done
+
+    def rollout_lockstep(self, n_steps, seed=0):
+        """Random-action rollout in lock step (every step rewrites the stacked obs / reward / done arrays of the whole batch);
+        returns (env_steps_done, reward_sum)."""
+        rs = ctypes.c_double()
+        total = lib().orc_batch_rollout_lockstep(self._h, int(n_steps), int(seed), _p(self.obs), _p(self.reward), _p(self.done),
+                                                 ctypes.byref(rs))
+        return int(total), rs.value
 
     def close(self):
         if getattr(self, "_h", None):

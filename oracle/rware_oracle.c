@@ -889,3 +889,66 @@ void orc_batch_step(orc_batch *b, const int32_t *actions, int auto_reset, float 
     j.b = b; j.mode = 1; j.actions = actions; j.auto_reset = auto_reset; j.obs = obs; j.reward = reward; j.done = done;
     batch_run(b, j);
 }
+
+/* Lock-step random-action rollout of the whole batch: what a vector environment built on the reference does -- every step
+ * advances ALL worlds once and leaves the stacked observations / rewards / done flags of the batch in [E][n][L] / [E][n] / [E]
+ * arrays (written in full every step).  Threads are created once and meet at a barrier after every step; actions are generated
+ * per world from a counter-based generator.  Returns env-steps done. */
+typedef struct {
+    orc_batch *b;
+    int64_t lo, hi;
+    int n_steps;
+    uint64_t seed;
+    float *obs, *reward;
+    uint8_t *done;
+    pthread_barrier_t *bar;
+    double reward_sum;
+} lockstep_job;
+
+static void *lockstep_worker(void *arg) {
+    lockstep_job *j = (lockstep_job *)arg;
+    orc_batch *b = j->b;
+    const int n = b->cfg.n_agents, mb = b->cfg.msg_bits, A = 1 + mb;
+    int32_t actions[MAX_AGENTS * 17];
+    double rew[MAX_AGENTS];
+    for (int t = 0; t < j->n_steps; t++) {
+        for (int64_t e = j->lo; e < j->hi; e++) {
+            orc_env *w = b->env[e];
+            uint64_t as = (j->seed + (uint64_t)t) * 0x9e3779b97f4a7c15ULL + (uint64_t)e * 0xbf58476d1ce4e5b9ULL;
+            for (int a = 0; a < n; a++) {
+                actions[a * A] = (int32_t)(((splitmix64(&as) >> 32) * 5ULL) >> 32);
+                for (int k = 0; k < mb; k++) actions[a * A + 1 + k] = (int32_t)(splitmix64(&as) & 1);
+            }
+            float *obs = j->obs + (size_t)e * n * w->L;
+            uint8_t d = 0;
+            orc_step(w, actions, obs, rew, &d);
+            for (int a = 0; a < n; a++) { j->reward[(size_t)e * n + a] = (float)rew[a]; j->reward_sum += rew[a]; }
+            j->done[e] = d;
+            if (d) orc_reset(w, -1, obs);
+        }
+        pthread_barrier_wait(j->bar);
+    }
+    return NULL;
+}
+
+int64_t orc_batch_rollout_lockstep(orc_batch *b, int n_steps, uint64_t seed, float *obs, float *reward, uint8_t *done,
+                                   double *reward_sum) {
+    int T = b->n_threads < 1 ? 1 : b->n_threads;
+    if (T > b->E) T = (int)b->E;
+    pthread_barrier_t bar;
+    pthread_barrier_init(&bar, NULL, (unsigned)T);
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)T);
+    lockstep_job *jobs = (lockstep_job *)calloc((size_t)T, sizeof(lockstep_job));
+    for (int t = 0; t < T; t++) {
+        jobs[t].b = b; jobs[t].lo = b->E * t / T; jobs[t].hi = b->E * (t + 1) / T; jobs[t].n_steps = n_steps; jobs[t].seed = seed;
+        jobs[t].obs = obs; jobs[t].reward = reward; jobs[t].done = done; jobs[t].bar = &bar;
+        pthread_create(&th[t], NULL, lockstep_worker, &jobs[t]);
+    }
+    double rs = 0;
+    for (int t = 0; t < T; t++) { pthread_join(th[t], NULL); rs += jobs[t].reward_sum; }
+    if (reward_sum) *reward_sum = rs;
+    pthread_barrier_destroy(&bar);
+    free(th);
+    free(jobs);
+    return (int64_t)n_steps * b->E;
+}

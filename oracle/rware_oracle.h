@@ -107,6 +107,10 @@ orc_batch *orc_batch_create(const orc_config *cfg, int64_t n_envs, int n_threads
 void orc_batch_destroy(orc_batch *b);
 void orc_batch_reset(orc_batch *b, const uint64_t *seeds, float *obs);
 void orc_batch_step(orc_batch *b, const int32_t *actions, int auto_reset, float *obs, float *reward, uint8_t *done);
+/* Lock-step random-action rollout of the whole batch (a vector environment on the CPU): every step advances all worlds once and
+ * rewrites the stacked obs [E][n][L] / reward [E][n] / done [E] arrays; reset on done.  Returns env-steps done. */
+int64_t orc_batch_rollout_lockstep(orc_batch *b, int n_steps, uint64_t seed, float *obs, float *reward, uint8_t *done,
+                                   double *reward_sum);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,8 @@ import numpy as np
 import torch
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "lib", "librware_b200.so")
+# RWARE_B200_LIB_PATH: load another build of the library (A/B measurements of build-time options); default: the in-tree build
+LIB_PATH = os.environ.get("RWARE_B200_LIB_PATH") or os.path.join(_PKG_DIR, "lib", "librware_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_PKG_DIR), "include", "rware_b200.h")
 RW_ABI_VERSION = 2
 RNG_WORDS = 10

@@ -613,32 +613,64 @@ int rw_step_host(rw_handle *h, const int32_t *actions_host, float *obs_host, flo
     if (compress) {
         const double f = h->dma_frac_fixed >= 0 ? h->dma_frac_fixed : h->dma_frac;
         rows_cpu = (size_t)((1.0 - f) * (double)n_rows);
-        rows_cpu &= ~(size_t)63;  // rows_cpu * L is then a multiple of 64 floats: whole bit words, whole 64-byte lines
+        // whole tiles of 32 worlds (the fused bit form is produced per tile); rows_cpu * L is then also a multiple of 64
+        // floats: whole bit words, whole 64-byte lines
+        const size_t gran = 2 * (size_t)RW_TILE * p.n;
+        rows_cpu = rows_cpu / gran * gran;
         if (f <= 0.0 || rows_cpu > n_rows) rows_cpu = n_rows;
         if (rows_cpu * L < ((size_t)1 << 18)) rows_cpu = 0;
     }
     const size_t n_cpu = rows_cpu * L;
+    // FLATTENED rows come out of the step kernel in bit form directly (rw_obs_agent_bits): the worlds whose rows the host pool
+    // expands are stepped by one launch that writes bits + coordinate bytes, the copy engine's worlds by a second launch that
+    // writes float32 rows.  Other row types are packed from the float32 tensor by a separate small kernel.
+    static const bool allow_fused = !(getenv("RWARE_B200_HOST_FUSED") && atoi(getenv("RWARE_B200_HOST_FUSED")) == 0);
+    const bool fused = bits && rows_cpu && p.obs_kind == 0 && allow_fused &&
+                       (size_t)p.obs_buf_stride * p.obs_nbuf >= (size_t)p.n * L * 4 + 64u * p.n;
     static const bool trace = getenv("RWARE_B200_HOST_TRACE") != nullptr;  // diagnostics: where the call spends its time
     auto now_us = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
     const double t_call = now_us();
     if (n_cpu) rw_hostpool_prewake();  // parked workers wake up while the copies and the kernel are in flight
     CK(cudaMemcpyAsync(h->d_actions, actions_host, (size_t)p.E * p.n * p.A * 4, cudaMemcpyHostToDevice, st));
-    rc = rw_step(h, h->d_actions, obs_host ? h->d_obs : nullptr, h->d_reward, h->d_done, st);
-    if (rc) return rc;
     int nch = 0;
     size_t chunk_end[8] = {0};
-    const size_t bits_bytes = ((n_obs + 31) / 32) * 4, off_wide = (bits_bytes + 255) & ~(size_t)255;
+    const size_t rows_pad = (size_t)p.E_pad * p.n;  // the fused form writes whole tiles
+    const size_t bits_bytes = ((rows_pad * L + 31) / 32) * 4, off_wide = (bits_bytes + 255) & ~(size_t)255;
     const bool timed_dma = n_cpu && n_cpu < n_obs;
-    if (n_cpu) {
-        if (!h->d_pack) {
-            h->pack_bytes = n_obs + 256;  // the byte transport needs n_obs, the bit transport n_obs / 8 + 2 bytes per row
-            if (h->pack_bytes < off_wide + n_rows * 2 + 256) h->pack_bytes = off_wide + n_rows * 2 + 256;
-            CK(cudaMalloc(&h->d_pack, h->pack_bytes));
-            CK(alloc_pinned_placed((void **)&h->h_pack, h->pack_bytes, gpu_numa_node(h->device), 1.0));
-            for (auto &e : h->pack_ev) CK(cudaEventCreate(&e));
-            CK(cudaEventCreate(&h->dma_ev[0]));
-            CK(cudaEventCreate(&h->dma_ev[1]));
+    if (n_cpu && !h->d_pack) {
+        h->pack_bytes = n_obs + 256;  // the byte transport needs n_obs, the bit transport n_obs / 8 + 2 bytes per row
+        if (h->pack_bytes < off_wide + rows_pad * 2 + 256) h->pack_bytes = off_wide + rows_pad * 2 + 256;
+        CK(cudaMalloc(&h->d_pack, h->pack_bytes));
+        CK(alloc_pinned_placed((void **)&h->h_pack, h->pack_bytes, gpu_numa_node(h->device), 1.0));
+        for (auto &e : h->pack_ev) CK(cudaEventCreate(&e));
+        CK(cudaEventCreate(&h->dma_ev[0]));
+        CK(cudaEventCreate(&h->dma_ev[1]));
+    }
+    if (!h->ready) return fail(h, RW_ESTATE, "rw_step_host before rw_reset / rw_set_state");
+    if (fused) {
+        const int64_t e_cpu = (int64_t)(rows_cpu / p.n);
+        auto range = [&](int64_t env0, int64_t count) {  // the same launch for the worlds [env0, env0 + count), env0 % 32 == 0
+            RwParams q = p;
+            q.state += (size_t)(env0 / RW_TILE) * p.nw * RW_TILE;
+            q.rng += env0;  // E_pad (the stride of the generator words) stays
+            q.E = count;
+            q.tiles = (int)((count + RW_TILE - 1) / RW_TILE);
+            return q;
+        };
+        RwParams a = range(0, e_cpu);
+        a.obs_bits_out = (uint32_t *)h->d_pack;
+        a.obs_wide_out = h->d_pack + off_wide;
+        CK(rw_launch_main(RW_MODE_STEP, a, h->d_actions, nullptr, h->d_reward, h->d_done, nullptr, st));
+        if (e_cpu < p.E) {
+            RwParams b = range(e_cpu, p.E - e_cpu);
+            CK(rw_launch_main(RW_MODE_STEP, b, h->d_actions + e_cpu * p.n * p.A, h->d_obs + (size_t)e_cpu * p.n * L,
+                              h->d_reward + e_cpu * p.n, h->d_done + e_cpu, nullptr, st));
         }
+    } else {
+        rc = rw_step(h, h->d_actions, obs_host ? h->d_obs : nullptr, h->d_reward, h->d_done, st);
+        if (rc) return rc;
+    }
+    if (n_cpu) {
         // The compressed rows reach the host in a few pieces of growing size (each packed by its own small launch, so the
         // first copy starts as early as possible); the pool starts expanding when the first piece has landed.
         static const int want_chunks = getenv("RWARE_B200_HOST_CHUNKS") ? atoi(getenv("RWARE_B200_HOST_CHUNKS")) : 4;
@@ -661,7 +693,7 @@ int rw_step_host(rw_handle *h, const int32_t *actions_host, float *obs_host, flo
             if (bits) {
                 const size_t ba = a / 8, bb = (b + 7) / 8;
                 const size_t ra = a / L, rb = (b + L - 1) / L > rows_cpu ? rows_cpu : (b + L - 1) / L;
-                CK(rw_launch_pack_bits(h->d_obs, (uint32_t *)h->d_pack, h->d_pack + off_wide, a, b, (int)L, nwide, ra, rb, st));
+                if (!fused) CK(rw_launch_pack_bits(h->d_obs, (uint32_t *)h->d_pack, h->d_pack + off_wide, a, b, (int)L, nwide, ra, rb, st));
                 CK(cudaMemcpyAsync(h->h_pack + ba, h->d_pack + ba, bb - ba, cudaMemcpyDeviceToHost, st));
                 if (nwide)
                     CK(cudaMemcpyAsync(h->h_pack + off_wide + ra * nwide, h->d_pack + off_wide + ra * nwide, (rb - ra) * nwide,
@@ -735,7 +767,7 @@ int rw_step_host(rw_handle *h, const int32_t *actions_host, float *obs_host, flo
     if (trace)
         fprintf(stderr, "[rw_step_host] %s rows_cpu %zu/%zu chunks %d | enqueue %.0f first-chunk %.0f last-chunk %.0f expand-done %.0f "
                         "end %.0f us | dma %.0f us, ends at %.0f | dma_frac -> %.3f | threads %d isa %d\n",
-                !n_cpu ? "plain" : bits ? "bits" : "bytes", rows_cpu, n_rows, nch, 0.0, n_cpu ? t_first - t_call : 0.0,
+                !n_cpu ? "plain" : fused ? "bits(fused)" : bits ? "bits" : "bytes", rows_cpu, n_rows, nch, 0.0, n_cpu ? t_first - t_call : 0.0,
                 n_cpu ? t_last - t_call : 0.0, n_cpu ? t_done - t_call : 0.0, t_end - t_call, dma_us, timed_dma ? dma_end - t_call : 0.0,
                 h->dma_frac,
                 n_cpu ? rw_hostpool_threads() : 0, n_cpu ? rw_hostpool_isa() : 0);

@@ -822,24 +822,35 @@ RW_HD void rw_obs_agent(const RwParams &p, const RwLane &l, int i, float *out, i
         out[6] = d == 3 ? 1.0f : 0.0f;
         out[7] = (l.highway[y * W + x] & 1) ? 1.0f : 0.0f;  // ref:647
     }
-    // Slice s covers window cells [s*Kp, min(K, (s+1)*Kp)).  `part` varies across lanes: with two slices everything
-    // that depends on it is a select between the compile-time values of slice 0 and slice 1 (no divergence, no
-    // integer division); with more slices the cell index is computed (division by the compile-time window width).
-    const int Kp = (K + nparts - 1) / nparts;
+    // With two slices, slice 0 covers the window cells [0, Ka) and slice 1 the cells [Ka, K), Ka = rw_obs_plan's split (a
+    // compile-time constant for the fully static configurations, p.obs_split otherwise); with more slices, slice s covers
+    // [s*Kp, min(K, (s+1)*Kp)).  `part` varies across lanes: with two slices everything that depends on it is a select
+    // between the values of slice 0 and slice 1 (no divergence, no integer division).
+    int Ka = (K + 1) / 2;
+    if (nparts == 2) {
+        if constexpr (C::full_static) {
+            constexpr int Ka_static = rw_obs_plan_for(C::static_n, (2 * C::kR + 1) * (2 * C::kR + 1), 7 + C::kMB).split;
+            Ka = Ka_static;
+        } else {
+            Ka = p.obs_split;
+        }
+    }
+    const int Kp = nparts == 2 ? (Ka > K - Ka ? Ka : K - Ka) : (K + nparts - 1) / nparts;
     const bool hi = part != 0;
     const uint8_t *gc = l.g + (y * W + x);
-    float *ob = out + 8 + (nparts <= 2 ? (hi ? Kp * cellF : 0) : part * Kp * cellF);
+    float *ob = out + 8 + (nparts <= 2 ? (hi ? Ka * cellF : 0) : part * Kp * cellF);
 #pragma unroll
     for (int k = 0; k < Kp; k++) {                        // ref:628-629 window cells, rows outer, columns inner
         int dy, dx;
         bool live;
         if (nparts <= 2) {
-            const int ca = k, cb = Kp + k;                // cell index in slice 0 / slice 1 (compile time when unrolled)
-            const int dya = ca / win - r, dxa = ca % win - r;
-            const int dyb = (cb < K ? cb : K - 1) / win - r, dxb = (cb < K ? cb : K - 1) % win - r;
+            const int ca = k, cb = Ka + k;                // cell index in slice 0 / slice 1 (compile time when unrolled)
+            const int ca_c = ca < K ? ca : K - 1, cb_c = cb < K ? cb : K - 1;
+            const int dya = ca_c / win - r, dxa = ca_c % win - r;
+            const int dyb = cb_c / win - r, dxb = cb_c % win - r;
             dy = hi ? dyb : dya;
             dx = hi ? dxb : dxa;
-            live = hi ? (cb < K) : (ca < K);
+            live = hi ? (cb < K) : (nparts == 2 ? ca < Ka : ca < K);
         } else {
             const int c = part * Kp + k;
             const int cc = c < K ? c : K - 1;
@@ -867,6 +878,81 @@ RW_HD void rw_obs_agent(const RwParams &p, const RwLane &l, int i, float *out, i
             oc[6 + mb] = (gb & RW_G_REQ) ? 1.0f : 0.0f;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same row as rw_obs_agent, as BITS: every value of a flattened row is a 0/1 flag except the two coordinates, so the
+// host-buffer transport (rw_step_host) can carry a row as L bits + 2 bytes instead of L floats.  Bit k of the row is
+// "value k is non-zero" (the bits of the coordinates are left 0; the host ignores them); bits are OR-ed into `words`, a
+// zeroed bit image of the whole tile in shared memory, at bit offset row * L.  x / y go to wide[2 * row], wide[2 * row + 1].
+struct RwBitWriter {
+    uint32_t *words;
+    uint32_t w;
+    uint64_t acc;
+    int nacc;
+};
+RW_HD void rw_bw_or(uint32_t *addr, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    if (v) atomicOr(addr, v);  // rows of different lanes share the words at their boundaries
+#else
+    *addr |= v;
+#endif
+}
+RW_HD void rw_bw_init(RwBitWriter &b, uint32_t *words, uint32_t bitpos) {
+    b.words = words; b.w = bitpos >> 5; b.nacc = (int)(bitpos & 31u); b.acc = 0;
+}
+RW_HD void rw_bw_put(RwBitWriter &b, uint32_t value, int nbits) {  // nbits <= 32
+    b.acc |= (uint64_t)value << b.nacc;
+    b.nacc += nbits;
+    if (b.nacc >= 32) {
+        rw_bw_or(b.words + b.w, (uint32_t)b.acc);
+        b.w++;
+        b.acc >>= 32;
+        b.nacc -= 32;
+    }
+}
+RW_HD void rw_bw_flush(RwBitWriter &b) {
+    if (b.nacc > 0) rw_bw_or(b.words + b.w, (uint32_t)b.acc);
+}
+
+template <class C>
+RW_HD void rw_obs_agent_bits(const RwParams &p, const RwLane &l, int i, uint32_t row, uint32_t *words, uint8_t *wide, int part,
+                             int nparts) {
+    const RwOff o = rw_off<C>(p);
+    const uint32_t aw = rw_agent(l, i);
+    const int x = rw_ax(aw), y = rw_ay(aw);
+    const int W = C::W(p), H = C::H(p);
+    const int r = C::r(p), mb = C::mb(p), win = 2 * r + 1, K = win * win, cellF = 7 + mb;
+    const int L = 8 + K * cellF;
+    const int Kp = (K + nparts - 1) / nparts;
+    RwBitWriter bw;
+    if (part == 0) {
+        wide[2 * row] = (uint8_t)x;
+        wide[2 * row + 1] = (uint8_t)y;
+        rw_bw_init(bw, words, row * (uint32_t)L);
+        const uint32_t d = (uint32_t)rw_adir(aw);
+        rw_bw_put(bw, (rw_acarry(aw) ? 4u : 0u) | (8u << d) | ((l.highway[y * W + x] & 1) ? 128u : 0u), 8);  // ref:636-647
+    } else {
+        rw_bw_init(bw, words, row * (uint32_t)L + 8u + (uint32_t)(part * Kp * cellF));
+    }
+    const uint8_t *gc = l.g + (y * W + x);
+    int c = part * Kp;
+    int dy = c / win - r, dx = c - (c / win) * win - r;
+    for (int k = 0; k < Kp && c < K; k++, c++) {  // ref:628-629 window cells, rows outer, columns inner
+        uint32_t gb = 0;                           // zero padding outside the map (ref:606-626)
+        if ((unsigned)(y + dy) < (unsigned)H && (unsigned)(x + dx) < (unsigned)W) gb = gc[dy * W + dx];
+        const uint32_t ida = gb & RW_G_AGENT;
+        uint32_t od = 0, bits = 0;
+        if (ida) {
+            od = (uint32_t)rw_adir(rw_agent(l, (int)ida - 1));
+            if (mb) bits = (uint32_t)l.tile[(o.w_msg + (int)ida - 1) * RW_TILE];
+        }
+        // ref:656-673: has_agent, direction one-hot (an empty cell reads [1,0,0,0]), message bits, has_shelf, requested
+        rw_bw_put(bw, (ida ? 1u : 0u) | (2u << od) | (bits << 5) | ((gb & RW_G_SHELF) ? (1u << (5 + mb)) : 0u) |
+                          ((gb & RW_G_REQ) ? (1u << (6 + mb)) : 0u), cellF);
+        if (++dx > r) { dx = -r; dy++; }
+    }
+    rw_bw_flush(bw);
 }
 
 // ------------------------------------------------------------------------------------------------

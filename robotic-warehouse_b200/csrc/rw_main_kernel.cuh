@@ -75,6 +75,41 @@ __device__ __forceinline__ unsigned long long rw_gtime() {
 
 __device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
+// ---- 4'. bit form of a tile's rows for the host-buffer transport (rw_step_host): both warps of the pair OR their rows' bits
+//      into a zeroed bit image of the tile (n * L words + 64 n coordinate bytes, in the staging area), which leaves with
+//      coalesced stores.  Kept out of line so that the float path of the kernel does not pay for it in registers.
+template <class C>
+__device__ __noinline__ void rw_tile_bits(const RwParams &p, uint8_t *wb, int32_t *tilew, uint8_t *grid, const uint8_t *s_highway,
+                                          const uint16_t *s_home_id, int tile, int tl, int role, int lane) {
+    const int n = p.n, L = p.L, P = p.obs_parts;
+    const int64_t tile_env0 = (int64_t)tile * RW_TILE;
+    uint32_t *sb = reinterpret_cast<uint32_t *>(wb + p.sm_obs);
+    uint8_t *sw = reinterpret_cast<uint8_t *>(sb + n * L);
+    for (int i = role * 32 + lane; i < n * L; i += 64) sb[i] = 0;
+    pair_barrier(1 + tl);
+    const int items = RW_TILE * n * P;
+    for (int it = role * 32 + lane; it < items; it += 64) {
+        const int part = P == 1 ? 0 : (P == 2 ? (it & 1) : (it & 3));
+        const int ea = P == 1 ? it : (P == 2 ? (it >> 1) : (it >> 2));
+        const int e = (int)rw_div((uint32_t)ea, p.divN);
+        RwLane le;
+        le.tile = tilew + e;
+        le.g = grid + e * p.grid_env_stride;
+        le.sc = nullptr;
+        le.sc_step = 0;
+        le.highway = s_highway;
+        le.home_id = s_home_id;
+        if (tile_env0 + e < p.E) rw_obs_agent_bits<C>(p, le, ea - e * n, (uint32_t)ea, sb, sw, part, P);
+        else if (part == 0) { sw[2 * ea] = 0; sw[2 * ea + 1] = 0; }
+    }
+    pair_barrier(1 + tl);
+    uint32_t *gb = p.obs_bits_out + (size_t)tile * n * L;
+    for (int i = role * 32 + lane; i < n * L; i += 64) gb[i] = sb[i];
+    uint32_t *gw = reinterpret_cast<uint32_t *>(p.obs_wide_out + (size_t)tile * RW_TILE * n * 2);
+    const uint32_t *sw32 = reinterpret_cast<const uint32_t *>(sw);
+    for (int i = role * 32 + lane; i < RW_TILE * n / 2; i += 64) gw[i] = sw32[i];
+}
+
 // Two warps serve one tile.  The PRIMARY warp (even) runs the per-world logic, one lane per world.  The HELPER warp
 // (odd) zeroes the grids, then sleeps on a named barrier until the post-step state is in shared memory; after that
 // both warps run the observation gather on alternate chunks, each with its own staging buffer and its own TMA bulk
@@ -171,6 +206,8 @@ __global__ void __launch_bounds__(MAXT, 1) rw_main_kernel(const __grid_constant_
             __syncwarp();
             stores_in_flight = nbw - 1;
         }
+        // rows of world el of the chunk start at word el * n * L + (el / G) * padw of the staging buffer (rw_obs_plan)
+        const int G = p.obs_pad_group, padw = p.obs_pad_words;
         for (int it = lane; it < items; it += 32) {
             const int part = P == 4 ? (it & 3) : P == 2 ? (it & 1) : 0;
             const int ea = P == 4 ? (it >> 2) : P == 2 ? (it >> 1) : it;  // (world, agent) row inside the chunk
@@ -184,9 +221,10 @@ __global__ void __launch_bounds__(MAXT, 1) rw_main_kernel(const __grid_constant_
                 le.sc_step = 0;
                 le.highway = s_highway;
                 le.home_id = s_home_id;
-                if (P == 4) rw_obs_row<C, 4>(p, le, ea - el * n, buf + ea * L, part);
-                else if (P == 2) rw_obs_row<C, 2>(p, le, ea - el * n, buf + ea * L, part);
-                else rw_obs_row<C, 1>(p, le, ea - el * n, buf + ea * L, 0);
+                float *row = buf + ea * L + (padw ? (G == 1 ? el : el / G) * padw : 0);
+                if (P == 4) rw_obs_row<C, 4>(p, le, ea - el * n, row, part);
+                else if (P == 2) rw_obs_row<C, 2>(p, le, ea - el * n, row, part);
+                else rw_obs_row<C, 1>(p, le, ea - el * n, row, 0);
             }
         }
         // destinations: the caller's tensor, or (fused push all-gather) this rank's slot of every rank's gathered tensor,
@@ -197,22 +235,29 @@ __global__ void __launch_bounds__(MAXT, 1) rw_main_kernel(const __grid_constant_
                 return p.peer_obs[(p.my_rank + d) % p.n_peers] + (size_t)(p.gather_env0 + tile_env0 + c0) * n * L;
             return obs + (tile_env0 + c0) * n * L;
         };
+        const int ngroups = padw ? CH / G : 1;              // pieces of the staged chunk, each contiguous in shared memory
+        const int gwords = padw ? G * n * L : CH * n * L;   // words per piece
         if (fast && p.obs_tma) {
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-                for (int d = 0; d < ndst; d++) bulk_s2g(dst_ptr(d), buf, (uint32_t)p.obs_chunk_bytes);
+                for (int d = 0; d < ndst; d++) {
+                    float *dst = dst_ptr(d);
+                    for (int g = 0; g < ngroups; g++) bulk_s2g(dst + g * gwords, buf + g * (gwords + padw), (uint32_t)gwords * 4u);
+                }
                 bulk_commit();
             }
             stores_in_flight++;
         } else if (fast) {  // 16-byte coalesced stores: 512 B per warp instruction
             __syncwarp();
-            const int4 *src = reinterpret_cast<const int4 *>(buf);
-            const int n16 = p.obs_chunk_bytes >> 4;
+            const int n16 = gwords >> 2;
             for (int d = 0; d < ndst; d++) {
-                int4 *dst = reinterpret_cast<int4 *>(dst_ptr(d));
+                for (int g = 0; g < ngroups; g++) {
+                    const int4 *src = reinterpret_cast<const int4 *>(buf + g * (gwords + padw));
+                    int4 *dst = reinterpret_cast<int4 *>(dst_ptr(d) + g * gwords);
 #pragma unroll 4
-                for (int i = lane; i < n16; i += 32) __stcs(dst + i, src[i]);
+                    for (int i = lane; i < n16; i += 32) __stcs(dst + i, src[i]);
+                }
             }
             __syncwarp();
         } else {  // ragged tail / unaligned geometry: plain coalesced stores
@@ -223,7 +268,7 @@ __global__ void __launch_bounds__(MAXT, 1) rw_main_kernel(const __grid_constant_
             const int nf = (int)(envs_here > 0 ? envs_here : 0) * n * L;
             for (int d = 0; d < ndst; d++) {
                 float *gdst = dst_ptr(d);
-                for (int i = lane; i < nf; i += 32) gdst[i] = buf[i];
+                for (int i = lane; i < nf; i += 32) gdst[i] = buf[i + (padw ? (i / (G * n * L)) * padw : 0)];
             }
             __syncwarp();
         }
@@ -293,13 +338,18 @@ __global__ void __launch_bounds__(MAXT, 1) rw_main_kernel(const __grid_constant_
             bulk_commit();
         }
     }
-    if (obs != nullptr && !interleave) {
+    const bool want_bits = p.obs_bits_out != nullptr;
+    if ((obs != nullptr || want_bits) && !interleave) {
         if (!coop) {
             pair_barrier(1 + tl);  // post-step tile + grids are visible to the helper
             RW_STAMP(4);
         }
-        // ---- 4. observation gather after the fact: this warp takes every second chunk
-        for (int c0 = role * CH; c0 < RW_TILE; c0 += 2 * CH) emit_chunk(c0);
+        if (want_bits) {
+            rw_tile_bits<C>(p, wb, tilew, grid, s_highway, s_home_id, tile, tl, role, lane);
+        } else {
+            // ---- 4. observation gather after the fact: this warp takes every second chunk
+            for (int c0 = role * CH; c0 < RW_TILE; c0 += 2 * CH) emit_chunk(c0);
+        }
     }
     if (MODE == RW_MODE_STEP && p.n_peers > 1 && role == 1) {
         // rewards / done of this tile -> every peer's gathered tensors (the primary wrote the local copy; the pair
