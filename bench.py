@@ -621,11 +621,17 @@ def main():
     b_step = int(info["algorithmic_bytes_step"])
     b_packed = int(info["packed_bytes_step"])
     achieved = b_step * E / (kernel_ms * 1e-3) / 1e9
-    traffic = None
-    prof = os.path.join(ROOT, "profiles", "ncu_step_traffic.json")
-    if os.path.exists(prof) and args.workload == "tiny-4ag" and E == 65536:
+    # dram__bytes_read + dram__bytes_write per launch: not measurable from inside this process -- taken from the committed ncu
+    # capture of this same rotating loop (profiles/r2_step_traffic.json: one pass per launch, caches untouched, launches 60..75)
+    traffic, traffic_source = None, None
+    prof = os.path.join(ROOT, "profiles", "r2_step_traffic.json")
+    if os.path.exists(prof) and args.workload == "tiny-4ag" and E == 65536 and args.l2 == "rotate":
         with open(prof) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            rec = json.load(f)
+        traffic = rec.get("dram_bytes_per_launch")
+        traffic_source = ("profiles/r2_step_traffic.json: ncu --cache-control none, launches 60..75 of this bench loop (steady state, "
+                          f"read {rec.get('dram_bytes_read_per_launch', 0) / 1e6:.1f} MB + write {rec.get('dram_bytes_write_per_launch', 0) / 1e6:.1f} MB "
+                          "per launch); a file value, not measured in this run")
     cb = None
     if not args.no_cpu_baseline:
         cb = cpu_baseline(env_id, overrides, target_seconds=12.0, n_worlds=E)
@@ -648,8 +654,11 @@ def main():
                               "none": "one CUDA event pair around the K back-to-back launches; max over ranks"}[args.l2]},
         "agent_steps_per_s": world * E * n * args.steps / (total_ms * 1e-3),
         "value_single_set_l2_resident": world * E * args.steps / (warm_ms * 1e-3),
+        "sequential_rollout_of_one_world_set": {"value": world * E * args.steps / (warm_ms * 1e-3), "ms_per_step": warm_ms / args.steps,
+                                                "note": "ONE world set stepped back to back on one stream (step k+1 needs step k's state: the "
+                                                        "launches serialise, no overlap across launches; its 83 MB working set stays in the L2)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "rw_main_kernel<STEP>",
+                     "traffic": traffic, "traffic_source": traffic_source, "peak_source": peak_src, "kernel": "rw_main_kernel<STEP>",
                      "algorithmic_bytes_per_env_step": b_step, "layout_bytes_per_env_step": b_packed,
                      "achieved_layout_bytes": b_packed * E / (kernel_ms * 1e-3) / 1e9,
                      "kernel_us": kernel_ms * 1e3},

@@ -26,6 +26,30 @@
 #include "rw_views.cuh"
 
 #define RW_DMA_FRAC0 0.15
+
+// What one rw_step_host call does on the device side, decided before anything is enqueued
+struct HostPlan {
+    const int32_t *actions_host;
+    float *obs_host, *reward_host;
+    uint8_t *done_host;
+    size_t rows_cpu;   // observation rows (world-major) the host pool expands; the rest is delivered by the copy engine
+    bool bits, fused;  // bit transport (else bytes); bit form written by the step kernel itself (else packed from float rows)
+    int nwide, nch;
+    size_t chunk_end[8];
+    size_t off_wide;
+    int64_t epoch;
+    bool same(const HostPlan &o) const {
+        return actions_host == o.actions_host && obs_host == o.obs_host && reward_host == o.reward_host && done_host == o.done_host &&
+               rows_cpu == o.rows_cpu && bits == o.bits && fused == o.fused && nch == o.nch && epoch == o.epoch;
+    }
+};
+
+struct HostGraph {
+    HostPlan plan;
+    cudaGraphExec_t exec = nullptr;
+    int64_t last_use = 0;
+};
+
 #define RW_HOST_LOCAL_TAIL 0.25  // share of a buffer from rw_host_alloc_near that stays on the GPU's NUMA node (the copy engine's rows)
 
 struct rw_handle {
@@ -45,8 +69,12 @@ struct rw_handle {
     uint8_t *d_pack = nullptr, *h_pack = nullptr;
     size_t pack_bytes = 0;
     cudaEvent_t pack_ev[8] = {};
-    cudaEvent_t dma_ev[2] = {}, kernel_ev = nullptr;
-    cudaStream_t dma_stream = nullptr;
+    cudaEvent_t dma_ev[2] = {};
+    uint32_t *d_flag_ctr = nullptr;            // device counters behind the host-visible flags
+    volatile uint32_t *h_flags = nullptr;      // mapped host memory, one flag per 64-byte line: piece c -> h_flags[16 c], copy engine -> [16 * 8]
+    uint32_t flag_seen[16] = {};
+    struct HostGraph graphs[6];
+    int64_t host_calls_graph = 0, host_epoch = 0;  // epoch: bumped by whatever changes what the captured launches would do
     int host_pack = 1;  // 0 plain float32 copy, 1 compressed (bits where the rows allow it, else bytes), 2 compressed, bytes only
     // share of the observation rows that the copy engine delivers as plain float32 while the host pool expands the rest;
     // follows the measured rates of the two unless fixed (rw_set_host_dma_share / RWARE_B200_HOST_DMA_SHARE)
@@ -239,8 +267,9 @@ int rw_destroy(rw_handle *h) {
         free_pinned(h->h_pack);
         for (auto &e : h->pack_ev) if (e) cudaEventDestroy(e);
         for (auto &e : h->dma_ev) if (e) cudaEventDestroy(e);
-        if (h->kernel_ev) cudaEventDestroy(h->kernel_ev);
-        if (h->dma_stream) cudaStreamDestroy(h->dma_stream);
+        for (auto &g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+        cudaFree(h->d_flag_ctr);
+        if (h->h_flags) cudaFreeHost((void *)h->h_flags);
     }
     cudaFree(h->d_highway); cudaFree(h->d_home); cudaFree(h->d_home_id); cudaFree(h->d_cta_tables); cudaFree(h->d_normx); cudaFree(h->d_normy);
     cudaFree(h->d_state); cudaFree(h->d_rng); cudaFree(h->d_err);
@@ -262,12 +291,14 @@ int rw_get_info(const rw_handle *h, rw_info *out) {
 int rw_debug_set_clock_buffer(rw_handle *h, void *dev_ptr) {  // diagnostics: [CTA][32][8] uint64 phase timestamps
     if (!h) return RW_EINVAL;
     h->p.dbg_clock = (unsigned long long *)dev_ptr;
+    h->host_epoch++;
     return RW_OK;
 }
 
 int rw_set_auto_reset(rw_handle *h, int enabled) {
     if (!h) return RW_EINVAL;
     h->p.auto_reset = enabled ? 1 : 0;
+    h->host_epoch++;
     return RW_OK;
 }
 
@@ -589,66 +620,15 @@ static int ensure_host_staging(rw_handle *h) {
     return RW_OK;
 }
 
-extern "C" {
-
-int rw_step_host(rw_handle *h, const int32_t *actions_host, float *obs_host, float *reward_host, uint8_t *done_host) {
-    if (!h || !actions_host) return RW_EINVAL;
-    int rc = ensure_host_staging(h);
-    if (rc) return rc;
+// Everything one call puts on the stream: actions in, the step (one or two launches), the compressed rows out in pieces of
+// growing size (each followed by a flag the host can see), rewards / done, and the copy engine's share of the float32 rows.
+static int enqueue_step_host(rw_handle *h, const HostPlan &pl, bool pdl_ok) {
     const RwParams &p = h->p;
     cudaStream_t st = h->host_stream;
-    const size_t n_rows = (size_t)p.E * p.n, L = (size_t)p.L, n_obs = n_rows * L;
-    // What the caller gets is float32 rows in host memory.  The plain way is one device-to-host copy of them (PCIe bound).
-    // Unless the coordinates are normalised every value is a small integer, and in large batches the rows travel compressed
-    // and are expanded by the host pool (rw_hostpack.cpp): one BIT per value plus one byte per coordinate when everything
-    // else is a 0/1 flag (FLATTENED rows; image rows without the AGENT_DIRECTION layer), one BYTE per value otherwise.  The
-    // expansion is bound by host DRAM writes, so the copy engine delivers a share of the rows as plain float32 at the same
-    // time; the share follows the measured rates of the two (dma_frac).
-    bool has_dir_layer = false;
-    for (int i = 0; i < p.n_layers; i++) has_dir_layer |= (p.obs_kind != 0 && p.img_layers[i] == RW_LAYER_AGENT_DIRECTION);
-    const bool compress = obs_host && h->host_pack != 0 && !p.norm_coords && n_obs >= ((size_t)1 << 20);
-    const bool bits = compress && h->host_pack == 1 && !has_dir_layer && (reinterpret_cast<uintptr_t>(obs_host) & 63u) == 0;
-    const int nwide = p.obs_kind == 0 ? 2 : 0;
-    size_t rows_cpu = 0;
-    if (compress) {
-        const double f = h->dma_frac_fixed >= 0 ? h->dma_frac_fixed : h->dma_frac;
-        rows_cpu = (size_t)((1.0 - f) * (double)n_rows);
-        // whole tiles of 32 worlds (the fused bit form is produced per tile); rows_cpu * L is then also a multiple of 64
-        // floats: whole bit words, whole 64-byte lines
-        const size_t gran = 2 * (size_t)RW_TILE * p.n;
-        rows_cpu = rows_cpu / gran * gran;
-        if (f <= 0.0 || rows_cpu > n_rows) rows_cpu = n_rows;
-        if (rows_cpu * L < ((size_t)1 << 18)) rows_cpu = 0;
-    }
-    const size_t n_cpu = rows_cpu * L;
-    // FLATTENED rows come out of the step kernel in bit form directly (rw_obs_agent_bits): the worlds whose rows the host pool
-    // expands are stepped by one launch that writes bits + coordinate bytes, the copy engine's worlds by a second launch that
-    // writes float32 rows.  Other row types are packed from the float32 tensor by a separate small kernel.
-    static const bool allow_fused = !(getenv("RWARE_B200_HOST_FUSED") && atoi(getenv("RWARE_B200_HOST_FUSED")) == 0);
-    const bool fused = bits && rows_cpu && p.obs_kind == 0 && allow_fused &&
-                       (size_t)p.obs_buf_stride * p.obs_nbuf >= (size_t)p.n * L * 4 + 64u * p.n;
-    static const bool trace = getenv("RWARE_B200_HOST_TRACE") != nullptr;  // diagnostics: where the call spends its time
-    auto now_us = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
-    const double t_call = now_us();
-    if (n_cpu) rw_hostpool_prewake();  // parked workers wake up while the copies and the kernel are in flight
-    CK(cudaMemcpyAsync(h->d_actions, actions_host, (size_t)p.E * p.n * p.A * 4, cudaMemcpyHostToDevice, st));
-    int nch = 0;
-    size_t chunk_end[8] = {0};
-    const size_t rows_pad = (size_t)p.E_pad * p.n;  // the fused form writes whole tiles
-    const size_t bits_bytes = ((rows_pad * L + 31) / 32) * 4, off_wide = (bits_bytes + 255) & ~(size_t)255;
-    const bool timed_dma = n_cpu && n_cpu < n_obs;
-    if (n_cpu && !h->d_pack) {
-        h->pack_bytes = n_obs + 256;  // the byte transport needs n_obs, the bit transport n_obs / 8 + 2 bytes per row
-        if (h->pack_bytes < off_wide + rows_pad * 2 + 256) h->pack_bytes = off_wide + rows_pad * 2 + 256;
-        CK(cudaMalloc(&h->d_pack, h->pack_bytes));
-        CK(alloc_pinned_placed((void **)&h->h_pack, h->pack_bytes, gpu_numa_node(h->device), 1.0));
-        for (auto &e : h->pack_ev) CK(cudaEventCreate(&e));
-        CK(cudaEventCreate(&h->dma_ev[0]));
-        CK(cudaEventCreate(&h->dma_ev[1]));
-    }
-    if (!h->ready) return fail(h, RW_ESTATE, "rw_step_host before rw_reset / rw_set_state");
-    if (fused) {
-        const int64_t e_cpu = (int64_t)(rows_cpu / p.n);
+    const size_t n_rows = (size_t)p.E * p.n, L = (size_t)p.L, n_obs = n_rows * L, n_cpu = pl.rows_cpu * L;
+    CK(cudaMemcpyAsync(h->d_actions, pl.actions_host, (size_t)p.E * p.n * p.A * 4, cudaMemcpyHostToDevice, st));
+    if (pl.fused) {
+        const int64_t e_cpu = (int64_t)(pl.rows_cpu / p.n);
         auto range = [&](int64_t env0, int64_t count) {  // the same launch for the worlds [env0, env0 + count), env0 % 32 == 0
             RwParams q = p;
             q.state += (size_t)(env0 / RW_TILE) * p.nw * RW_TILE;
@@ -659,98 +639,224 @@ int rw_step_host(rw_handle *h, const int32_t *actions_host, float *obs_host, flo
         };
         RwParams a = range(0, e_cpu);
         a.obs_bits_out = (uint32_t *)h->d_pack;
-        a.obs_wide_out = h->d_pack + off_wide;
-        CK(rw_launch_main(RW_MODE_STEP, a, h->d_actions, nullptr, h->d_reward, h->d_done, nullptr, st));
+        a.obs_wide_out = h->d_pack + pl.off_wide;
+        CK(rw_launch_main(RW_MODE_STEP, a, h->d_actions, nullptr, h->d_reward, h->d_done, nullptr, st, pdl_ok));
         if (e_cpu < p.E) {
             RwParams b = range(e_cpu, p.E - e_cpu);
             CK(rw_launch_main(RW_MODE_STEP, b, h->d_actions + e_cpu * p.n * p.A, h->d_obs + (size_t)e_cpu * p.n * L,
-                              h->d_reward + e_cpu * p.n, h->d_done + e_cpu, nullptr, st));
+                              h->d_reward + e_cpu * p.n, h->d_done + e_cpu, nullptr, st, pdl_ok));
         }
     } else {
-        rc = rw_step(h, h->d_actions, obs_host ? h->d_obs : nullptr, h->d_reward, h->d_done, st);
-        if (rc) return rc;
+        CK(rw_launch_main(RW_MODE_STEP, p, h->d_actions, pl.obs_host ? h->d_obs : nullptr, h->d_reward, h->d_done, nullptr, st, pdl_ok));
+    }
+    for (int c = 0; c < pl.nch; c++) {
+        const size_t a = (c ? pl.chunk_end[c - 1] : 0) * RW_HOST_BLOCK;
+        const size_t b = pl.chunk_end[c] * RW_HOST_BLOCK > n_cpu ? n_cpu : pl.chunk_end[c] * RW_HOST_BLOCK;
+        if (pl.bits) {
+            const size_t ba = a / 8, bb = (b + 7) / 8;
+            const size_t ra = a / L, rb = (b + L - 1) / L > pl.rows_cpu ? pl.rows_cpu : (b + L - 1) / L;
+            if (!pl.fused)
+                CK(rw_launch_pack_bits(h->d_obs, (uint32_t *)h->d_pack, h->d_pack + pl.off_wide, a, b, (int)L, pl.nwide, ra, rb, st));
+            CK(cudaMemcpyAsync(h->h_pack + ba, h->d_pack + ba, bb - ba, cudaMemcpyDeviceToHost, st));
+            if (pl.nwide)
+                CK(cudaMemcpyAsync(h->h_pack + pl.off_wide + ra * pl.nwide, h->d_pack + pl.off_wide + ra * pl.nwide,
+                                   (rb - ra) * pl.nwide, cudaMemcpyDeviceToHost, st));
+        } else {
+            CK(rw_launch_pack_u8(h->d_obs + a, h->d_pack + a, b - a, st));
+            CK(cudaMemcpyAsync(h->h_pack + a, h->d_pack + a, b - a, cudaMemcpyDeviceToHost, st));
+        }
+        if (c == 0) CK(cudaEventRecord(h->pack_ev[0], st));  // timing only (read after the stream is idle)
+        CK(rw_launch_host_flag(h->d_flag_ctr + c, h->h_flags + 16 * c, st));
+    }
+    if (pl.reward_host) CK(cudaMemcpyAsync(pl.reward_host, h->d_reward, (size_t)p.E * p.n * 4, cudaMemcpyDeviceToHost, st));
+    if (pl.done_host) CK(cudaMemcpyAsync(pl.done_host, h->d_done, (size_t)p.E, cudaMemcpyDeviceToHost, st));
+    if (pl.obs_host && n_cpu < n_obs) {  // the copy engine's share (everything, for the plain transport).  Device-to-host copies
+        // of different streams do not overlap on this hardware, so it simply follows the compressed pieces on the same stream.
+        if (n_cpu) CK(cudaEventRecord(h->dma_ev[0], st));
+        CK(cudaMemcpyAsync(pl.obs_host + n_cpu, h->d_obs + n_cpu, (n_obs - n_cpu) * 4, cudaMemcpyDeviceToHost, st));
+        if (n_cpu) {
+            CK(cudaEventRecord(h->dma_ev[1], st));
+            CK(rw_launch_host_flag(h->d_flag_ctr + 8, h->h_flags + 16 * 8, st));
+        }
+    }
+    return RW_OK;
+}
+
+extern "C" {
+
+int rw_step_host(rw_handle *h, const int32_t *actions_host, float *obs_host, float *reward_host, uint8_t *done_host) {
+    if (!h || !actions_host) return RW_EINVAL;
+    int rc = ensure_host_staging(h);
+    if (rc) return rc;
+    if (!h->ready) return fail(h, RW_ESTATE, "rw_step_host before rw_reset / rw_set_state");
+    const RwParams &p = h->p;
+    cudaStream_t st = h->host_stream;
+    const size_t n_rows = (size_t)p.E * p.n, L = (size_t)p.L, n_obs = n_rows * L;
+    // What the caller gets is float32 rows in host memory.  The plain way is one device-to-host copy of them (PCIe bound).
+    // Unless the coordinates are normalised every value is a small integer, and in large batches the rows travel compressed
+    // and are expanded by the host pool (rw_hostpack.cpp): one BIT per value plus one byte per coordinate when everything
+    // else is a 0/1 flag (FLATTENED rows; image rows without the AGENT_DIRECTION layer), one BYTE per value otherwise.  The
+    // expansion is bound by host DRAM writes, so the copy engine delivers a share of the rows as plain float32 at the same
+    // time; the share follows the measured finish times of the two (dma_frac).
+    bool has_dir_layer = false;
+    for (int i = 0; i < p.n_layers; i++) has_dir_layer |= (p.obs_kind != 0 && p.img_layers[i] == RW_LAYER_AGENT_DIRECTION);
+    const bool compress = obs_host && h->host_pack != 0 && !p.norm_coords && n_obs >= ((size_t)1 << 20);
+    HostPlan pl;
+    memset(&pl, 0, sizeof(pl));
+    pl.actions_host = actions_host; pl.obs_host = obs_host; pl.reward_host = reward_host; pl.done_host = done_host;
+    pl.bits = compress && h->host_pack == 1 && !has_dir_layer && (reinterpret_cast<uintptr_t>(obs_host) & 63u) == 0;
+    pl.nwide = p.obs_kind == 0 ? 2 : 0;
+    pl.epoch = h->host_epoch;
+    if (compress) {
+        const double f = h->dma_frac_fixed >= 0 ? h->dma_frac_fixed : h->dma_frac;
+        // whole tiles of 32 worlds (the fused bit form is produced per tile); in steps of 1/64 of the batch so that the
+        // self-adjusting share settles on a handful of distinct plans (each plan has its own CUDA graph)
+        size_t gran = 2 * (size_t)RW_TILE * p.n;
+        const size_t coarse = n_rows / 64 / gran * gran;
+        if (coarse > gran) gran = coarse;
+        pl.rows_cpu = (size_t)((1.0 - f) * (double)n_rows) / gran * gran;
+        if (f <= 0.0 || pl.rows_cpu > n_rows) pl.rows_cpu = n_rows;
+        if (pl.rows_cpu * L < ((size_t)1 << 18)) pl.rows_cpu = 0;
+    }
+    const size_t n_cpu = pl.rows_cpu * L;
+    // FLATTENED rows come out of the step kernel in bit form directly (rw_obs_agent_bits): the worlds whose rows the host pool
+    // expands are stepped by one launch that writes bits + coordinate bytes, the copy engine's worlds by a second launch that
+    // writes float32 rows.  Other row types are packed from the float32 tensor by a separate small kernel.
+    static const bool allow_fused = !(getenv("RWARE_B200_HOST_FUSED") && atoi(getenv("RWARE_B200_HOST_FUSED")) == 0);
+    pl.fused = pl.bits && pl.rows_cpu && p.obs_kind == 0 && allow_fused &&
+               (size_t)p.obs_buf_stride * p.obs_nbuf >= (size_t)p.n * L * 4 + 64u * p.n;
+    const size_t rows_pad = (size_t)p.E_pad * p.n;  // the fused form writes whole tiles
+    const size_t bits_bytes = ((rows_pad * L + 31) / 32) * 4;
+    pl.off_wide = (bits_bytes + 255) & ~(size_t)255;
+    if (!h->d_pack) {
+        h->pack_bytes = n_obs + 256;  // the byte transport needs n_obs, the bit transport n_obs / 8 + 2 bytes per row
+        if (h->pack_bytes < pl.off_wide + rows_pad * 2 + 256) h->pack_bytes = pl.off_wide + rows_pad * 2 + 256;
+        CK(cudaMalloc(&h->d_pack, h->pack_bytes));
+        CK(alloc_pinned_placed((void **)&h->h_pack, h->pack_bytes, gpu_numa_node(h->device), 1.0));
+        for (auto &e : h->pack_ev) CK(cudaEventCreate(&e));
+        CK(cudaEventCreate(&h->dma_ev[0]));
+        CK(cudaEventCreate(&h->dma_ev[1]));
+        CK(cudaMalloc((void **)&h->d_flag_ctr, 16 * 4));
+        CK(cudaMemset(h->d_flag_ctr, 0, 16 * 4));
+        CK(cudaHostAlloc((void **)&h->h_flags, 16 * 64, cudaHostAllocMapped | cudaHostAllocPortable));
+        memset((void *)h->h_flags, 0, 16 * 64);
+        memset(h->flag_seen, 0, sizeof(h->flag_seen));
     }
     if (n_cpu) {
-        // The compressed rows reach the host in a few pieces of growing size (each packed by its own small launch, so the
-        // first copy starts as early as possible); the pool starts expanding when the first piece has landed.
+        // The compressed rows reach the host in a few pieces of growing size (sizes 1 : 2 : 3 : ...); the pool starts expanding
+        // when the first piece has landed.
         static const int want_chunks = getenv("RWARE_B200_HOST_CHUNKS") ? atoi(getenv("RWARE_B200_HOST_CHUNKS")) : 4;
         const size_t nblocks = (n_cpu + RW_HOST_BLOCK - 1) / RW_HOST_BLOCK;
-        nch = want_chunks < 1 ? 1 : (want_chunks > 8 ? 8 : want_chunks);
+        int nch = want_chunks < 1 ? 1 : (want_chunks > 8 ? 8 : want_chunks);
         if ((size_t)nch > nblocks) nch = (int)nblocks;
-        {   // piece c ends at block nblocks * (c + 1) * (c + 2) / (nch * (nch + 1)): sizes 1 : 2 : 3 : ...
-            size_t prev = 0;
-            int k = 0;
-            for (int c = 0; c < nch; c++) {
-                size_t end = c + 1 == nch ? nblocks : nblocks * (size_t)(c + 1) * (c + 2) / ((size_t)nch * (nch + 1));
-                if (end <= prev) continue;
-                chunk_end[k++] = end;
-                prev = end;
-            }
-            nch = k;
-        }
+        size_t prev = 0;
+        int k = 0;
         for (int c = 0; c < nch; c++) {
-            const size_t a = (c ? chunk_end[c - 1] : 0) * RW_HOST_BLOCK, b = chunk_end[c] * RW_HOST_BLOCK > n_cpu ? n_cpu : chunk_end[c] * RW_HOST_BLOCK;
-            if (bits) {
-                const size_t ba = a / 8, bb = (b + 7) / 8;
-                const size_t ra = a / L, rb = (b + L - 1) / L > rows_cpu ? rows_cpu : (b + L - 1) / L;
-                if (!fused) CK(rw_launch_pack_bits(h->d_obs, (uint32_t *)h->d_pack, h->d_pack + off_wide, a, b, (int)L, nwide, ra, rb, st));
-                CK(cudaMemcpyAsync(h->h_pack + ba, h->d_pack + ba, bb - ba, cudaMemcpyDeviceToHost, st));
-                if (nwide)
-                    CK(cudaMemcpyAsync(h->h_pack + off_wide + ra * nwide, h->d_pack + off_wide + ra * nwide, (rb - ra) * nwide,
-                                       cudaMemcpyDeviceToHost, st));
+            size_t end = c + 1 == nch ? nblocks : nblocks * (size_t)(c + 1) * (c + 2) / ((size_t)nch * (nch + 1));
+            if (end <= prev) continue;
+            pl.chunk_end[k++] = end;
+            prev = end;
+        }
+        pl.nch = k;
+    }
+    const bool timed_dma = n_cpu && n_cpu < n_obs;
+    static const bool trace = getenv("RWARE_B200_HOST_TRACE") != nullptr;  // diagnostics: where the call spends its time
+    static const bool use_graph = !(getenv("RWARE_B200_HOST_GRAPH") && atoi(getenv("RWARE_B200_HOST_GRAPH")) == 0);
+    auto now_us = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
+    const double t_call = now_us();
+    if (n_cpu) rw_hostpool_prewake();  // parked workers wake up while the copies and the kernel are in flight
+    // The ~20 stream operations of a call cost more host time than the GPU needs to execute the first of them, so a plan is
+    // captured into a CUDA graph the first time it is seen and replayed with a single launch afterwards.
+    bool launched = false;
+    if (use_graph) {
+        HostGraph *g = nullptr, *victim = nullptr;
+        for (auto &cand : h->graphs) {
+            if (cand.exec && cand.plan.same(pl)) { g = &cand; break; }
+            if (!victim || (victim->exec && (!cand.exec || cand.last_use < victim->last_use))) victim = &cand;  // empty, else least recent
+        }
+        if (!g) {
+            g = victim;
+            if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; }
+            cudaGraph_t graph = nullptr;
+            CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            rc = enqueue_step_host(h, pl, /*pdl_ok=*/false);
+            cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            if (rc == RW_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&g->exec, graph, 0) == cudaSuccess) {
+                g->plan = pl;
             } else {
-                CK(rw_launch_pack_u8(h->d_obs + a, h->d_pack + a, b - a, st));
-                CK(cudaMemcpyAsync(h->h_pack + a, h->d_pack + a, b - a, cudaMemcpyDeviceToHost, st));
+                g->exec = nullptr;
+                (void)cudaGetLastError();
             }
-            CK(cudaEventRecord(h->pack_ev[c], st));
+            if (graph) cudaGraphDestroy(graph);
+        }
+        if (g->exec) {
+            g->last_use = ++h->host_calls_graph;
+            CK(cudaGraphLaunch(g->exec, st));
+            launched = true;
         }
     }
-    if (reward_host) CK(cudaMemcpyAsync(reward_host, h->d_reward, (size_t)p.E * p.n * 4, cudaMemcpyDeviceToHost, st));
-    if (done_host) CK(cudaMemcpyAsync(done_host, h->d_done, (size_t)p.E, cudaMemcpyDeviceToHost, st));
-    if (obs_host && n_cpu < n_obs) {  // the copy engine's share (everything, for the plain transport).  Device-to-host copies of
-        // different streams do not overlap on this hardware, so it simply follows the compressed pieces on the same stream.
-        if (timed_dma) CK(cudaEventRecord(h->dma_ev[0], st));
-        CK(cudaMemcpyAsync(obs_host + n_cpu, h->d_obs + n_cpu, (n_obs - n_cpu) * 4, cudaMemcpyDeviceToHost, st));
-        if (timed_dma) CK(cudaEventRecord(h->dma_ev[1], st));
+    if (!launched) {
+        rc = enqueue_step_host(h, pl, true);
+        if (rc) return rc;
     }
+    const double t_enq = now_us();
     double t_first = 0, t_last = 0, t_done = 0;
+    auto flag_wait = [&](int idx, bool block) -> bool {  // the flag kernel behind piece idx bumps a counter the host can see
+        volatile uint32_t *f = h->h_flags + 16 * idx;
+        const uint32_t want = h->flag_seen[idx] + 1;
+        if (!block) return (int32_t)(*f - want) >= 0;
+        unsigned spins = 0;
+        while ((int32_t)(*f - want) < 0) {
+            if ((++spins & 0x3ff) == 0 && cudaStreamQuery(st) != cudaErrorNotReady) {  // the stream finished or failed
+                if ((int32_t)(*f - want) >= 0) break;
+                return false;
+            }
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+        return true;
+    };
+    bool flags_ok = true;
     if (n_cpu) {
         RwHostJob job;
-        job.kind = bits ? RW_HOSTJOB_BITS : RW_HOSTJOB_WIDEN;
+        job.kind = pl.bits ? RW_HOSTJOB_BITS : RW_HOSTJOB_WIDEN;
         job.src = h->h_pack;
-        job.wide = h->h_pack + off_wide;
+        job.wide = h->h_pack + pl.off_wide;
         job.dst = obs_host;
         job.n = n_cpu;
         job.L = (int)L;
-        job.nwide = nwide;
-        job.n_rows = rows_cpu;
-        job.nchunks = nch;
-        for (int c = 0; c < nch; c++) job.chunk_end[c] = chunk_end[c];
+        job.nwide = pl.nwide;
+        job.n_rows = pl.rows_cpu;
+        job.nchunks = pl.nch;
+        for (int c = 0; c < pl.nch; c++) job.chunk_end[c] = pl.chunk_end[c];
         rw_hostpool_begin(job);
-        cudaError_t err = cudaSuccess;
-        for (int c = 0; c < nch && err == cudaSuccess; c++) {
-            err = cudaEventSynchronize(h->pack_ev[c]);
-            if (err == cudaSuccess) rw_hostpool_chunk_ready(c + 1);
+        for (int c = 0; c < pl.nch && flags_ok; c++) {
+            flags_ok = flag_wait(c, true);
+            if (flags_ok) rw_hostpool_chunk_ready(c + 1);
             if (c == 0) t_first = now_us();
         }
         t_last = now_us();
-        if (err != cudaSuccess) rw_hostpool_cancel();
+        if (!flags_ok) rw_hostpool_cancel();
         rw_hostpool_finish();
         t_done = now_us();
-        CK(err);
     }
+    bool dma_late = false;
+    if (timed_dma && flags_ok) dma_late = !flag_wait(8, false);
+    CK(cudaStreamSynchronize(st));
+    const double t_end = now_us();
+    for (int c = 0; c < pl.nch; c++) h->flag_seen[c] = h->h_flags[16 * c];
+    h->flag_seen[8] = h->h_flags[16 * 8];
+    if (!flags_ok) return fail(h, RW_ECUDA, "rw_step_host: the stream went idle before a piece of the compressed rows was flagged");
     double dma_us = 0, dma_end = 0;
     if (timed_dma) {
-        const bool late = cudaEventQuery(h->dma_ev[1]) == cudaErrorNotReady;
-        CK(cudaEventSynchronize(h->dma_ev[1]));
-        const double t_sync = now_us();
         float ms = 0, ms_end = 0;
         CK(cudaEventElapsedTime(&ms, h->dma_ev[0], h->dma_ev[1]));
-        CK(cudaEventElapsedTime(&ms_end, h->pack_ev[0], h->dma_ev[1]));  // negative when the copy ended before chunk 0 landed
+        CK(cudaEventElapsedTime(&ms_end, h->pack_ev[0], h->dma_ev[1]));
         dma_us = ms * 1e3;
-        dma_end = late ? t_sync : t_first + ms_end * 1e3;  // on the host clock (chunk 0 was seen at t_first)
+        dma_end = dma_late ? t_end : t_first + ms_end * 1e3;  // on the host clock (piece 0 was seen at t_first)
         // re-balance so that the expansion and the copy engine FINISH together.  With the rates observed in this call (each
-        // includes what the other took from the memory system) and the copy's head start d0 over the expansion, the copy
+        // includes what the other took from the memory system) and the copy's start d0 relative to the expansion's, the copy
         // engine's bytes x solve (B - x) / r_cpu = d0 + x / r_dma.
         const double B = (double)n_obs * 4, x_now = (double)(n_obs - n_cpu) * 4;
         const double r_cpu = (B - x_now) / ((t_done - t_first) > 1 ? (t_done - t_first) : 1);  // bytes / us
@@ -761,16 +867,14 @@ int rw_step_host(rw_handle *h, const int32_t *actions_host, float *obs_host, flo
         if (target > 0.9) target = 0.9;
         h->dma_frac = 0.5 * h->dma_frac + 0.5 * target;
     }
-    CK(cudaStreamSynchronize(st));
-    const double t_end = now_us();
     h->host_calls++;
     if (trace)
-        fprintf(stderr, "[rw_step_host] %s rows_cpu %zu/%zu chunks %d | enqueue %.0f first-chunk %.0f last-chunk %.0f expand-done %.0f "
+        fprintf(stderr, "[rw_step_host] %s%s rows_cpu %zu/%zu pieces %d | enqueued %.0f first-piece %.0f last-piece %.0f expand-done %.0f "
                         "end %.0f us | dma %.0f us, ends at %.0f | dma_frac -> %.3f | threads %d isa %d\n",
-                !n_cpu ? "plain" : fused ? "bits(fused)" : bits ? "bits" : "bytes", rows_cpu, n_rows, nch, 0.0, n_cpu ? t_first - t_call : 0.0,
-                n_cpu ? t_last - t_call : 0.0, n_cpu ? t_done - t_call : 0.0, t_end - t_call, dma_us, timed_dma ? dma_end - t_call : 0.0,
-                h->dma_frac,
-                n_cpu ? rw_hostpool_threads() : 0, n_cpu ? rw_hostpool_isa() : 0);
+                !n_cpu ? "plain" : pl.fused ? "bits(fused)" : pl.bits ? "bits" : "bytes", launched ? " graph" : "", pl.rows_cpu, n_rows,
+                pl.nch, t_enq - t_call, n_cpu ? t_first - t_call : 0.0, n_cpu ? t_last - t_call : 0.0, n_cpu ? t_done - t_call : 0.0,
+                t_end - t_call, dma_us, timed_dma ? dma_end - t_call : 0.0, h->dma_frac, n_cpu ? rw_hostpool_threads() : 0,
+                n_cpu ? rw_hostpool_isa() : 0);
     return RW_OK;
 }
 

@@ -121,6 +121,21 @@ cudaError_t rw_launch_pack_bits(const float *in, uint32_t *bits, uint8_t *wide, 
     return cudaGetLastError();
 }
 
+// Host-visible progress flag of rw_step_host: bumps a device counter and publishes it to a word of mapped host memory; stream
+// order puts it behind the device-to-host copy it announces.  (A counter rather than a value passed by the caller, so that the
+// launch can be replayed unchanged from a CUDA graph.)
+__global__ void rw_host_flag_kernel(uint32_t *counter, volatile uint32_t *host_flag) {
+    const uint32_t v = *counter + 1;
+    *counter = v;
+    __threadfence_system();
+    *host_flag = v;
+}
+
+cudaError_t rw_launch_host_flag(uint32_t *counter, volatile uint32_t *host_flag, cudaStream_t stream) {
+    rw_host_flag_kernel<<<1, 1, 0, stream>>>(counter, host_flag);
+    return cudaGetLastError();
+}
+
 // L2 flush for benchmarks: streams `bytes` of writes through the L2 with the SAME shared-memory carve-out as the step
 // kernel (a flush kernel with a different carve-out makes the next launch pay an SM reconfiguration).
 __global__ void rw_flush_l2_kernel(int4 *buf, size_t n16, int value) {
@@ -174,7 +189,7 @@ cudaError_t rw_configure_kernels(const RwParams &p, int smem_bytes_per_cta) {
 }
 
 cudaError_t rw_launch_main(RwMode mode, const RwParams &p, const int32_t *actions, float *obs, float *reward, uint8_t *done,
-                           const uint8_t *mask, cudaStream_t stream) {
+                           const uint8_t *mask, cudaStream_t stream, bool pdl_ok) {
     dim3 block(64 * p.warps_per_cta);  // a warp pair per tile
     dim3 grid((p.tiles + p.warps_per_cta - 1) / p.warps_per_cta);
     size_t smem = (size_t)p.sm_cta_bytes + (size_t)p.sm_warp_bytes * p.warps_per_cta;
@@ -192,7 +207,7 @@ cudaError_t rw_launch_main(RwMode mode, const RwParams &p, const int32_t *action
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = (pdl && pdl_ok) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, select_kernel(mode, p, g_force_dynamic), p, actions, obs, reward, done, mask);
 }
 

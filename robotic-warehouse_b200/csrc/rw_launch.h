@@ -7,7 +7,8 @@ enum RwMode { RW_MODE_STEP = 0, RW_MODE_OBS = 1, RW_MODE_RESET = 2 };
 
 // one launch = the whole hot path for every world of the handle
 cudaError_t rw_launch_main(RwMode mode, const RwParams &p, const int32_t *actions, float *obs, float *reward,
-                           uint8_t *done, const uint8_t *mask, cudaStream_t stream);
+                           uint8_t *done, const uint8_t *mask, cudaStream_t stream, bool pdl_ok = true);
+cudaError_t rw_launch_host_flag(uint32_t *counter, volatile uint32_t *host_flag, cudaStream_t stream);
 cudaError_t rw_configure_kernels(const RwParams &p, int smem_bytes_per_cta);
 void rw_force_dynamic_kernels(bool on);  // diagnostics/tests: bypass the static specialisations
 cudaError_t rw_launch_get_state(const RwParams &p, const void *view /* rw_state_view */, cudaStream_t stream);

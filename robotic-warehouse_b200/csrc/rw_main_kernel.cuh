@@ -183,6 +183,13 @@ __global__ void __launch_bounds__(MAXT, 1) rw_main_kernel(const __grid_constant_
     __syncthreads();  // mbarrier inits and the zeroed grids are visible CTA-wide
     if (!active) return;
     mbar_wait(cta_bar, 0);  // static tables landed
+#if defined(RW_SANITIZER_SYNC)
+    // compute-sanitizer's racecheck does not model "TMA write -> mbarrier complete_tx -> try_wait" as an ordering between the
+    // bulk copy issued by thread 0 and the other threads' reads of the tables; this build-time option (-DRW_SANITIZER_SYNC)
+    // adds a CTA barrier the tool does understand, so that a racecheck run of such a build shows the REST of the kernel's
+    // synchronisation (staging buffers aliased onto the resolver scratch, pair barriers, bulk-group waits) to be hazard free.
+    __syncthreads();
+#endif
     if (role == 0 && MODE == RW_MODE_STEP && !coop && valid && pre) rw_commit_actions<C>(p, l, areg);
     RW_STAMP(1);
 
