@@ -627,6 +627,8 @@ static int enqueue_step_host(rw_handle *h, const HostPlan &pl, bool pdl_ok) {
     cudaStream_t st = h->host_stream;
     const size_t n_rows = (size_t)p.E * p.n, L = (size_t)p.L, n_obs = n_rows * L, n_cpu = pl.rows_cpu * L;
     CK(cudaMemcpyAsync(h->d_actions, pl.actions_host, (size_t)p.E * p.n * p.A * 4, cudaMemcpyHostToDevice, st));
+    RwParams float_part;
+    int64_t float_env0 = -1;
     if (pl.fused) {
         const int64_t e_cpu = (int64_t)(pl.rows_cpu / p.n);
         auto range = [&](int64_t env0, int64_t count) {  // the same launch for the worlds [env0, env0 + count), env0 % 32 == 0
@@ -641,10 +643,9 @@ static int enqueue_step_host(rw_handle *h, const HostPlan &pl, bool pdl_ok) {
         a.obs_bits_out = (uint32_t *)h->d_pack;
         a.obs_wide_out = h->d_pack + pl.off_wide;
         CK(rw_launch_main(RW_MODE_STEP, a, h->d_actions, nullptr, h->d_reward, h->d_done, nullptr, st, pdl_ok));
-        if (e_cpu < p.E) {
-            RwParams b = range(e_cpu, p.E - e_cpu);
-            CK(rw_launch_main(RW_MODE_STEP, b, h->d_actions + e_cpu * p.n * p.A, h->d_obs + (size_t)e_cpu * p.n * L,
-                              h->d_reward + e_cpu * p.n, h->d_done + e_cpu, nullptr, st, pdl_ok));
+        if (e_cpu < p.E) {  // the copy engine's worlds: launched below, behind the first piece of the compressed rows
+            float_part = range(e_cpu, p.E - e_cpu);
+            float_env0 = e_cpu;
         }
     } else {
         CK(rw_launch_main(RW_MODE_STEP, p, h->d_actions, pl.obs_host ? h->d_obs : nullptr, h->d_reward, h->d_done, nullptr, st, pdl_ok));
@@ -665,19 +666,23 @@ static int enqueue_step_host(rw_handle *h, const HostPlan &pl, bool pdl_ok) {
             CK(rw_launch_pack_u8(h->d_obs + a, h->d_pack + a, b - a, st));
             CK(cudaMemcpyAsync(h->h_pack + a, h->d_pack + a, b - a, cudaMemcpyDeviceToHost, st));
         }
-        if (c == 0) CK(cudaEventRecord(h->pack_ev[0], st));  // timing only (read after the stream is idle)
         CK(rw_launch_host_flag(h->d_flag_ctr + c, h->h_flags + 16 * c, st));
+        if (c == 0 && float_env0 >= 0) {
+            CK(rw_launch_main(RW_MODE_STEP, float_part, h->d_actions + float_env0 * p.n * p.A, h->d_obs + (size_t)float_env0 * p.n * L,
+                              h->d_reward + float_env0 * p.n, h->d_done + float_env0, nullptr, st, pdl_ok));
+            float_env0 = -1;
+        }
     }
+    if (float_env0 >= 0)  // (no pieces: cannot happen with a fused plan, kept for safety)
+        CK(rw_launch_main(RW_MODE_STEP, float_part, h->d_actions + float_env0 * p.n * p.A, h->d_obs + (size_t)float_env0 * p.n * L,
+                          h->d_reward + float_env0 * p.n, h->d_done + float_env0, nullptr, st, pdl_ok));
     if (pl.reward_host) CK(cudaMemcpyAsync(pl.reward_host, h->d_reward, (size_t)p.E * p.n * 4, cudaMemcpyDeviceToHost, st));
     if (pl.done_host) CK(cudaMemcpyAsync(pl.done_host, h->d_done, (size_t)p.E, cudaMemcpyDeviceToHost, st));
     if (pl.obs_host && n_cpu < n_obs) {  // the copy engine's share (everything, for the plain transport).  Device-to-host copies
         // of different streams do not overlap on this hardware, so it simply follows the compressed pieces on the same stream.
-        if (n_cpu) CK(cudaEventRecord(h->dma_ev[0], st));
+        if (n_cpu) CK(rw_launch_host_flag(h->d_flag_ctr + 9, h->h_flags + 16 * 9, st));  // stamps the start of the copy
         CK(cudaMemcpyAsync(pl.obs_host + n_cpu, h->d_obs + n_cpu, (n_obs - n_cpu) * 4, cudaMemcpyDeviceToHost, st));
-        if (n_cpu) {
-            CK(cudaEventRecord(h->dma_ev[1], st));
-            CK(rw_launch_host_flag(h->d_flag_ctr + 8, h->h_flags + 16 * 8, st));
-        }
+        if (n_cpu) CK(rw_launch_host_flag(h->d_flag_ctr + 8, h->h_flags + 16 * 8, st));               // and its end
     }
     return RW_OK;
 }
@@ -733,9 +738,6 @@ int rw_step_host(rw_handle *h, const int32_t *actions_host, float *obs_host, flo
         if (h->pack_bytes < pl.off_wide + rows_pad * 2 + 256) h->pack_bytes = pl.off_wide + rows_pad * 2 + 256;
         CK(cudaMalloc(&h->d_pack, h->pack_bytes));
         CK(alloc_pinned_placed((void **)&h->h_pack, h->pack_bytes, gpu_numa_node(h->device), 1.0));
-        for (auto &e : h->pack_ev) CK(cudaEventCreate(&e));
-        CK(cudaEventCreate(&h->dma_ev[0]));
-        CK(cudaEventCreate(&h->dma_ev[1]));
         CK(cudaMalloc((void **)&h->d_flag_ctr, 16 * 4));
         CK(cudaMemset(h->d_flag_ctr, 0, 16 * 4));
         CK(cudaHostAlloc((void **)&h->h_flags, 16 * 64, cudaHostAllocMapped | cudaHostAllocPortable));
@@ -845,16 +847,13 @@ int rw_step_host(rw_handle *h, const int32_t *actions_host, float *obs_host, flo
     if (timed_dma && flags_ok) dma_late = !flag_wait(8, false);
     CK(cudaStreamSynchronize(st));
     const double t_end = now_us();
-    for (int c = 0; c < pl.nch; c++) h->flag_seen[c] = h->h_flags[16 * c];
-    h->flag_seen[8] = h->h_flags[16 * 8];
+    for (int c = 0; c < 10; c++) h->flag_seen[c] = h->h_flags[16 * c];
     if (!flags_ok) return fail(h, RW_ECUDA, "rw_step_host: the stream went idle before a piece of the compressed rows was flagged");
     double dma_us = 0, dma_end = 0;
     if (timed_dma) {
-        float ms = 0, ms_end = 0;
-        CK(cudaEventElapsedTime(&ms, h->dma_ev[0], h->dma_ev[1]));
-        CK(cudaEventElapsedTime(&ms_end, h->pack_ev[0], h->dma_ev[1]));
-        dma_us = ms * 1e3;
-        dma_end = dma_late ? t_end : t_first + ms_end * 1e3;  // on the host clock (piece 0 was seen at t_first)
+        auto stamp_ns = [&](int idx) { return (double)*reinterpret_cast<volatile unsigned long long *>(h->h_flags + 16 * idx + 2); };
+        dma_us = (stamp_ns(8) - stamp_ns(9)) * 1e-3;  // GPU timer: start / end of the copy engine's share
+        dma_end = dma_late ? t_end : t_first + (stamp_ns(8) - stamp_ns(0)) * 1e-3;  // on the host clock (piece 0 was seen at t_first)
         // re-balance so that the expansion and the copy engine FINISH together.  With the rates observed in this call (each
         // includes what the other took from the memory system) and the copy's start d0 relative to the expansion's, the copy
         // engine's bytes x solve (B - x) / r_cpu = d0 + x / r_dma.

@@ -101,76 +101,7 @@ struct RwParams {
     // of every row (rw_obs_agent_bits); tile t owns the words [t * n * L, (t + 1) * n * L) and the bytes [t * 64 n, ...).
     uint32_t *obs_bits_out;
     uint8_t *obs_wide_out;
-    // bank-conflict-free staging of FLATTENED rows with two lanes per row (rw_obs_plan): slice 0 of a row holds the 8 self features
-    // and the first obs_split window cells, slice 1 the rest; in shared memory every group of obs_pad_group worlds of a chunk is
-    // followed by obs_pad_words unused words (each group leaves through its own TMA bulk store)
-    int32_t obs_split, obs_pad_words, obs_pad_group;
 };
-
-// Staging plan of the observation gather for two lanes per row.  The 32 lanes of a warp store the same element of 32 different
-// (row, slice) pairs at once: rows of a chunk are L words apart, the two slices of a row cellF * split words apart, and L is odd
-// for FLATTENED rows (8 + K * 7), so whether the 32 addresses fall into 32 different banks depends on where the row is split and
-// on how far apart consecutive worlds are.  This picks the split (cells in slice 0) and the padding (words after every `group`
-// worlds, a multiple of 4 so that every group stays 16-byte aligned for its bulk store) with the fewest colliding lanes;
-// ties go to no padding and the most even split.  constexpr so that the fully static kernels fold it.
-struct RwObsPlan {
-    int split, pad_words;
-};
-RW_HD constexpr int rw_obs_plan_collisions(int n, int L, int cellF, int group, int split, int pad) {
-    int seen[32] = {0};
-    int collisions = 0;
-    for (int it = 0; it < 32; it++) {
-        const int part = it & 1, ea = it >> 1, w = ea / n, r = ea - w * n;
-        const int bank = (w * n * L + (w / group) * pad + r * L + part * cellF * split) & 31;
-        if (seen[bank]) collisions++;
-        seen[bank] = 1;
-    }
-    return collisions;
-}
-RW_HD constexpr RwObsPlan rw_obs_plan(int n, int K, int cellF, int group, int chunk_worlds) {
-    const int L = 8 + K * cellF, half = (K + 1) / 2;
-    RwObsPlan best = {half, 0};
-    if (K < 2) return best;
-    int best_c = rw_obs_plan_collisions(n, L, cellF, group, half, 0);
-    for (int pad = 0; pad < 32 && best_c > 0; pad += 4) {
-        if (pad > 0 && chunk_worlds <= group) break;  // a single group per chunk: padding changes nothing
-        for (int d = 0; d < K; d++) {                 // splits in order of increasing imbalance
-            const int cand[2] = {half - d, half + d};
-            for (int j = 0; j < 2; j++) {
-                const int a = cand[j];
-                if (a < 1 || a > K - 1 || (d == 0 && j == 1)) continue;
-                if (a * 3 < K || (K - a) * 3 < K) continue;  // keep the slices within a factor of two of each other
-                const int c = rw_obs_plan_collisions(n, L, cellF, group, a, pad);
-                if (c < best_c) { best_c = c; best.split = a; best.pad_words = pad; }
-            }
-        }
-    }
-    return best;
-}
-// Worlds per staged chunk: the smallest power of two whose rows keep a warp busy (worlds * n * parts >= 32) and whose bytes are
-// a multiple of 16 (one TMA bulk store), within 24 KB per buffer; 0 if no such chunk exists (then plain stores are used).
-RW_HD constexpr int rw_obs_chunk_worlds(int n, int L, int parts) {
-    const int bytes = n * L * 4, budget = 24 * 1024;
-    int best = 0;
-    for (int c = 1; c <= RW_TILE; c *= 2) {
-        if (c * bytes > budget && best) break;
-        if ((c * bytes) % 16 == 0) best = c;
-        if (c * n * parts >= 32 && best == c) break;
-    }
-    return best;
-}
-// worlds per padded group: the fewest worlds whose rows are a multiple of 16 bytes
-RW_HD constexpr int rw_obs_group_worlds(int n, int L) { return (n * L) % 4 == 0 ? 1 : ((2 * n * L) % 4 == 0 ? 2 : 4); }
-// the plan of a FLATTENED configuration with two lanes per row
-#ifndef RW_OBS_PLAN
-#define RW_OBS_PLAN 1  // -DRW_OBS_PLAN=0 builds the library with the even split and no padding (A/B measurements)
-#endif
-RW_HD constexpr RwObsPlan rw_obs_plan_for(int n, int K, int cellF) {
-    const int L = 8 + K * cellF, ch = rw_obs_chunk_worlds(n, L, 2), group = rw_obs_group_worlds(n, L);
-    if (ch == 0 || !RW_OBS_PLAN) return RwObsPlan{(K + 1) / 2, 0};
-    return rw_obs_plan(n, K, cellF, group, ch);
-}
-
 
 RW_HD uint32_t rw_div(uint32_t x, const RwDiv &dv) {
     if (dv.magic == 0) return x;  // d == 1 (ceil(2^32 / 1) does not fit 32 bits)
@@ -224,7 +155,6 @@ struct RwStatic {
     static constexpr bool is_static = true;
     static constexpr bool full_static = (N_ > 0 && RQ_ >= 0);
     static constexpr int static_n = N_;
-    static constexpr int kR = R_, kMB = MB_;
     RW_HD static int n(const RwParams &p) { return N_ > 0 ? N_ : p.n; }
     RW_HD static int R(const RwParams &p) { return RQ_ >= 0 ? RQ_ : p.R; }
     RW_HD static int H(const RwParams &) { return H_; }

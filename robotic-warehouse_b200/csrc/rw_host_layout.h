@@ -127,7 +127,12 @@ static inline void rw_fill_params(RwParams &p, const rw_config &c, int64_t num_e
             if (ev && (atoi(ev) == 1 || atoi(ev) == 2 || atoi(ev) == 4)) p.obs_parts = atoi(ev);
             if (p.obs_parts == 4 && p.K < 4) p.obs_parts = 2;
         }
-        int best = rw_obs_chunk_worlds(n, p.L, p.obs_parts);
+        int best = 0;
+        for (int C = 1; C <= RW_TILE; C *= 2) {
+            if (C * p.obs_env_bytes > budget && best) break;
+            if ((C * p.obs_env_bytes) % 16 == 0) best = C;
+            if (C * n * p.obs_parts >= 32 && best == C) break;  // a full warp of (world, agent, slice) items is enough
+        }
         p.obs_bulk = best ? 1 : 0;
         if (!best) {
             best = 1;
@@ -135,21 +140,10 @@ static inline void rw_fill_params(RwParams &p, const rw_config &c, int64_t num_e
         }
         p.obs_chunk_envs = best;
         p.obs_chunk_bytes = best * p.obs_env_bytes;
-        // bank-conflict-free staging (rw_obs_plan): FLATTENED rows, two lanes per row, bulk stores
-        p.obs_split = (p.K + 1) / 2;
-        p.obs_pad_words = 0;
-        p.obs_pad_group = rw_obs_group_worlds(n, p.L);
-        if (p.obs_kind == 0 && p.obs_parts == 2 && p.obs_bulk) {
-            const RwObsPlan plan = rw_obs_plan_for(n, p.K, p.cellF);
-            p.obs_split = plan.split;
-            p.obs_pad_words = plan.pad_words;
-        }
-        const int groups_per_chunk = best / p.obs_pad_group > 0 ? best / p.obs_pad_group : 1;
-        const int staged_bytes = p.obs_chunk_bytes + (p.obs_pad_words ? groups_per_chunk * p.obs_pad_words * 4 : 0);
         // staging buffers per tile: one per warp of the pair; with quarter-row slices (obs_parts == 4) the chunks are half
         // as large, so each warp double-buffers (its next chunk is assembled while the previous TMA store drains)
         p.obs_nbuf = (p.obs_parts == 4 && RW_TILE / best >= 4) ? 4 : 2;
-        p.obs_buf_stride = rw_round_up(staged_bytes, 128);
+        p.obs_buf_stride = rw_round_up(p.obs_chunk_bytes, 128);
     }
     int off = 0;
     p.sm_tile = off; off += p.nw * RW_TILE * 4; off = rw_round_up(off, 128);
@@ -162,27 +156,17 @@ static inline void rw_fill_params(RwParams &p, const rw_config &c, int64_t num_e
         off += obs_bytes > scratch_bytes ? obs_bytes : scratch_bytes;
     }
     p.sm_bar = off; off += 8;
-    {
-        const char *ev = getenv("RWARE_B200_COOP");
-        p.coop = ev ? atoi(ev) : 0;  // measured (profiles/phase_timeline.py): one lane per world is ~2.5 us faster per launch
-    }
-    // tie buffers of the cooperative step (32 words per warp of the pair, rw_coop.cuh): like the resolver scratch they are dead
-    // before the observation gather starts, so they sit in the staging area behind the scratch -- except in the interleaved
-    // cooperative form (coop == 2), which emits observations between its passes
-    {
-        const int scratch_bytes = rw_round_up(2 * n * RW_TILE * 4, 128), obs_bytes = p.obs_buf_stride * p.obs_nbuf;
-        if (p.coop != 2 && obs_bytes >= scratch_bytes + 2 * 32 * 4) {
-            p.sm_tie = p.sm_obs + scratch_bytes;
-        } else {
-            off = rw_round_up(off, 128);
-            p.sm_tie = off; off += 2 * 32 * 4;
-        }
-    }
+    off = rw_round_up(off, 128);
+    p.sm_tie = off; off += 2 * 32 * 4;  // 32 words per warp of the pair (rw_coop.cuh)
     p.sm_warp_bytes = rw_round_up(off, 128);
     p.sm_cta_tx = rw_round_up(((cells + 1) & ~1) + 2 * cells, 16);
     p.sm_cta_bytes = rw_round_up(p.sm_cta_tx + 8, 128);
     p.gshift = 0;
     while ((1 << p.gshift) < n) p.gshift++;
+    {
+        const char *ev = getenv("RWARE_B200_COOP");
+        p.coop = ev ? atoi(ev) : 0;  // measured (profiles/phase_timeline.py): one lane per world is ~2.5 us faster per launch
+    }
     {
         const char *ev = getenv("RWARE_B200_OBS_TMA");
         p.obs_tma = ev ? atoi(ev) : 1;  // measured: TMA bulk stores beat st.global.v4 copy-out (30 vs 38 us under ncu)

@@ -13,11 +13,11 @@
 #define RW_FULL(H_, W_, S_, R_, N_, RQ_)                                                                    \
     if (!force_dynamic && p.msg_bits == 0 && !p.coop && p.H == H_ && p.W == W_ && p.S == S_ && p.r == R_ && \
         p.n == N_ && p.R == RQ_)                                                                            \
-        return rw_kernel_for_mode<RwStatic<H_, W_, S_, R_, 0, N_, RQ_>>(mode, small_cta);
+        return rw_kernel_for_mode<RwStatic<H_, W_, S_, R_, 0, N_, RQ_>>(mode, small_cta, p.obs_bits_out != nullptr);
 #define RW_GEOM(H_, W_, S_, R_)                                                                  \
     if (!force_dynamic && p.msg_bits == 0 && p.H == H_ && p.W == W_ && p.S == S_ && p.r == R_)   \
-        return rw_kernel_for_mode<RwStatic<H_, W_, S_, R_, 0>>(mode, small_cta);
-#define RW_DYN() return rw_kernel_for_mode<RwDynamic>(mode, small_cta);
+        return rw_kernel_for_mode<RwStatic<H_, W_, S_, R_, 0>>(mode, small_cta, p.obs_bits_out != nullptr);
+#define RW_DYN() return rw_kernel_for_mode<RwDynamic>(mode, small_cta, p.obs_bits_out != nullptr);
 
 #define RW_CAT2(a, b) a##b
 #define RW_CAT(a, b) RW_CAT2(a, b)

@@ -121,18 +121,21 @@ cudaError_t rw_launch_pack_bits(const float *in, uint32_t *bits, uint8_t *wide, 
     return cudaGetLastError();
 }
 
-// Host-visible progress flag of rw_step_host: bumps a device counter and publishes it to a word of mapped host memory; stream
-// order puts it behind the device-to-host copy it announces.  (A counter rather than a value passed by the caller, so that the
-// launch can be replayed unchanged from a CUDA graph.)
-__global__ void rw_host_flag_kernel(uint32_t *counter, volatile uint32_t *host_flag) {
+// Host-visible progress flag of rw_step_host: bumps a device counter and publishes it, with the GPU's nanosecond timer, to a line
+// of mapped host memory; stream order puts it behind the device-to-host copy it announces.  (A counter rather than a value passed
+// by the caller, and a timestamp rather than CUDA events, so that the launch can be replayed unchanged from a CUDA graph.)
+__global__ void rw_host_flag_kernel(uint32_t *counter, volatile uint32_t *host_line) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     const uint32_t v = *counter + 1;
     *counter = v;
+    *reinterpret_cast<volatile unsigned long long *>(host_line + 2) = t;
     __threadfence_system();
-    *host_flag = v;
+    *host_line = v;
 }
 
-cudaError_t rw_launch_host_flag(uint32_t *counter, volatile uint32_t *host_flag, cudaStream_t stream) {
-    rw_host_flag_kernel<<<1, 1, 0, stream>>>(counter, host_flag);
+cudaError_t rw_launch_host_flag(uint32_t *counter, volatile uint32_t *host_line, cudaStream_t stream) {
+    rw_host_flag_kernel<<<1, 1, 0, stream>>>(counter, host_line);
     return cudaGetLastError();
 }
 
@@ -178,11 +181,15 @@ static bool g_force_dynamic = false;
 void rw_force_dynamic_kernels(bool on) { g_force_dynamic = on; }
 
 cudaError_t rw_configure_kernels(const RwParams &p, int smem_bytes_per_cta) {
-    for (int m = 0; m < 3; m++) {
-        for (int dyn = 0; dyn < 2; dyn++) {
-            cudaError_t e = cudaFuncSetAttribute((const void *)select_kernel((RwMode)m, p, dyn != 0),
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_per_cta);
-            if (e != cudaSuccess) return e;
+    RwParams q = p;
+    for (int bits = 0; bits < 2; bits++) {  // the float kernels of every mode, and the bit-form instantiation of the step kernel
+        q.obs_bits_out = bits ? reinterpret_cast<uint32_t *>(uintptr_t(16)) : nullptr;
+        for (int m = 0; m < (bits ? 1 : 3); m++) {
+            for (int dyn = 0; dyn < 2; dyn++) {
+                cudaError_t e = cudaFuncSetAttribute((const void *)select_kernel((RwMode)m, q, dyn != 0),
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_per_cta);
+                if (e != cudaSuccess) return e;
+            }
         }
     }
     return cudaSuccess;

@@ -822,35 +822,24 @@ RW_HD void rw_obs_agent(const RwParams &p, const RwLane &l, int i, float *out, i
         out[6] = d == 3 ? 1.0f : 0.0f;
         out[7] = (l.highway[y * W + x] & 1) ? 1.0f : 0.0f;  // ref:647
     }
-    // With two slices, slice 0 covers the window cells [0, Ka) and slice 1 the cells [Ka, K), Ka = rw_obs_plan's split (a
-    // compile-time constant for the fully static configurations, p.obs_split otherwise); with more slices, slice s covers
-    // [s*Kp, min(K, (s+1)*Kp)).  `part` varies across lanes: with two slices everything that depends on it is a select
-    // between the values of slice 0 and slice 1 (no divergence, no integer division).
-    int Ka = (K + 1) / 2;
-    if (nparts == 2) {
-        if constexpr (C::full_static) {
-            constexpr int Ka_static = rw_obs_plan_for(C::static_n, (2 * C::kR + 1) * (2 * C::kR + 1), 7 + C::kMB).split;
-            Ka = Ka_static;
-        } else {
-            Ka = p.obs_split;
-        }
-    }
-    const int Kp = nparts == 2 ? (Ka > K - Ka ? Ka : K - Ka) : (K + nparts - 1) / nparts;
+    // Slice s covers window cells [s*Kp, min(K, (s+1)*Kp)).  `part` varies across lanes: with two slices everything
+    // that depends on it is a select between the compile-time values of slice 0 and slice 1 (no divergence, no
+    // integer division); with more slices the cell index is computed (division by the compile-time window width).
+    const int Kp = (K + nparts - 1) / nparts;
     const bool hi = part != 0;
     const uint8_t *gc = l.g + (y * W + x);
-    float *ob = out + 8 + (nparts <= 2 ? (hi ? Ka * cellF : 0) : part * Kp * cellF);
+    float *ob = out + 8 + (nparts <= 2 ? (hi ? Kp * cellF : 0) : part * Kp * cellF);
 #pragma unroll
     for (int k = 0; k < Kp; k++) {                        // ref:628-629 window cells, rows outer, columns inner
         int dy, dx;
         bool live;
         if (nparts <= 2) {
-            const int ca = k, cb = Ka + k;                // cell index in slice 0 / slice 1 (compile time when unrolled)
-            const int ca_c = ca < K ? ca : K - 1, cb_c = cb < K ? cb : K - 1;
-            const int dya = ca_c / win - r, dxa = ca_c % win - r;
-            const int dyb = cb_c / win - r, dxb = cb_c % win - r;
+            const int ca = k, cb = Kp + k;                // cell index in slice 0 / slice 1 (compile time when unrolled)
+            const int dya = ca / win - r, dxa = ca % win - r;
+            const int dyb = (cb < K ? cb : K - 1) / win - r, dxb = (cb < K ? cb : K - 1) % win - r;
             dy = hi ? dyb : dya;
             dx = hi ? dxb : dxa;
-            live = hi ? (cb < K) : (nparts == 2 ? ca < Ka : ca < K);
+            live = hi ? (cb < K) : (ca < K);
         } else {
             const int c = part * Kp + k;
             const int cc = c < K ? c : K - 1;

@@ -116,7 +116,9 @@ __device__ __noinline__ void rw_tile_bits(const RwParams &p, uint8_t *wb, int32_
 // stores.  p.warps_per_cta counts TILES per CTA (blockDim = 64 * tiles).  MAXT bounds the CTA size: 896 threads (14 tiles) leave
 // 72 registers per thread; configurations whose tiles are large enough that at most 7 fit an SM use the 448-thread build of the
 // step kernel, which may keep up to 144 registers and does not spill.
-template <int MODE, class C, int MAXT = 896>
+// BITS: the launch writes the bit form of the rows (p.obs_bits_out / p.obs_wide_out) instead of float rows -- a separate
+// instantiation of the step kernel, so that the float kernels carry none of it.
+template <int MODE, class C, int MAXT = 896, bool BITS = false>
 __global__ void __launch_bounds__(MAXT, 1) rw_main_kernel(const __grid_constant__ RwParams p, const int32_t *__restrict__ actions,
                                                        float *__restrict__ obs, float *__restrict__ reward,
                                                        uint8_t *__restrict__ done, const uint8_t *__restrict__ mask) {
@@ -143,31 +145,41 @@ __global__ void __launch_bounds__(MAXT, 1) rw_main_kernel(const __grid_constant_
     l.highway = s_highway;
     l.home_id = s_home_id;
 
-    // Programmatic dependent launch: this grid may have been scheduled while the previous grid on the stream was still
-    // draining; nothing it wrote may be read before this point.  Dependents of this grid may start launching right away
-    // (they wait at the same instruction).  Both are no-ops for an ordinary launch.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    RW_STAMP(0);
-    // ---- 1. prologue.  Thread 0: the CTA-shared static tables (highway bytes + home ids) arrive through one TMA bulk
-    //         copy on a CTA-level mbarrier.  Primary lane 0: this tile's packed state through another TMA bulk copy on
-    //         the tile's mbarrier.  While they are in flight: helper zeroes the occupancy grids, primary issues its
-    //         action loads.
     // the fully static specialisations carry only the one-lane-per-world step (select_kernel routes p.coop elsewhere)
     const bool coop = !C::full_static && (MODE == RW_MODE_STEP) && p.coop;
-    uint64_t *cta_bar = reinterpret_cast<uint64_t *>(smem + p.sm_cta_bytes - 8);
-    if (threadIdx.x == 0) {
-        mbar_init(cta_bar, 1);
-        fence_mbar_init();
-        mbar_expect_tx(cta_bar, (uint32_t)p.sm_cta_tx);
-        bulk_g2s(smem, p.cta_tables, (uint32_t)p.sm_cta_tx, cta_bar);
+    // ---- 1. prologue, part one: everything that does NOT depend on what earlier work on the stream wrote.  Under
+    //         programmatic dependent launch this grid's CTAs become resident while the previous grid is still draining, and this
+    //         part runs in that shadow: the CTA-shared static tables (highway bytes + home ids, a few hundred bytes: every thread
+    //         copies 16 bytes with plain loads -- a TMA bulk copy bought nothing for so few bytes, and compute-sanitizer's
+    //         racecheck cannot follow "bulk copy issued by thread 0 -> mbarrier -> reads by other warps"), the zeroed occupancy
+    //         grids (helper warp) and the tile's mbarrier (primary lane 0).
+    {
+        const int4 *g4 = reinterpret_cast<const int4 *>(p.cta_tables);
+        int4 *s4 = reinterpret_cast<int4 *>(smem);
+        for (int i = threadIdx.x; i < (p.sm_cta_tx >> 4); i += blockDim.x) s4[i] = __ldg(g4 + i);
     }
-    RwActRegs<C> areg;
-    const bool pre = rw_can_prefetch_actions<C>(p);
     if (role == 0) {
         if (active && lane == 0) {
             mbar_init(bar, 1);
             fence_mbar_init();
+        }
+    } else if (active) {
+        int4 *g4 = reinterpret_cast<int4 *>(grid);
+        const int n16 = (p.grid_env_stride * RW_TILE) >> 4;
+        for (int i = lane; i < n16; i += 32) g4[i] = make_int4(0, 0, 0, 0);
+    }
+    // Programmatic dependent launch: nothing the previous grid wrote (world state, the caller's actions) may be read before
+    // this point.  Dependents of this grid may start launching right away (they wait at the same instruction).  Both are
+    // no-ops for an ordinary launch.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    RW_STAMP(0);
+    // ---- 1. prologue, part two: the tile's packed state arrives through a TMA bulk copy on the tile's mbarrier (primary lane 0)
+    //         while the primary's lanes issue their action loads.
+    RwActRegs<C> areg;
+    const bool pre = rw_can_prefetch_actions<C>(p);
+    if (role == 0) {
+        if (active && lane == 0) {
             mbar_expect_tx(bar, tile_bytes);
             bulk_g2s(tilew, gtile, tile_bytes, bar);
         }
@@ -175,21 +187,9 @@ __global__ void __launch_bounds__(MAXT, 1) rw_main_kernel(const __grid_constant_
             if (pre) rw_prefetch_actions<C>(p, actions + env * p.n * p.A, areg);  // loads in flight, consumed below
             else rw_load_actions<C>(p, l, actions + env * p.n * p.A);
         }
-    } else if (active) {
-        int4 *g4 = reinterpret_cast<int4 *>(grid);
-        const int n16 = (p.grid_env_stride * RW_TILE) >> 4;
-        for (int i = lane; i < n16; i += 32) g4[i] = make_int4(0, 0, 0, 0);
     }
-    __syncthreads();  // mbarrier inits and the zeroed grids are visible CTA-wide
+    __syncthreads();  // static tables, mbarrier inits and the zeroed grids are visible CTA-wide
     if (!active) return;
-    mbar_wait(cta_bar, 0);  // static tables landed
-#if defined(RW_SANITIZER_SYNC)
-    // compute-sanitizer's racecheck does not model "TMA write -> mbarrier complete_tx -> try_wait" as an ordering between the
-    // bulk copy issued by thread 0 and the other threads' reads of the tables; this build-time option (-DRW_SANITIZER_SYNC)
-    // adds a CTA barrier the tool does understand, so that a racecheck run of such a build shows the REST of the kernel's
-    // synchronisation (staging buffers aliased onto the resolver scratch, pair barriers, bulk-group waits) to be hazard free.
-    __syncthreads();
-#endif
     if (role == 0 && MODE == RW_MODE_STEP && !coop && valid && pre) rw_commit_actions<C>(p, l, areg);
     RW_STAMP(1);
 
@@ -213,8 +213,6 @@ __global__ void __launch_bounds__(MAXT, 1) rw_main_kernel(const __grid_constant_
             __syncwarp();
             stores_in_flight = nbw - 1;
         }
-        // rows of world el of the chunk start at word el * n * L + (el / G) * padw of the staging buffer (rw_obs_plan)
-        const int G = p.obs_pad_group, padw = p.obs_pad_words;
         for (int it = lane; it < items; it += 32) {
             const int part = P == 4 ? (it & 3) : P == 2 ? (it & 1) : 0;
             const int ea = P == 4 ? (it >> 2) : P == 2 ? (it >> 1) : it;  // (world, agent) row inside the chunk
@@ -228,10 +226,9 @@ __global__ void __launch_bounds__(MAXT, 1) rw_main_kernel(const __grid_constant_
                 le.sc_step = 0;
                 le.highway = s_highway;
                 le.home_id = s_home_id;
-                float *row = buf + ea * L + (padw ? (G == 1 ? el : el / G) * padw : 0);
-                if (P == 4) rw_obs_row<C, 4>(p, le, ea - el * n, row, part);
-                else if (P == 2) rw_obs_row<C, 2>(p, le, ea - el * n, row, part);
-                else rw_obs_row<C, 1>(p, le, ea - el * n, row, 0);
+                if (P == 4) rw_obs_row<C, 4>(p, le, ea - el * n, buf + ea * L, part);
+                else if (P == 2) rw_obs_row<C, 2>(p, le, ea - el * n, buf + ea * L, part);
+                else rw_obs_row<C, 1>(p, le, ea - el * n, buf + ea * L, 0);
             }
         }
         // destinations: the caller's tensor, or (fused push all-gather) this rank's slot of every rank's gathered tensor,
@@ -242,29 +239,22 @@ __global__ void __launch_bounds__(MAXT, 1) rw_main_kernel(const __grid_constant_
                 return p.peer_obs[(p.my_rank + d) % p.n_peers] + (size_t)(p.gather_env0 + tile_env0 + c0) * n * L;
             return obs + (tile_env0 + c0) * n * L;
         };
-        const int ngroups = padw ? CH / G : 1;              // pieces of the staged chunk, each contiguous in shared memory
-        const int gwords = padw ? G * n * L : CH * n * L;   // words per piece
         if (fast && p.obs_tma) {
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-                for (int d = 0; d < ndst; d++) {
-                    float *dst = dst_ptr(d);
-                    for (int g = 0; g < ngroups; g++) bulk_s2g(dst + g * gwords, buf + g * (gwords + padw), (uint32_t)gwords * 4u);
-                }
+                for (int d = 0; d < ndst; d++) bulk_s2g(dst_ptr(d), buf, (uint32_t)p.obs_chunk_bytes);
                 bulk_commit();
             }
             stores_in_flight++;
         } else if (fast) {  // 16-byte coalesced stores: 512 B per warp instruction
             __syncwarp();
-            const int n16 = gwords >> 2;
+            const int4 *src = reinterpret_cast<const int4 *>(buf);
+            const int n16 = p.obs_chunk_bytes >> 4;
             for (int d = 0; d < ndst; d++) {
-                for (int g = 0; g < ngroups; g++) {
-                    const int4 *src = reinterpret_cast<const int4 *>(buf + g * (gwords + padw));
-                    int4 *dst = reinterpret_cast<int4 *>(dst_ptr(d) + g * gwords);
+                int4 *dst = reinterpret_cast<int4 *>(dst_ptr(d));
 #pragma unroll 4
-                    for (int i = lane; i < n16; i += 32) __stcs(dst + i, src[i]);
-                }
+                for (int i = lane; i < n16; i += 32) __stcs(dst + i, src[i]);
             }
             __syncwarp();
         } else {  // ragged tail / unaligned geometry: plain coalesced stores
@@ -275,7 +265,7 @@ __global__ void __launch_bounds__(MAXT, 1) rw_main_kernel(const __grid_constant_
             const int nf = (int)(envs_here > 0 ? envs_here : 0) * n * L;
             for (int d = 0; d < ndst; d++) {
                 float *gdst = dst_ptr(d);
-                for (int i = lane; i < nf; i += 32) gdst[i] = buf[i + (padw ? (i / (G * n * L)) * padw : 0)];
+                for (int i = lane; i < nf; i += 32) gdst[i] = buf[i];
             }
             __syncwarp();
         }
@@ -345,13 +335,12 @@ __global__ void __launch_bounds__(MAXT, 1) rw_main_kernel(const __grid_constant_
             bulk_commit();
         }
     }
-    const bool want_bits = p.obs_bits_out != nullptr;
-    if ((obs != nullptr || want_bits) && !interleave) {
+    if ((obs != nullptr || BITS) && !interleave) {
         if (!coop) {
             pair_barrier(1 + tl);  // post-step tile + grids are visible to the helper
             RW_STAMP(4);
         }
-        if (want_bits) {
+        if constexpr (BITS) {
             rw_tile_bits<C>(p, wb, tilew, grid, s_highway, s_home_id, tile, tl, role, lane);
         } else {
             // ---- 4. observation gather after the fact: this warp takes every second chunk
@@ -380,7 +369,9 @@ __global__ void __launch_bounds__(MAXT, 1) rw_main_kernel(const __grid_constant_
 typedef void (*rw_kernel_fn)(const RwParams, const int32_t *, float *, float *, uint8_t *, const uint8_t *);
 
 template <class C>
-static rw_kernel_fn rw_kernel_for_mode(RwMode mode, bool small_cta) {
+static rw_kernel_fn rw_kernel_for_mode(RwMode mode, bool small_cta, bool bits = false) {
+    if (mode == RW_MODE_STEP && bits)
+        return small_cta ? rw_main_kernel<RW_MODE_STEP, C, 448, true> : rw_main_kernel<RW_MODE_STEP, C, 896, true>;
     switch (mode) {
         case RW_MODE_STEP: return small_cta ? rw_main_kernel<RW_MODE_STEP, C, 448> : rw_main_kernel<RW_MODE_STEP, C>;
         case RW_MODE_OBS: return rw_main_kernel<RW_MODE_OBS, C>;
