@@ -25,7 +25,7 @@
 #include "rw_hostpack.h"
 #include "rw_views.cuh"
 
-#define RW_DMA_FRAC0 0.15
+#define RW_DMA_FRAC0 0.08
 
 // What one rw_step_host call does on the device side, decided before anything is enqueued
 struct HostPlan {
@@ -719,7 +719,7 @@ int rw_step_host(rw_handle *h, const int32_t *actions_host, float *obs_host, flo
         size_t gran = 2 * (size_t)RW_TILE * p.n;
         const size_t coarse = n_rows / 64 / gran * gran;
         if (coarse > gran) gran = coarse;
-        pl.rows_cpu = (size_t)((1.0 - f) * (double)n_rows) / gran * gran;
+        pl.rows_cpu = ((size_t)((1.0 - f) * (double)n_rows) + gran / 2) / gran * gran;  // nearest step
         if (f <= 0.0 || pl.rows_cpu > n_rows) pl.rows_cpu = n_rows;
         if (pl.rows_cpu * L < ((size_t)1 << 18)) pl.rows_cpu = 0;
     }
