@@ -181,13 +181,20 @@ static bool g_force_dynamic = false;
 void rw_force_dynamic_kernels(bool on) { g_force_dynamic = on; }
 
 cudaError_t rw_configure_kernels(const RwParams &p, int smem_bytes_per_cta) {
+    // The attribute is a property of the FUNCTION, shared by every handle of the process: it is raised to the device's opt-in
+    // maximum once and never lowered (a later handle with a smaller CTA used to lower it under the earlier handles' feet).
+    int dev = 0, cap = smem_bytes_per_cta;
+    if (cudaGetDevice(&dev) == cudaSuccess) {
+        int optin = 0;
+        if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess && optin > cap) cap = optin;
+    }
     RwParams q = p;
     for (int bits = 0; bits < 2; bits++) {  // the float kernels of every mode, and the bit-form instantiation of the step kernel
         q.obs_bits_out = bits ? reinterpret_cast<uint32_t *>(uintptr_t(16)) : nullptr;
         for (int m = 0; m < (bits ? 1 : 3); m++) {
             for (int dyn = 0; dyn < 2; dyn++) {
                 cudaError_t e = cudaFuncSetAttribute((const void *)select_kernel((RwMode)m, q, dyn != 0),
-                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_per_cta);
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
                 if (e != cudaSuccess) return e;
             }
         }

@@ -176,3 +176,18 @@ def test_out_of_range_state_is_rejected_or_clamped(backend):
     assert int(back["queue"][9, 0]) == vec.n_shelves and int(back["agent_carry"][11, 1]) == vec.n_shelves
     obs, rew, done = vec.step(torch.ones((40, 2), dtype=torch.int32))  # and stepping such worlds is safe
     assert obs.shape == (40, 2, vec.obs_len)
+
+
+@pytest.mark.gpu
+def test_handles_of_different_batch_sizes_coexist():
+    """The dynamic-shared-memory limit is a property of the kernel FUNCTION, shared by all handles of a process: creating a small
+    batch (few tiles per CTA) after a large one must not lower it under the large one's feet."""
+    big = rware_b200.make_vec("rware-tiny-4ag-v1", 8192)     # 2 tiles per CTA
+    big.reset(seed=0)
+    small = rware_b200.make_vec("rware-tiny-4ag-v1", 64)      # 1 tile per CTA, same kernel function
+    small.reset(seed=0)
+    a = torch.ones((8192, 4), dtype=torch.int32, device="cuda")
+    obs, _, _ = big.step(a)
+    obs2, _, _ = small.step(a[:64].contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(obs[:64], obs2)
