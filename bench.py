@@ -237,7 +237,9 @@ def make_actions(vec, E, n, A, dev, rank, p_forward, ring=8, seed=4242):
 
 def other_workloads_records(dev, rank, peak, steps, warmup):
     """N=1 sub-records: BASELINE config 4 (medium-8ag-hard x 32 768, the dense-collision stress) under uniform actions and under
-    P(FORWARD)=0.68, and config 5's per-GPU shard, same rotate-over-world-sets protocol as the headline."""
+    P(FORWARD)=0.68, and config 5's per-GPU shard.  Same rotate-over-world-sets protocol as the headline, timed
+    over ONE FULL EPISODE of every set (500 steps after a 50-step warm-up): the cost of a step depends on how
+    far the worlds are from their reset (shelves get carried away from their home cells), so a few steps after a reset would flatter it."""
     import rware_b200
     out = []
     for name, pf in (("medium-8ag-hard", None), ("medium-8ag-hard", 0.68), ("large-16ag-r2", None)):
@@ -248,11 +250,13 @@ def other_workloads_records(dev, rank, peak, steps, warmup):
             v.reset(seed=(1000 + k) * E)
         v0 = sets[0]
         acts = make_actions(v0, E, v0.n_agents, 1 + v0.msg_bits, dev, rank, pf)
-        ms = time_rotating(lambda i: sets[i % nsets].step(acts[i % len(acts)]), max(steps, 200), max(300, warmup), None, dev)
+        episode = int(v0.cfg.max_steps or 500)
+        ms = time_rotating(lambda i: sets[i % nsets].step(acts[(i + i // nsets) % len(acts)]), episode * nsets, 50 * nsets, None, dev)
         b_step = int(v0.info["algorithmic_bytes_step"])
         out.append({"workload": f"{env_id} {overrides or ''}".strip(), "worlds": E, "actions": "uniform" if pf is None else f"P(FORWARD)={pf}",
                     "kernel_us": ms * 1e3, "env_steps_per_s": E / (ms * 1e-3), "algorithmic_bytes_per_env_step": b_step,
-                    "roofline_frac": b_step * E / (ms * 1e-3) / 1e9 / peak, "l2": f"rotating over {nsets} world sets"})
+                    "roofline_frac": b_step * E / (ms * 1e-3) / 1e9 / peak,
+                    "protocol": f"rotating over {nsets} world sets, {episode} timed steps per set (one full episode) after 50 warm-up steps per set"})
         for v in sets:
             v.close()
         del sets
@@ -308,7 +312,7 @@ def gathered_records(dist, dev, rank, local_rank, world, steps, warmup):
                      torch.empty((world * E,), dtype=torch.uint8, device=dev))
 
                 def step_fn(i):
-                    obs, rew, done = sets[i % nsets].step(acts[i % len(acts)])
+                    obs, rew, done = sets[i % nsets].step(acts[(i + i // nsets) % len(acts)])
                     dist.all_gather_into_tensor(g[0], obs)
                     dist.all_gather_into_tensor(g[1], rew)
                     dist.all_gather_into_tensor(g[2], done)
@@ -321,7 +325,7 @@ def gathered_records(dist, dev, rank, local_rank, world, steps, warmup):
                 dist.barrier()
 
                 def step_fn(i):
-                    sets[i % nsets].backend.step_gather(acts[i % len(acts)])
+                    sets[i % nsets].backend.step_gather(acts[(i + i // nsets) % len(acts)])
                     dist.all_reduce(flag)
             ms = time_rotating(step_fn, max(steps, 50), max(30, warmup), dist, dev)
             rec[f"{mode}_ms"] = ms
@@ -433,12 +437,17 @@ def main():
         flag = torch.zeros(1, dtype=torch.int32, device=dev)
         dist.barrier()
 
+    def act_of(i):
+        # every world set must see a DIFFERENT action tensor at each of its steps (with i % RING and RING == NSETS a set would be fed
+        # the same tensor for ever: agents repeating one action, a much cheaper rollout than the random one this bench claims)
+        return actions[(i + i // NSETS) % RING]
+
     def one_step(i):
         if fused is not None:
-            sets[i % NSETS].backend.step_gather(actions[i % RING])  # lands in slot (call count & 1) of every rank's tensors
+            sets[i % NSETS].backend.step_gather(act_of(i))  # lands in slot (call count & 1) of every rank's tensors
             dist.all_reduce(flag)  # the barrier: all ranks' pushes have landed
             return
-        obs, rew, done = sets[i % NSETS].step(actions[i % RING])
+        obs, rew, done = sets[i % NSETS].step(act_of(i))
         if gathered is not None:
             dist.all_gather_into_tensor(gathered[0], obs)
             dist.all_gather_into_tensor(gathered[1], rew)
@@ -553,23 +562,25 @@ def main():
     # with the library's own allocator), H2D actions + kernel + D2H observations / rewards / done + sync inside the timed region
     e2e_steps = args.e2e_steps
     be = vec.backend
-    h_act = be.host_alloc((E, n, A), torch.int32)
-    h_act.copy_(actions[0].cpu())
+    h_acts = [be.host_alloc((E, n, A), torch.int32) for _ in range(8)]  # fresh actions every step, like the device loop
+    for k, h in enumerate(h_acts):
+        h.copy_(actions[k % RING].cpu())
+    h_act = h_acts[0]
     h_obs = be.host_alloc((E, n, L), torch.float32)
     h_rew = be.host_alloc((E, n), torch.float32)
     h_done = be.host_alloc((E,), torch.uint8)
     def time_e2e(mode, repeats=1):
         be.set_host_transport(mode)
-        for _ in range(max(3, args.e2e_warmup)):  # also lets the copy-engine share settle
-            be.step_host(h_act, h_obs, h_rew, h_done)
+        for k in range(max(3, args.e2e_warmup)):  # also lets the copy-engine share settle
+            be.step_host(h_acts[k % 8], h_obs, h_rew, h_done)
         runs = []
         for _ in range(repeats):
             torch.cuda.synchronize()
             if dist:
                 dist.barrier()
             t0 = time.perf_counter()
-            for _ in range(e2e_steps):
-                be.step_host(h_act, h_obs, h_rew, h_done)  # synchronises internally
+            for k in range(e2e_steps):
+                be.step_host(h_acts[k % 8], h_obs, h_rew, h_done)  # synchronises internally
             runs.append(time.perf_counter() - t0)
         return sorted(runs)[len(runs) // 2], runs  # the median repeat (other tenants of the host share its memory system)
     e2e_plain_s, _ = time_e2e(0)   # float32 observations over PCIe

@@ -17,8 +17,9 @@ v = rware_b200.make_vec(env_id, E, auto_reset=True)
 v.reset(seed=0)
 n, L = v.n_agents, v.obs_len
 be = v.backend
-h_act = be.host_alloc((E, n), torch.int32)
-h_act.copy_(torch.randint(0, 5, (E, n), dtype=torch.int32))
+h_acts = [be.host_alloc((E, n), torch.int32) for _ in range(8)]   # fresh actions every step
+for h in h_acts:
+    h.copy_(torch.randint(0, 5, (E, n), dtype=torch.int32))
 h_obs = be.host_alloc((E, n, L), torch.float32)
 h_rew = be.host_alloc((E, n), torch.float32)
 h_done = be.host_alloc((E,), torch.uint8)
@@ -31,13 +32,13 @@ if len(sys.argv) > 3:
 for mode, share in settings:
     be.set_host_transport(mode)
     be.set_host_dma_share(share)
-    for _ in range(10):
-        be.step_host(h_act, h_obs, h_rew, h_done)
+    for k in range(10):
+        be.step_host(h_acts[k % 8], h_obs, h_rew, h_done)
     if dist:
         dist.barrier()
     t0 = time.perf_counter()
-    for _ in range(30):
-        be.step_host(h_act, h_obs, h_rew, h_done)
+    for k in range(30):
+        be.step_host(h_acts[k % 8], h_obs, h_rew, h_done)
     ms = (time.perf_counter() - t0) / 30 * 1e3
     if dist:
         t = torch.tensor([ms], device="cuda")

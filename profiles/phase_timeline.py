@@ -15,11 +15,13 @@ wl = sys.argv[1] if len(sys.argv) > 1 else "rware-tiny-4ag-v1"
 E = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
 vec = rware_b200.make_vec(wl, E, auto_reset=True)
 vec.reset(seed=0)
-acts = torch.empty((E, vec.n_agents), dtype=torch.int32, device="cuda")
-vec.backend.random_actions(acts, 1, 0)
+acts_ring = [torch.empty((E, vec.n_agents), dtype=torch.int32, device="cuda") for _ in range(8)]
+for k, a in enumerate(acts_ring):
+    vec.backend.random_actions(a, 1, k)
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
-for _ in range(20):
-    vec.step(acts)
+for k in range(120):  # fresh random actions every step (the same tensor again and again makes agents repeat one action: a much cheaper step)
+    vec.step(acts_ring[k % 8])
+acts = acts_ring[3]
 ncta = 256
 buf = torch.zeros((ncta * 32 * 8,), dtype=torch.int64, device="cuda")
 vec.backend.set_clock_buffer(buf)

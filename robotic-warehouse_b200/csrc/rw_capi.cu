@@ -39,7 +39,7 @@ struct HostPlan {
     size_t off_wide;
     int64_t epoch;
     bool same(const HostPlan &o) const {
-        return actions_host == o.actions_host && obs_host == o.obs_host && reward_host == o.reward_host && done_host == o.done_host &&
+        return obs_host == o.obs_host && reward_host == o.reward_host && done_host == o.done_host &&  // (actions are copied outside the graph)
                rows_cpu == o.rows_cpu && bits == o.bits && fused == o.fused && nch == o.nch && epoch == o.epoch;
     }
 };
@@ -626,7 +626,6 @@ static int enqueue_step_host(rw_handle *h, const HostPlan &pl, bool pdl_ok) {
     const RwParams &p = h->p;
     cudaStream_t st = h->host_stream;
     const size_t n_rows = (size_t)p.E * p.n, L = (size_t)p.L, n_obs = n_rows * L, n_cpu = pl.rows_cpu * L;
-    CK(cudaMemcpyAsync(h->d_actions, pl.actions_host, (size_t)p.E * p.n * p.A * 4, cudaMemcpyHostToDevice, st));
     RwParams float_part;
     int64_t float_env0 = -1;
     if (pl.fused) {
@@ -769,6 +768,7 @@ int rw_step_host(rw_handle *h, const int32_t *actions_host, float *obs_host, flo
     if (n_cpu) rw_hostpool_prewake();  // parked workers wake up while the copies and the kernel are in flight
     // The ~20 stream operations of a call cost more host time than the GPU needs to execute the first of them, so a plan is
     // captured into a CUDA graph the first time it is seen and replayed with a single launch afterwards.
+    CK(cudaMemcpyAsync(h->d_actions, actions_host, (size_t)p.E * p.n * p.A * 4, cudaMemcpyHostToDevice, st));  // not part of the graph: callers rotate action buffers
     bool launched = false;
     if (use_graph) {
         HostGraph *g = nullptr, *victim = nullptr;
