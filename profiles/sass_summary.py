@@ -6,9 +6,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 obj = os.path.join(ROOT, "robotic-warehouse_b200", "build", "rw_inst_0.o")
 txt = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True, check=True).stdout
 funcs = re.split(r"\n\s*Function : ", txt)[1:]
-want = {"_Z14rw_main_kernelILi0E8RwStaticILi11ELi10ELi32ELi1ELi0ELi4ELi4EELi896EE": "STEP  tiny-4ag (full static, 896 threads)",
-        "_Z14rw_main_kernelILi1E8RwStaticILi11ELi10ELi32ELi1ELi0ELi4ELi4EELi896EE": "OBS   tiny-4ag",
-        "_Z14rw_main_kernelILi2E8RwStaticILi11ELi10ELi32ELi1ELi0ELi4ELi4EELi896EE": "RESET tiny-4ag"}
+want = {"_Z14rw_main_kernelILi0E8RwStaticILi11ELi10ELi32ELi1ELi0ELi4ELi4EELi896ELb0EE": "STEP  tiny-4ag (full static, 896 threads)",
+        "_Z14rw_main_kernelILi1E8RwStaticILi11ELi10ELi32ELi1ELi0ELi4ELi4EELi896ELb0EE": "OBS   tiny-4ag",
+        "_Z14rw_main_kernelILi2E8RwStaticILi11ELi10ELi32ELi1ELi0ELi4ELi4EELi896ELb0EE": "RESET tiny-4ag",
+        "_Z14rw_main_kernelILi0E8RwStaticILi11ELi10ELi32ELi1ELi0ELi4ELi4EELi896ELb1EE": "STEP  tiny-4ag, bit form of the rows (host transport)"}
 groups = [("TMA bulk copies (cp.async.bulk)", r"^UBLKCP"), ("TMA command flush / bulk-group wait", r"^UTMACMDFLUSH|^UTMACCTL|^DEPBAR"),
           ("mbarrier (SYNCS.*)", r"^SYNCS"), ("named / CTA barriers (BAR)", r"^BAR"), ("proxy fences (FENCE)", r"^FENCE"),
           ("shared loads (LDS)", r"^LDS"), ("shared stores (STS)", r"^STS"), ("global loads (LDG)", r"^LDG"), ("global stores (STG)", r"^STG"),
