@@ -50,7 +50,7 @@ struct HostGraph {
     int64_t last_use = 0;
 };
 
-#define RW_HOST_LOCAL_TAIL 0.25  // share of a buffer from rw_host_alloc_near that stays on the GPU's NUMA node (the copy engine's rows)
+#define RW_HOST_LOCAL_TAIL 0.10  // share of a buffer from rw_host_alloc_near that stays on the GPU's NUMA node (the copy engine's rows)
 
 struct rw_handle {
     RwParams p;
