@@ -68,8 +68,6 @@ struct rw_handle {
     // compressed transport of rw_step_host: bit / byte image of the observations on the device and in pinned host memory
     uint8_t *d_pack = nullptr, *h_pack = nullptr;
     size_t pack_bytes = 0;
-    cudaEvent_t pack_ev[8] = {};
-    cudaEvent_t dma_ev[2] = {};
     uint32_t *d_flag_ctr = nullptr;            // device counters behind the host-visible flags
     volatile uint32_t *h_flags = nullptr;      // mapped host memory, one flag per 64-byte line: piece c -> h_flags[16 c], copy engine -> [16 * 8]
     uint32_t flag_seen[16] = {};
@@ -265,8 +263,6 @@ int rw_destroy(rw_handle *h) {
     if (h->d_pack) {
         cudaFree(h->d_pack);
         free_pinned(h->h_pack);
-        for (auto &e : h->pack_ev) if (e) cudaEventDestroy(e);
-        for (auto &e : h->dma_ev) if (e) cudaEventDestroy(e);
         for (auto &g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
         cudaFree(h->d_flag_ctr);
         if (h->h_flags) cudaFreeHost((void *)h->h_flags);
