@@ -251,7 +251,7 @@ def other_workloads_records(dev, rank, peak, steps, warmup):
         v0 = sets[0]
         acts = make_actions(v0, E, v0.n_agents, 1 + v0.msg_bits, dev, rank, pf)
         episode = int(v0.cfg.max_steps or 500)
-        ms = time_rotating(lambda i: sets[i % nsets].step(acts[(i + i // nsets) % len(acts)]), episode * nsets, 50 * nsets, None, dev)
+        ms = time_rotating(lambda i: sets[i % nsets].step(acts[(i // nsets + i % nsets) % len(acts)]), episode * nsets, 50 * nsets, None, dev)
         b_step = int(v0.info["algorithmic_bytes_step"])
         out.append({"workload": f"{env_id} {overrides or ''}".strip(), "worlds": E, "actions": "uniform" if pf is None else f"P(FORWARD)={pf}",
                     "kernel_us": ms * 1e3, "env_steps_per_s": E / (ms * 1e-3), "algorithmic_bytes_per_env_step": b_step,
@@ -312,7 +312,7 @@ def gathered_records(dist, dev, rank, local_rank, world, steps, warmup):
                      torch.empty((world * E,), dtype=torch.uint8, device=dev))
 
                 def step_fn(i):
-                    obs, rew, done = sets[i % nsets].step(acts[(i + i // nsets) % len(acts)])
+                    obs, rew, done = sets[i % nsets].step(acts[(i // nsets + i % nsets) % len(acts)])
                     dist.all_gather_into_tensor(g[0], obs)
                     dist.all_gather_into_tensor(g[1], rew)
                     dist.all_gather_into_tensor(g[2], done)
@@ -325,7 +325,7 @@ def gathered_records(dist, dev, rank, local_rank, world, steps, warmup):
                 dist.barrier()
 
                 def step_fn(i):
-                    sets[i % nsets].backend.step_gather(acts[(i + i // nsets) % len(acts)])
+                    sets[i % nsets].backend.step_gather(acts[(i // nsets + i % nsets) % len(acts)])
                     dist.all_reduce(flag)
             ms = time_rotating(step_fn, max(steps, 50), max(30, warmup), dist, dev)
             rec[f"{mode}_ms"] = ms
@@ -440,7 +440,7 @@ def main():
     def act_of(i):
         # every world set must see a DIFFERENT action tensor at each of its steps (with i % RING and RING == NSETS a set would be fed
         # the same tensor for ever: agents repeating one action, a much cheaper rollout than the random one this bench claims)
-        return actions[(i + i // NSETS) % RING]
+        return actions[(i // NSETS + i % NSETS) % RING]
 
     def one_step(i):
         if fused is not None:

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _index(i, nsets, ring):
-    return (i + i // nsets) % ring
+    return (i // nsets + i % nsets) % ring  # set k = i % nsets, at its j-th visit (j = i // nsets): tensor (j + k) % ring
 
 
 def test_every_world_set_sees_every_action_tensor():
@@ -25,5 +25,5 @@ def test_every_world_set_sees_every_action_tensor():
 def test_bench_uses_that_index():
     src = open(os.path.join(ROOT, "bench.py")).read()
     ast.parse(src)
-    assert "actions[(i + i // NSETS) % RING]" in src
+    assert "actions[(i // NSETS + i % NSETS) % RING]" in src
     assert "sets[i % NSETS].step(actions[i % RING])" not in src
