@@ -3,9 +3,10 @@
 //
 // rw_main_kernel<MODE, C>: ONE launch does the whole env.step for every world.  A tile = 32 worlds (rw_common.h) is
 // served by a warp pair; a CTA holds as many tiles as fit the SM's shared memory.
-//   1. prologue, all in flight together: the CTA-shared static tables and each tile's packed state (nw*128 B,
-//      contiguous in HBM) arrive through TMA bulk copies (cp.async.bulk.shared::cluster.global + mbarrier complete_tx);
-//      the primary warp issues its action loads; the helper warp zeroes the tile's occupancy grids.
+//   1. prologue.  Before griddepcontrol.wait (so it overlaps the previous launch's tail under PDL): the CTA-shared static
+//      tables are read with plain loads, the helper warp zeroes the tile's occupancy grids, the mbarriers are initialised.
+//      After it: each tile's packed state (nw*128 B, contiguous in HBM) arrives through one TMA bulk copy
+//      (cp.async.bulk.shared::cluster.global + mbarrier complete_tx) and the primary warp issues its action loads.
 //   2. primary: lane e advances world e (rw_logic.cuh): grid build, proposals, collision resolution, apply,
 //      deliveries/resample, counters, optional auto-reset -- all on shared memory, no HBM traffic.  (Opt-in: the
 //      warp-cooperative form of rw_coop.cuh, a group of lanes per world on both warps.)
