@@ -88,6 +88,7 @@ struct RwParams {
     float *peer_rew[RW_MAX_PEERS];
     uint8_t *peer_done[RW_MAX_PEERS];
     int32_t coop, gshift;  // cooperative step: a group of 1 << gshift lanes per world (rw_coop.cuh); 0 = one lane per world
+    int32_t pair;          // agent-split step (rw_logic.cuh, rw_pair_*): both warps of a pair step the tile, half of the agents each
     int32_t obs_parts;     // lanes per agent row in the observation gather (1 or 2)
     int32_t obs_tma;       // 1: observation chunks leave through cp.async.bulk, 0: 16-byte st.global from all lanes
     int32_t grid_env_stride;  // bytes per world of the occupancy grid: one byte per cell (see RW_G_*)
@@ -140,6 +141,7 @@ struct RwDynamic {
     static constexpr bool is_static = false;
     static constexpr bool full_static = false;
     static constexpr int static_n = 0;
+    static constexpr int static_mb = 0;
     RW_HD static int n(const RwParams &p) { return p.n; }
     RW_HD static int R(const RwParams &p) { return p.R; }
     RW_HD static int H(const RwParams &p) { return p.H; }
@@ -155,6 +157,7 @@ struct RwStatic {
     static constexpr bool is_static = true;
     static constexpr bool full_static = (N_ > 0 && RQ_ >= 0);
     static constexpr int static_n = N_;
+    static constexpr int static_mb = MB_;
     RW_HD static int n(const RwParams &p) { return N_ > 0 ? N_ : p.n; }
     RW_HD static int R(const RwParams &p) { return RQ_ >= 0 ? RQ_ : p.R; }
     RW_HD static int H(const RwParams &) { return H_; }

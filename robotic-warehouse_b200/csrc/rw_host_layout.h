@@ -168,6 +168,10 @@ static inline void rw_fill_params(RwParams &p, const rw_config &c, int64_t num_e
         p.coop = ev ? atoi(ev) : 0;  // measured (profiles/phase_timeline.py): one lane per world is ~2.5 us faster per launch
     }
     {
+        const char *ev = getenv("RWARE_B200_PAIR");
+        p.pair = ev ? atoi(ev) : 1;  // only the fully static kernels with an even agent count <= 8 carry it
+    }
+    {
         const char *ev = getenv("RWARE_B200_OBS_TMA");
         p.obs_tma = ev ? atoi(ev) : 1;  // measured: TMA bulk stores beat st.global.v4 copy-out (30 vs 38 us under ncu)
     }

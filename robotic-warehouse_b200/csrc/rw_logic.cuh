@@ -126,13 +126,14 @@ RW_HD bool rw_in_queue(const RwOff &o, const RwLane &l, int id) {
     return false;
 }
 
+// shelf bits of the state words [k_lo, k_hi) (two shelves per word; `tail`: also the odd last shelf)
 template <class C>
-RW_HD void rw_build_grid(const RwParams &p, const RwLane &l) {
+RW_HD void rw_grid_shelves(const RwParams &p, const RwLane &l, int k_lo, int k_hi, bool tail) {
     const RwOff o = rw_off<C>(p);
     const int S = C::S(p);
-    {   // two shelves per state word; batches of 8 words: all loads first, then the scattered byte stores
-        int k2 = 0;
-        for (; k2 + 8 <= (S >> 1); k2 += 8) {
+    {   // batches of 8 words: all loads first, then the scattered byte stores
+        int k2 = k_lo;
+        for (; k2 + 8 <= k_hi; k2 += 8) {
             uint32_t w[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) w[j] = (uint32_t)l.tile[(o.w_shelf + k2 + j) * RW_TILE];
@@ -142,13 +143,20 @@ RW_HD void rw_build_grid(const RwParams &p, const RwLane &l) {
                 l.g[w[j] >> 16] = (uint8_t)RW_G_SHELF;
             }
         }
-        for (; k2 < (S >> 1); k2++) {
-            uint32_t w = (uint32_t)l.tile[(o.w_shelf + k2) * RW_TILE];
+        const int rest = k_hi - k2;  // < 8
+        for (int j = 0; j < rest; j++) {
+            uint32_t w = (uint32_t)l.tile[(o.w_shelf + k2 + j) * RW_TILE];
             l.g[w & 0xffffu] = (uint8_t)RW_G_SHELF;
             l.g[w >> 16] = (uint8_t)RW_G_SHELF;
         }
     }
-    if (S & 1) l.g[(uint32_t)l.tile[(o.w_shelf + (S >> 1)) * RW_TILE] & 0xffffu] = (uint8_t)RW_G_SHELF;
+    if (tail && (S & 1)) l.g[(uint32_t)l.tile[(o.w_shelf + (S >> 1)) * RW_TILE] & 0xffffu] = (uint8_t)RW_G_SHELF;
+}
+
+// request bits and agent ids on top of the shelf bits
+template <class C>
+RW_HD void rw_grid_requests_agents(const RwParams &p, const RwLane &l) {
+    const RwOff o = rw_off<C>(p);
     const bool overlap = ((uint32_t)l.tile[o.w_inact * RW_TILE] & RW_OVERLAP_BIT) != 0;
     for (int q = 0; q < o.R; q++) {
         int id = rw_queue(o, l, q);
@@ -164,6 +172,12 @@ RW_HD void rw_build_grid(const RwParams &p, const RwLane &l) {
     }
 }
 
+template <class C>
+RW_HD void rw_build_grid(const RwParams &p, const RwLane &l) {
+    rw_grid_shelves<C>(p, l, 0, C::S(p) >> 1, true);
+    rw_grid_requests_agents<C>(p, l);
+}
+
 // literal _recalc_grid for worlds flagged with overlapping shelves; also refreshes the flag (O(S^2), cold)
 template <class C>
 RW_HD_NOINLINE void rw_rebuild_grid_slow(const RwParams &p, const RwLane l) {  // by value: `l` must not escape the caller
@@ -175,6 +189,8 @@ RW_HD_NOINLINE void rw_rebuild_grid_slow(const RwParams &p, const RwLane l) {  /
         int c = rw_shelf_cell(o, l, k);
         for (int j = 0; j < k; j++) overlap |= (rw_shelf_cell(o, l, j) == c);
     }
+    for (int i = 1; i < o.n && !overlap; i++)  // two agents on one cell (injected): same flag, same literal path
+        for (int j = 0; j < i; j++) overlap |= ((rw_agent(l, i) & 0xffffu) == (rw_agent(l, j) & 0xffffu));
     uint32_t w = (uint32_t)l.tile[o.w_inact * RW_TILE];
     l.tile[o.w_inact * RW_TILE] = (int32_t)((w & ~RW_OVERLAP_BIT) | (overlap ? RW_OVERLAP_BIT : 0u));
     rw_build_grid<C>(p, l);
@@ -798,6 +814,172 @@ RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, float *reward, int64
         reward[i] = 0.5f * (float)half;
     }
     return done;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Agent-split form of the step above for the fully static configurations with 2, 4, 6 or 8 agents and no message bits:
+// BOTH warps of a tile's pair run one lane per world and warp `part` owns the agents [part * N/2, (part + 1) * N/2), so the
+// per-agent work (proposals, apply) and the shelf marking of the grid halve on the critical path and the helper warp's issue
+// slots, idle during the one-warp step, are used.  The phases are separated by pair barriers in the kernel (the host twin runs
+// part 0 then part 1 of every phase, one valid interleaving); inside a phase the two parts touch disjoint words, bytes and
+// half-words: own agent words, own scratch entries, the start / target cells of own agents (agents stand on distinct cells and
+// committed targets are distinct).  The collision resolver and the deliveries stay with the primary.  Two words per world
+// (`xw[0]`: helper -> primary, `xw[RW_TILE]`: primary -> helper) carry the masks across.  Worlds flagged RW_OVERLAP_BIT
+// (injected degenerate states) never come here: the kernel steps them with the one-lane form.
+template <class C>
+struct RwPairRegs {
+    static constexpr int NH = C::static_n >= 2 ? C::static_n / 2 : 1;
+    uint32_t awv[NH], av[NH], sv[NH], tv[NH], lift[NH];
+    uint32_t stay, moved, rew;  // bit j / nibble j: own agent j
+};
+template <class C>
+RW_HD constexpr bool rw_pair_capable() {
+    return C::full_static && C::static_mb == 0 && C::static_n >= 2 && C::static_n <= 8 && (C::static_n & 1) == 0;
+}
+
+// phase 1 (both parts; needs no grid): own half of the shelf bits; own agents' words, actions and start / target cells
+template <class C>
+RW_HD void rw_pair_propose_a(const RwParams &p, const RwLane &l, int part, const int32_t *act, RwPairRegs<C> &r) {
+    constexpr int NH = RwPairRegs<C>::NH;
+    const int W = C::W(p), H = C::H(p), words = C::S(p) >> 1, half = (words + 1) >> 1, i0 = part * NH;
+    if (part == 0) rw_grid_shelves<C>(p, l, 0, half, false);
+    else rw_grid_shelves<C>(p, l, half, words, true);
+    uint32_t bad = 0;
+    r.stay = 0; r.moved = 0; r.rew = 0;
+#pragma unroll
+    for (int j = 0; j < NH; j++) {
+        r.awv[j] = rw_agent(l, i0 + j);
+        int a = act[j];
+        if ((unsigned)a > 4u) { a = RW_ACT_NOOP; bad++; }
+        r.av[j] = (uint32_t)a;
+    }
+#pragma unroll
+    for (int j = 0; j < NH; j++) {
+        int x = rw_ax(r.awv[j]), y = rw_ay(r.awv[j]), tx = x, ty = y;
+        if (r.av[j] == RW_ACT_FORWARD) {  // Agent.req_location ref:102-116, clamped at the walls
+            int d = rw_adir(r.awv[j]);
+            if (d == 0) ty = y > 0 ? y - 1 : 0;
+            else if (d == 1) ty = y < H - 1 ? y + 1 : H - 1;
+            else if (d == 2) tx = x > 0 ? x - 1 : 0;
+            else tx = x < W - 1 ? x + 1 : W - 1;
+        }
+        r.sv[j] = (uint32_t)(y * W + x);
+        r.tv[j] = (uint32_t)(ty * W + tx);
+    }
+    if (bad) {
+#if defined(__CUDA_ARCH__)
+        atomicAdd(p.err_count, (unsigned long long)bad);
+#else
+        *p.err_count += bad;
+#endif
+    }
+}
+
+// phase 3 (both parts; the grid is complete): classify own proposals (ref:825-846) into the scratch
+template <class C>
+RW_HD void rw_pair_propose_b(const RwParams &p, const RwLane &l, int part, RwPairRegs<C> &r) {
+    constexpr int NH = RwPairRegs<C>::NH;
+    const int i0 = part * NH;
+    uint32_t gtv[NH];
+#pragma unroll
+    for (int j = 0; j < NH; j++) gtv[j] = l.g[r.tv[j]];
+#pragma unroll
+    for (int j = 0; j < NH; j++) {
+        uint32_t nxt;
+        if (r.tv[j] == r.sv[j]) { nxt = RW_NXT_SELF; r.stay |= 1u << j; }
+        else {
+            uint32_t occ = gtv[j] & RW_G_AGENT;
+            // ref:829-844 a carrier may not enter a cell holding a shelf unless an agent there carries it
+            if (rw_acarry(r.awv[j]) && (gtv[j] & RW_G_SHELF) && !(occ && rw_acarry(rw_agent(l, (int)occ - 1)))) {
+                r.av[j] = RW_ACT_NOOP; r.tv[j] = r.sv[j]; nxt = RW_NXT_SELF; r.stay |= 1u << j;
+            } else {
+                nxt = occ ? occ - 1 : RW_NXT_SINK;
+            }
+        }
+        rw_st(l, i0 + j) = r.sv[j] | (r.tv[j] << 16);
+        rw_meta(l, i0 + j) = r.av[j] | (nxt << 3);
+    }
+}
+
+// phase 5 (both parts): first half of apply (ref:878-899) for own agents -- turns, load / unload, and the movers leave
+// their start cells.  `commit`: the resolver's mask over all agents.
+template <class C>
+RW_HD void rw_pair_apply_a(const RwParams &p, const RwLane &l, int part, uint32_t commit, RwPairRegs<C> &r) {
+    constexpr int NH = RwPairRegs<C>::NH;
+    const int i0 = part * NH;
+    uint32_t gsv[NH];
+#pragma unroll
+    for (int j = 0; j < NH; j++) gsv[j] = l.g[r.sv[j]];
+#pragma unroll
+    for (int j = 0; j < NH; j++) {
+        r.lift[j] = 0;
+        const uint32_t a = r.av[j];
+        if (a == RW_ACT_FORWARD) {
+            if (((commit >> (i0 + j)) & 1u) && r.tv[j] != r.sv[j]) {
+                r.moved |= 1u << j;
+                if (rw_acarry(r.awv[j])) { r.lift[j] = gsv[j] & (RW_G_SHELF | RW_G_REQ); l.g[r.sv[j]] = 0; }
+                else l.g[r.sv[j]] = (uint8_t)(gsv[j] & (RW_G_SHELF | RW_G_REQ));
+            }
+        } else if (a == RW_ACT_LEFT || a == RW_ACT_RIGHT) {  // Agent.req_direction ref:118-125
+            uint32_t d = (uint32_t)rw_adir(r.awv[j]);
+            uint32_t nd = ((a == RW_ACT_RIGHT ? 0x4Bu : 0x1Eu) >> (2 * d)) & 3u;
+            r.awv[j] = (r.awv[j] & ~(3u << 16)) | (nd << 16);
+            rw_set_agent(l, i0 + j, r.awv[j]);
+        } else if (a == RW_ACT_TOGGLE) {  // ref:889-899
+            if (!rw_acarry(r.awv[j])) {
+                if (gsv[j] & RW_G_SHELF) rw_set_agent(l, i0 + j, r.awv[j] | ((uint32_t)rw_shelf_at<C>(p, l, r.sv[j]) << 19));
+            } else if (!(l.highway[r.sv[j]] & 1)) {
+                if (rw_adeliv(r.awv[j]) && p.reward_type == 2) r.rew += 1u << (4 * j);
+                rw_set_agent(l, i0 + j, r.awv[j] & 0x3ffffu & ~(1u << 18));
+            }
+        }
+    }
+}
+
+// phase 6 (both parts; every mover has left its start cell): own movers arrive
+template <class C>
+RW_HD void rw_pair_apply_b(const RwParams &p, const RwLane &l, int part, const RwPairRegs<C> &r) {
+    constexpr int NH = RwPairRegs<C>::NH;
+    const RwOff o = rw_off<C>(p);
+    const int W = C::W(p), i0 = part * NH;
+    if (!r.moved) return;
+#pragma unroll
+    for (int j = 0; j < NH; j++) {
+        if (!((r.moved >> j) & 1u)) continue;
+        const uint32_t t = r.tv[j];
+        uint32_t ty = C::div_w(p, t), tx = t - ty * (uint32_t)W;
+        rw_set_agent(l, i0 + j, (r.awv[j] & ~0xffffu) | tx | (ty << 8));
+        int carry = rw_acarry(r.awv[j]);
+        if (carry) {
+            l.g[t] = (uint8_t)((uint32_t)(i0 + j + 1) | r.lift[j]);
+            rw_set_shelf_cell(o, l, carry - 1, (int)t);
+        } else {
+            l.g[t] = (uint8_t)((l.g[t] & (RW_G_SHELF | RW_G_REQ)) | (uint32_t)(i0 + j + 1));
+        }
+    }
+}
+
+// phase 7 (primary): deliveries, counters, rewards.  `rew_h`: the helper's reward nibbles.  Returns done.
+template <class C>
+RW_HD bool rw_pair_finish(const RwParams &p, const RwLane &l, const RwPairRegs<C> &r, uint32_t rew_h, float *reward, int64_t env) {
+    constexpr int NH = RwPairRegs<C>::NH, N = 2 * NH;
+    uint64_t rew_lo = (uint64_t)r.rew | ((uint64_t)rew_h << (4 * NH)), rew_hi = 0;
+    int rew_global = 0;
+    const bool done = rw_finish_lane<C>(p, l, env, rew_lo, rew_hi, rew_global);
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        uint32_t half = (uint32_t)((rew_lo >> (4 * i)) & 15ULL) + 2u * (uint32_t)rew_global;
+        reward[i] = 0.5f * (float)half;
+    }
+    return done;
+}
+
+// the one-lane step of a whole world out of line: worlds the agent-split form must not take (RW_OVERLAP_BIT), cold
+template <class C>
+RW_HD_NOINLINE bool rw_step_world_serial(const RwParams &p, const RwLane l, const int32_t *act, float *reward, int64_t env) {
+    rw_build_grid<C>(p, l);
+    rw_load_actions<C>(p, l, act);
+    return rw_step_lane<C>(p, l, reward, env);
 }
 
 // ------------------------------------------------------------------------------------------------

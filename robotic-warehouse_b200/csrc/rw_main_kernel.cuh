@@ -179,19 +179,29 @@ __global__ void __launch_bounds__(MAXT, 1) rw_main_kernel(const __grid_constant_
     //         while the primary's lanes issue their action loads.
     RwActRegs<C> areg;
     const bool pre = rw_can_prefetch_actions<C>(p);
-    if (role == 0) {
-        if (active && lane == 0) {
-            mbar_expect_tx(bar, tile_bytes);
-            bulk_g2s(tilew, gtile, tile_bytes, bar);
+    // agent-split step (rw_logic.cuh, rw_pair_*): both warps of the pair step the tile, each owning half of the agents
+    constexpr bool PAIRC = (MODE == RW_MODE_STEP) && rw_pair_capable<C>();
+    constexpr int NHP = RwPairRegs<C>::NH;
+    constexpr bool pair = PAIRC;  // (the fully static classes have no message bits: rw_inst.cu)
+    int32_t pact[NHP];
+    if (role == 0 && active && lane == 0) {
+        mbar_expect_tx(bar, tile_bytes);
+        bulk_g2s(tilew, gtile, tile_bytes, bar);
+    }
+    if constexpr (pair) {
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < NHP; j++) pact[j] = actions[env * p.n + role * NHP + j];  // in flight, consumed in the step
         }
-        if (MODE == RW_MODE_STEP && !coop && valid) {
-            if (pre) rw_prefetch_actions<C>(p, actions + env * p.n * p.A, areg);  // loads in flight, consumed below
-            else rw_load_actions<C>(p, l, actions + env * p.n * p.A);
-        }
+    } else if (role == 0 && MODE == RW_MODE_STEP && !coop && valid) {
+        if (pre) rw_prefetch_actions<C>(p, actions + env * p.n * p.A, areg);  // loads in flight, consumed below
+        else rw_load_actions<C>(p, l, actions + env * p.n * p.A);
     }
     __syncthreads();  // static tables, mbarrier inits and the zeroed grids are visible CTA-wide
     if (!active) return;
-    if (role == 0 && MODE == RW_MODE_STEP && !coop && valid && pre) rw_commit_actions<C>(p, l, areg);
+    if constexpr (!pair) {
+        if (role == 0 && MODE == RW_MODE_STEP && !coop && valid && pre) rw_commit_actions<C>(p, l, areg);
+    }
     RW_STAMP(1);
 
     // Observation staging of this warp: chunk of CH worlds starting at world c0 of the tile -> its slice of the caller's
@@ -304,6 +314,57 @@ __global__ void __launch_bounds__(MAXT, 1) rw_main_kernel(const __grid_constant_
         RW_STAMP(3);
         pair_barrier(1 + tl);  // every world of the tile is in its post-step state
         RW_STAMP(4);
+    } else if constexpr (pair) {
+        {
+            // both warps: lane e advances world e, warp `role` owning the agents [role * N/2, (role + 1) * N/2); the pair
+            // barriers separate the phases (see rw_logic.cuh).  Worlds flagged RW_OVERLAP_BIT -- and every world when the
+            // form is switched off (RWARE_B200_PAIR=0) -- are stepped by the primary alone with the one-lane form, out of line.
+            mbar_wait(bar, 0);
+            RW_STAMP(2);
+            uint32_t *xw = reinterpret_cast<uint32_t *>(wb + p.sm_tie) + lane;  // [0]: helper -> primary, [RW_TILE]: primary -> helper
+            const bool go = valid && p.pair && !((uint32_t)l.tile[rw_off<C>(p).w_inact * RW_TILE] & RW_OVERLAP_BIT);
+            RwPairRegs<C> r;
+            uint32_t commit = 0;
+            if (go) rw_pair_propose_a<C>(p, l, role, pact, r);
+            pair_barrier(1 + tl);  // shelf bits complete
+            if (go && role == 0) rw_grid_requests_agents<C>(p, l);
+            pair_barrier(1 + tl);  // grid complete
+            if (go) {
+                rw_pair_propose_b<C>(p, l, role, r);
+                if (role == 1) xw[0] = r.stay;
+            }
+            pair_barrier(1 + tl);  // every proposal is in the scratch
+            if (go && role == 0) {
+                commit = rw_resolve_lane<C>(p, l, r.stay | (xw[0] << NHP));
+                xw[RW_TILE] = commit;
+            }
+            pair_barrier(1 + tl);  // the resolver's mask is out
+            if (go) {
+                if (role == 1) commit = xw[RW_TILE];
+                rw_pair_apply_a<C>(p, l, role, commit, r);
+            }
+            pair_barrier(1 + tl);  // every mover has left its start cell
+            if (go) {
+                rw_pair_apply_b<C>(p, l, role, r);
+                if (role == 1) xw[0] = r.rew;
+            }
+            pair_barrier(1 + tl);  // moves applied
+            if (role == 0) {
+                if (valid) {
+                    const bool d = go ? rw_pair_finish<C>(p, l, r, xw[0], reward + env * p.n, env)
+                                      : rw_step_world_serial<C>(p, l, actions + env * p.n * p.A, reward + env * p.n, env);
+                    done[env] = d ? 1 : 0;
+                    if (d && p.auto_reset) {
+                        rw_reset_lane<C>(p, l, env);
+                        uint32_t *gz = reinterpret_cast<uint32_t *>(l.g);
+                        for (int i = 0; i < (p.grid_env_stride >> 2); i++) gz[i] = 0;
+                        rw_build_grid<C>(p, l);
+                    }
+                }
+                __syncwarp();
+            }
+            RW_STAMP(3);
+        }
     } else if (role == 0) {
         // primary: lane e advances world e
         mbar_wait(bar, 0);

@@ -41,12 +41,14 @@ RW_HD bool rw_set_state_world(const RwParams &p, const rw_state_view &v, int64_t
         for (int q = 0; q < p.R; q++) rw_set_queue(o, l, q, rw_clamp_flag(v.queue[env * p.R + q], 0, p.S, bad));
     if (v.cur_steps) t[p.w_steps * RW_TILE] = v.cur_steps[env];
     if (v.cur_inactive) t[p.w_inact * RW_TILE] = v.cur_inactive[env] & 0x7fffffff;
-    // flag worlds where two shelves share a cell (cold path, O(S^2)); see RW_OVERLAP_BIT
+    // flag worlds where two shelves (or two agents) share a cell (cold path, O(S^2)); see RW_OVERLAP_BIT
     bool overlap = false;
     for (int k = 1; k < p.S && !overlap; k++) {
         int c = rw_shelf_cell(o, l, k);
         for (int j = 0; j < k; j++) overlap |= (rw_shelf_cell(o, l, j) == c);
     }
+    for (int i = 1; i < p.n && !overlap; i++)  // two agents on one cell take the same literal path
+        for (int j = 0; j < i; j++) overlap |= ((rw_agent(l, i) & 0xffffu) == (rw_agent(l, j) & 0xffffu));
     uint32_t wi = (uint32_t)t[p.w_inact * RW_TILE] & ~RW_OVERLAP_BIT;
     t[p.w_inact * RW_TILE] = (int32_t)(wi | (overlap ? RW_OVERLAP_BIT : 0u));
     if (v.rng)

@@ -38,6 +38,9 @@ def _load():
         L.sim_run.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, vp]
         L.sim_force_dynamic.argtypes = [ctypes.c_int]
         L.sim_set_coop.argtypes = [vp, ctypes.c_int]
+        L.sim_set_pair.argtypes = [vp, ctypes.c_int]
+        L.sim_pair_steps.argtypes = [vp]
+        L.sim_pair_steps.restype = ctypes.c_longlong
         L.sim_get_state.argtypes = [vp, ctypes.POINTER(RwStateView)]
         L.sim_set_state.argtypes = [vp, ctypes.POINTER(RwStateView)]
         L.sim_global_image.argtypes = [vp, vp, ctypes.c_int, vp, vp]
@@ -105,6 +108,13 @@ class HostSimBackend:
 
     def error_count(self):
         return int(self.lib.sim_error_count(self._h))
+
+    def pair_steps(self):
+        """World-steps taken through the agent-split form of the step (rw_logic.cuh, rw_pair_*)."""
+        return int(self.lib.sim_pair_steps(self._h))
+
+    def set_pair(self, on):
+        self.lib.sim_set_pair(self._h, int(bool(on)))
 
     def global_image_shape(self, n_layers, pad_to_shape=None):
         H, W = self.cfg.grid_size

@@ -25,6 +25,7 @@ struct Sim {
     std::vector<int32_t> state;
     std::vector<uint32_t> rng;
     unsigned long long err = 0;
+    long long pair_steps = 0;
     // one warp's shared memory
     std::vector<uint8_t> smem;
 };
@@ -81,6 +82,8 @@ int sim_n_shelves(Sim *s) { return s->p.S; }
 void sim_set_auto_reset(Sim *s, int on) { s->p.auto_reset = on; }
 void sim_set_coop(Sim *s, int on) { s->p.coop = on; }
 long long sim_error_count(Sim *s) { return (long long)s->err; }
+long long sim_pair_steps(Sim *s) { return s->pair_steps; }  // world-steps taken through the agent-split form
+void sim_set_pair(Sim *s, int on) { s->p.pair = on; }
 
 void sim_seed(Sim *s, const uint64_t *seeds, const uint8_t *mask) {
     uint32_t w[RW_RNG_WORDS];
@@ -118,10 +121,40 @@ static void sim_run_t(Sim *s, int mode, const int32_t *actions, float *obs, floa
             if (env >= p.E) continue;
             RwLane l = lane_view(s, lane);
             if (mode == 2 && (!mask || mask[env])) rw_reset_lane<C>(p, l, env);
-            rw_build_grid<C>(p, l);
+            bool pair_done = false, d_pair = false;
+            if constexpr (rw_pair_capable<C>()) {
+                // the kernel's agent-split step: the phases in the kernel's order, part 0 then part 1 inside each phase
+                if (mode == 0) {
+                    uint32_t *xw = reinterpret_cast<uint32_t *>(wb + p.sm_tie) + lane;
+                    constexpr int NH = RwPairRegs<C>::NH;
+                    const int32_t *act = actions + env * p.n;
+                    if (p.pair && !((uint32_t)l.tile[rw_off<C>(p).w_inact * RW_TILE] & RW_OVERLAP_BIT)) {
+                        RwPairRegs<C> r[2];
+                        for (int part = 0; part < 2; part++) rw_pair_propose_a<C>(p, l, part, act + part * NH, r[part]);
+                        rw_grid_requests_agents<C>(p, l);
+                        for (int part = 0; part < 2; part++) rw_pair_propose_b<C>(p, l, part, r[part]);
+                        xw[0] = r[1].stay;
+                        uint32_t commit = rw_resolve_lane<C>(p, l, r[0].stay | (xw[0] << NH));
+                        xw[RW_TILE] = commit;
+                        for (int part = 0; part < 2; part++) rw_pair_apply_a<C>(p, l, part, part ? xw[RW_TILE] : commit, r[part]);
+                        for (int part = 0; part < 2; part++) rw_pair_apply_b<C>(p, l, part, r[part]);
+                        xw[0] = r[1].rew;
+                        d_pair = rw_pair_finish<C>(p, l, r[0], xw[0], reward + env * p.n, env);
+                        s->pair_steps++;
+                    } else {
+                        d_pair = rw_step_world_serial<C>(p, l, act, reward + env * p.n, env);
+                    }
+                    pair_done = true;
+                }
+            }
+            if (!pair_done) rw_build_grid<C>(p, l);
             if (mode == 0) {
-                rw_load_actions<C>(p, l, actions + env * p.n * p.A);
-                bool d = rw_step_lane<C>(p, l, reward + env * p.n, env);
+                bool d;
+                if (pair_done) d = d_pair;
+                else {
+                    rw_load_actions<C>(p, l, actions + env * p.n * p.A);
+                    d = rw_step_lane<C>(p, l, reward + env * p.n, env);
+                }
                 done[env] = d;
                 if (d && p.auto_reset) {
                     rw_reset_lane<C>(p, l, env);

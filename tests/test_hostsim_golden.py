@@ -46,3 +46,30 @@ def test_warp_cooperative_step_matches_too(name, backend, coop, monkeypatch):
     fx = replay.load_fixture(name)
     drv = replay.VecDriver(fx, backend_factory(backend), num_envs=35)
     assert replay.replay(drv, fx, max_steps=500) == 500
+
+
+# the fully static configurations with an even agent count <= 8 step through the agent-split form by default
+# (rw_logic.cuh, rw_pair_*: both warps of a tile's pair, half of the agents each)
+PAIR_FIXTURES = ["tiny2_indiv", "tiny4_indiv", "small4_global", "medium8_hard_twostage"]
+
+
+@pytest.mark.parametrize("backend", backend_params())
+@pytest.mark.parametrize("name", PAIR_FIXTURES)
+def test_one_lane_step_matches_too(name, backend, monkeypatch):
+    """RWARE_B200_PAIR=0 keeps the one-warp form of the step for those configurations; it must replay the reference too."""
+    monkeypatch.setenv("RWARE_B200_PAIR", "0")
+    fx = replay.load_fixture(name)
+    drv = replay.VecDriver(fx, backend_factory(backend), num_envs=35)
+    assert replay.replay(drv, fx) == len(fx["actions"])
+    if backend == "hostsim":
+        assert drv.vec.backend.pair_steps() == 0
+
+
+@pytest.mark.parametrize("name", PAIR_FIXTURES)
+def test_twin_takes_the_agent_split_step_by_default(name):
+    """Guards the test above and the golden replays against silently testing one form only."""
+    fx = replay.load_fixture(name)
+    drv = replay.VecDriver(fx, backend_factory("hostsim"), num_envs=33)
+    assert replay.replay(drv, fx, max_steps=50) == 50
+    # (the fixtures inject a few degenerate states -- overlapping shelves -- which are stepped by the one-lane form)
+    assert 0.9 * 33 * 50 <= drv.vec.backend.pair_steps() <= 33 * 50
