@@ -817,7 +817,7 @@ RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, float *reward, int64
 }
 
 // ------------------------------------------------------------------------------------------------
-// Agent-split form of the step above for the fully static configurations with 2, 4, 6 or 8 agents and no message bits:
+// Agent-split form of the step above for the fully static configurations with an even agent count <= 16 and no message bits:
 // BOTH warps of a tile's pair run one lane per world and warp `part` owns the agents [part * N/2, (part + 1) * N/2), so the
 // per-agent work (proposals, apply) and the shelf marking of the grid halve on the critical path and the helper warp's issue
 // slots, idle during the one-warp step, are used.  The phases are separated by pair barriers in the kernel (the host twin runs
@@ -829,12 +829,14 @@ RW_HD bool rw_step_lane(const RwParams &p, const RwLane &l, float *reward, int64
 template <class C>
 struct RwPairRegs {
     static constexpr int NH = C::static_n >= 2 ? C::static_n / 2 : 1;
-    uint32_t awv[NH], av[NH], sv[NH], tv[NH], lift[NH];
+    uint32_t awv[NH];  // agent word
+    uint32_t av[NH];   // action (bits 0-2) | lifted shelf / request bits of a moving carrier << 8
+    uint32_t st[NH];   // start cell | target cell << 16
     uint32_t stay, moved, rew;  // bit j / nibble j: own agent j
 };
 template <class C>
 RW_HD constexpr bool rw_pair_capable() {
-    return C::full_static && C::static_mb == 0 && C::static_n >= 2 && C::static_n <= 8 && (C::static_n & 1) == 0;
+    return C::full_static && C::static_mb == 0 && C::static_n >= 2 && C::static_n <= 16 && (C::static_n & 1) == 0;
 }
 
 // phase 1 (both parts; needs no grid): own half of the shelf bits; own agents' words, actions and start / target cells
@@ -863,8 +865,7 @@ RW_HD void rw_pair_propose_a(const RwParams &p, const RwLane &l, int part, const
             else if (d == 2) tx = x > 0 ? x - 1 : 0;
             else tx = x < W - 1 ? x + 1 : W - 1;
         }
-        r.sv[j] = (uint32_t)(y * W + x);
-        r.tv[j] = (uint32_t)(ty * W + tx);
+        r.st[j] = (uint32_t)(y * W + x) | ((uint32_t)(ty * W + tx) << 16);
     }
     if (bad) {
 #if defined(__CUDA_ARCH__)
@@ -882,21 +883,22 @@ RW_HD void rw_pair_propose_b(const RwParams &p, const RwLane &l, int part, RwPai
     const int i0 = part * NH;
     uint32_t gtv[NH];
 #pragma unroll
-    for (int j = 0; j < NH; j++) gtv[j] = l.g[r.tv[j]];
+    for (int j = 0; j < NH; j++) gtv[j] = l.g[r.st[j] >> 16];
 #pragma unroll
     for (int j = 0; j < NH; j++) {
+        const uint32_t s = r.st[j] & 0xffffu;
         uint32_t nxt;
-        if (r.tv[j] == r.sv[j]) { nxt = RW_NXT_SELF; r.stay |= 1u << j; }
+        if ((r.st[j] >> 16) == s) { nxt = RW_NXT_SELF; r.stay |= 1u << j; }
         else {
             uint32_t occ = gtv[j] & RW_G_AGENT;
             // ref:829-844 a carrier may not enter a cell holding a shelf unless an agent there carries it
             if (rw_acarry(r.awv[j]) && (gtv[j] & RW_G_SHELF) && !(occ && rw_acarry(rw_agent(l, (int)occ - 1)))) {
-                r.av[j] = RW_ACT_NOOP; r.tv[j] = r.sv[j]; nxt = RW_NXT_SELF; r.stay |= 1u << j;
+                r.av[j] = RW_ACT_NOOP; r.st[j] = s | (s << 16); nxt = RW_NXT_SELF; r.stay |= 1u << j;
             } else {
                 nxt = occ ? occ - 1 : RW_NXT_SINK;
             }
         }
-        rw_st(l, i0 + j) = r.sv[j] | (r.tv[j] << 16);
+        rw_st(l, i0 + j) = r.st[j];
         rw_meta(l, i0 + j) = r.av[j] | (nxt << 3);
     }
 }
@@ -909,16 +911,15 @@ RW_HD void rw_pair_apply_a(const RwParams &p, const RwLane &l, int part, uint32_
     const int i0 = part * NH;
     uint32_t gsv[NH];
 #pragma unroll
-    for (int j = 0; j < NH; j++) gsv[j] = l.g[r.sv[j]];
+    for (int j = 0; j < NH; j++) gsv[j] = l.g[r.st[j] & 0xffffu];
 #pragma unroll
     for (int j = 0; j < NH; j++) {
-        r.lift[j] = 0;
-        const uint32_t a = r.av[j];
+        const uint32_t a = r.av[j], s = r.st[j] & 0xffffu;
         if (a == RW_ACT_FORWARD) {
-            if (((commit >> (i0 + j)) & 1u) && r.tv[j] != r.sv[j]) {
+            if (((commit >> (i0 + j)) & 1u) && (r.st[j] >> 16) != s) {
                 r.moved |= 1u << j;
-                if (rw_acarry(r.awv[j])) { r.lift[j] = gsv[j] & (RW_G_SHELF | RW_G_REQ); l.g[r.sv[j]] = 0; }
-                else l.g[r.sv[j]] = (uint8_t)(gsv[j] & (RW_G_SHELF | RW_G_REQ));
+                if (rw_acarry(r.awv[j])) { r.av[j] = a | ((gsv[j] & (RW_G_SHELF | RW_G_REQ)) << 8); l.g[s] = 0; }
+                else l.g[s] = (uint8_t)(gsv[j] & (RW_G_SHELF | RW_G_REQ));
             }
         } else if (a == RW_ACT_LEFT || a == RW_ACT_RIGHT) {  // Agent.req_direction ref:118-125
             uint32_t d = (uint32_t)rw_adir(r.awv[j]);
@@ -927,8 +928,8 @@ RW_HD void rw_pair_apply_a(const RwParams &p, const RwLane &l, int part, uint32_
             rw_set_agent(l, i0 + j, r.awv[j]);
         } else if (a == RW_ACT_TOGGLE) {  // ref:889-899
             if (!rw_acarry(r.awv[j])) {
-                if (gsv[j] & RW_G_SHELF) rw_set_agent(l, i0 + j, r.awv[j] | ((uint32_t)rw_shelf_at<C>(p, l, r.sv[j]) << 19));
-            } else if (!(l.highway[r.sv[j]] & 1)) {
+                if (gsv[j] & RW_G_SHELF) rw_set_agent(l, i0 + j, r.awv[j] | ((uint32_t)rw_shelf_at<C>(p, l, s) << 19));
+            } else if (!(l.highway[s] & 1)) {
                 if (rw_adeliv(r.awv[j]) && p.reward_type == 2) r.rew += 1u << (4 * j);
                 rw_set_agent(l, i0 + j, r.awv[j] & 0x3ffffu & ~(1u << 18));
             }
@@ -946,12 +947,12 @@ RW_HD void rw_pair_apply_b(const RwParams &p, const RwLane &l, int part, const R
 #pragma unroll
     for (int j = 0; j < NH; j++) {
         if (!((r.moved >> j) & 1u)) continue;
-        const uint32_t t = r.tv[j];
+        const uint32_t t = r.st[j] >> 16;
         uint32_t ty = C::div_w(p, t), tx = t - ty * (uint32_t)W;
         rw_set_agent(l, i0 + j, (r.awv[j] & ~0xffffu) | tx | (ty << 8));
         int carry = rw_acarry(r.awv[j]);
         if (carry) {
-            l.g[t] = (uint8_t)((uint32_t)(i0 + j + 1) | r.lift[j]);
+            l.g[t] = (uint8_t)((uint32_t)(i0 + j + 1) | (r.av[j] >> 8));
             rw_set_shelf_cell(o, l, carry - 1, (int)t);
         } else {
             l.g[t] = (uint8_t)((l.g[t] & (RW_G_SHELF | RW_G_REQ)) | (uint32_t)(i0 + j + 1));
