@@ -48,9 +48,9 @@ def test_warp_cooperative_step_matches_too(name, backend, coop, monkeypatch):
     assert replay.replay(drv, fx, max_steps=500) == 500
 
 
-# the fully static configurations with an even agent count <= 16 step through the agent-split form by default
+# the fully static configurations with an even agent count <= 8 step through the agent-split form by default
 # (rw_logic.cuh, rw_pair_*: both warps of a tile's pair, half of the agents each)
-PAIR_FIXTURES = ["tiny2_indiv", "tiny4_indiv", "small4_global", "medium8_hard_twostage", "large16_r2"]
+PAIR_FIXTURES = ["tiny2_indiv", "tiny4_indiv", "small4_global", "medium8_hard_twostage"]
 
 
 @pytest.mark.parametrize("backend", backend_params())
