@@ -567,20 +567,6 @@ RW_HD uint32_t rw_resolve_lane(const RwParams &p, const RwLane &l, uint32_t comm
     // ---- resolve (ref:848-876 restated agent-centrically)
     uint32_t movers = ~commit & (n == 32 ? 0xffffffffu : ((1u << n) - 1u));
     if (movers) {
-        {   // The common case under random actions, settled without the machinery below: every mover heads for a cell no agent
-            // stands on and no two movers head for the same cell -> each is the only candidate of its sink cell and nobody steps
-            // onto a mover's own cell (heights 0): all of them move.  Lanes that leave here also shorten the loops below for the
-            // rest of the warp (trip counts are the maximum over the lanes still in them).
-            bool simple = true;
-            for (uint32_t b = movers; b; b &= b - 1) {
-                const int i = rw_ffs32(b);
-                if (rw_m_nxt(rw_meta(l, i)) != RW_NXT_SINK) { simple = false; break; }
-                const uint32_t t = rw_st(l, i) >> 16;
-                for (uint32_t b2 = b & (b - 1); b2; b2 &= b2 - 1)
-                    if ((rw_st(l, rw_ffs32(b2)) >> 16) == t) simple = false;
-            }
-            if (simple) return commit | movers;
-        }
         for (uint32_t b = movers; b; b &= b - 1) {
             int i = rw_ffs32(b);
             uint32_t j = rw_m_nxt(rw_meta(l, i));
@@ -854,21 +840,13 @@ RW_HD constexpr bool rw_pair_capable() {
     return C::full_static && C::static_mb == 0 && C::static_n >= 2 && C::static_n <= 8 && (C::static_n & 1) == 0;
 }
 
-// phase 1 (both parts; needs no grid): own half of the shelf and request bits; own agents' words, actions and start / target cells
+// phase 1 (both parts; needs no grid): own half of the shelf bits; own agents' words, actions and start / target cells
 template <class C>
 RW_HD void rw_pair_propose_a(const RwParams &p, const RwLane &l, int part, const int32_t *act, RwPairRegs<C> &r) {
     constexpr int NH = RwPairRegs<C>::NH;
     const int W = C::W(p), H = C::H(p), words = C::S(p) >> 1, half = (words + 1) >> 1, i0 = part * NH;
     if (part == 0) rw_grid_shelves<C>(p, l, 0, half, false);
     else rw_grid_shelves<C>(p, l, half, words, true);
-    {   // request bits of the requested shelves of the own half (their cells were written just above, by this lane)
-        const RwOff o = rw_off<C>(p);
-        const int id_lo = part == 0 ? 1 : 2 * half + 1, id_hi = part == 0 ? 2 * half : C::S(p);
-        for (int q = 0; q < o.R; q++) {
-            const int id = rw_queue(o, l, q);
-            if (id >= id_lo && id <= id_hi) l.g[rw_shelf_cell(o, l, id - 1)] |= (uint8_t)RW_G_REQ;
-        }
-    }
     uint32_t bad = 0;
     r.stay = 0; r.moved = 0; r.rew = 0;
 #pragma unroll
@@ -896,17 +874,6 @@ RW_HD void rw_pair_propose_a(const RwParams &p, const RwLane &l, int part, const
 #else
         *p.err_count += bad;
 #endif
-    }
-}
-
-// phase 2 (both parts; shelf and request bits are complete): the ids of the own agents go onto their cells
-template <class C>
-RW_HD void rw_pair_mark_agents(const RwParams &, const RwLane &l, int part, const RwPairRegs<C> &r) {
-    constexpr int NH = RwPairRegs<C>::NH;
-#pragma unroll
-    for (int j = 0; j < NH; j++) {
-        const uint32_t c = r.st[j] & 0xffffu;
-        l.g[c] = (uint8_t)((l.g[c] & (RW_G_SHELF | RW_G_REQ)) | (uint32_t)(part * NH + j + 1));
     }
 }
 

@@ -326,8 +326,8 @@ __global__ void __launch_bounds__(MAXT, 1) rw_main_kernel(const __grid_constant_
             RwPairRegs<C> r;
             uint32_t commit = 0;
             if (go) rw_pair_propose_a<C>(p, l, role, pact, r);
-            pair_barrier(1 + tl);  // shelf and request bits complete
-            if (go) rw_pair_mark_agents<C>(p, l, role, r);
+            pair_barrier(1 + tl);  // shelf bits complete
+            if (go && role == 0) rw_grid_requests_agents<C>(p, l);
             pair_barrier(1 + tl);  // grid complete
             if (go) {
                 rw_pair_propose_b<C>(p, l, role, r);

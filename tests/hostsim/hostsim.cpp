@@ -131,7 +131,7 @@ static void sim_run_t(Sim *s, int mode, const int32_t *actions, float *obs, floa
                     if (p.pair && !((uint32_t)l.tile[rw_off<C>(p).w_inact * RW_TILE] & RW_OVERLAP_BIT)) {
                         RwPairRegs<C> r[2];
                         for (int part = 0; part < 2; part++) rw_pair_propose_a<C>(p, l, part, act + part * NH, r[part]);
-                        for (int part = 0; part < 2; part++) rw_pair_mark_agents<C>(p, l, part, r[part]);
+                        rw_grid_requests_agents<C>(p, l);
                         for (int part = 0; part < 2; part++) rw_pair_propose_b<C>(p, l, part, r[part]);
                         xw[0] = r[1].stay;
                         uint32_t commit = rw_resolve_lane<C>(p, l, r[0].stay | (xw[0] << NH));
