@@ -130,14 +130,16 @@ static void sim_run_t(Sim *s, int mode, const int32_t *actions, float *obs, floa
                     const int32_t *act = actions + env * p.n;
                     if (p.pair && !((uint32_t)l.tile[rw_off<C>(p).w_inact * RW_TILE] & RW_OVERLAP_BIT)) {
                         RwPairRegs<C> r[2];
-                        for (int part = 0; part < 2; part++) rw_pair_propose_a<C>(p, l, part, act + part * NH, r[part]);
+                        // inside a phase the two parts are independent: p.pair == 2 runs them in the opposite order (tests)
+                        const int rev = p.pair == 2 ? 1 : 0;
+                        for (int k = 0; k < 2; k++) { const int part = k ^ rev; rw_pair_propose_a<C>(p, l, part, act + part * NH, r[part]); }
                         rw_grid_requests_agents<C>(p, l);
-                        for (int part = 0; part < 2; part++) rw_pair_propose_b<C>(p, l, part, r[part]);
+                        for (int k = 0; k < 2; k++) { const int part = k ^ rev; rw_pair_propose_b<C>(p, l, part, r[part]); }
                         xw[0] = r[1].stay;
                         uint32_t commit = rw_resolve_lane<C>(p, l, r[0].stay | (xw[0] << NH));
                         xw[RW_TILE] = commit;
-                        for (int part = 0; part < 2; part++) rw_pair_apply_a<C>(p, l, part, part ? xw[RW_TILE] : commit, r[part]);
-                        for (int part = 0; part < 2; part++) rw_pair_apply_b<C>(p, l, part, r[part]);
+                        for (int k = 0; k < 2; k++) { const int part = k ^ rev; rw_pair_apply_a<C>(p, l, part, part ? xw[RW_TILE] : commit, r[part]); }
+                        for (int k = 0; k < 2; k++) { const int part = k ^ rev; rw_pair_apply_b<C>(p, l, part, r[part]); }
                         xw[0] = r[1].rew;
                         d_pair = rw_pair_finish<C>(p, l, r[0], xw[0], reward + env * p.n, env);
                         s->pair_steps++;

@@ -73,3 +73,46 @@ def test_twin_takes_the_agent_split_step_by_default(name):
     assert replay.replay(drv, fx, max_steps=50) == 50
     # (the fixtures inject a few degenerate states -- overlapping shelves -- which are stepped by the one-lane form)
     assert 0.9 * 33 * 50 <= drv.vec.backend.pair_steps() <= 33 * 50
+
+
+@pytest.mark.parametrize("name", PAIR_FIXTURES)
+def test_agent_split_phases_do_not_depend_on_the_order_of_the_two_parts(name, monkeypatch):
+    """On the GPU the two warps of a pair run a phase concurrently.  The twin runs part 0 then part 1; RWARE_B200_PAIR=2 makes it
+    run part 1 first.  Inside a phase the parts touch disjoint data, so the trajectory must be the reference's either way."""
+    monkeypatch.setenv("RWARE_B200_PAIR", "2")
+    fx = replay.load_fixture(name)
+    drv = replay.VecDriver(fx, backend_factory("hostsim"), num_envs=33)
+    assert replay.replay(drv, fx) == len(fx["actions"])
+    assert drv.vec.backend.pair_steps() > 0
+
+
+@pytest.mark.parametrize("backend", backend_params())
+def test_worlds_with_two_agents_on_one_cell_take_the_one_lane_step(backend, monkeypatch):
+    """An injected state with two agents on one cell is flagged like overlapping shelves and stepped by the one-lane form, so the
+    agent-split step never sees two parts writing one cell; both forms must then agree world by world."""
+    import numpy as np
+    import torch
+    import rware_b200
+    outs = []
+    for pair in ("1", "0"):
+        monkeypatch.setenv("RWARE_B200_PAIR", pair)
+        vec = rware_b200.make_vec("rware-tiny-4ag-v1", 64, _backend_factory=backend_factory(backend))
+        vec.reset(seed=3)
+        st = vec.get_state()
+        ax, ay = st["agent_x"].clone(), st["agent_y"].clone()
+        ax[::2, 3], ay[::2, 3] = ax[::2, 0], ay[::2, 0]   # every second world: agent 3 onto agent 0's cell
+        vec.set_state(agent_x=ax, agent_y=ay)
+        before = vec.backend.pair_steps() if backend == "hostsim" else None
+        rs = np.random.default_rng(5)
+        traj = []
+        for t in range(6):
+            a = torch.from_numpy(rs.integers(0, 5, size=(64, 4, 1)).astype(np.int32)).to(vec.device)
+            o, r, d = vec.step(a)
+            traj.append((o.cpu().clone(), r.cpu().clone(), d.cpu().clone()))
+            if backend == "hostsim" and pair == "1" and t == 0:
+                # the flagged half does not take the agent-split step (the flag goes away once the two agents have parted)
+                assert vec.backend.pair_steps() - before == 32
+        outs.append(traj)
+        vec.close()
+    for (o1, r1, d1), (o0, r0, d0) in zip(*outs):
+        assert torch.equal(o1, o0) and torch.equal(r1, r0) and torch.equal(d1, d0)
